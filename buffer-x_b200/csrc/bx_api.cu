@@ -1,0 +1,25 @@
+// bx_api.cu -- library-level entry points (error string, version, device probe).
+#include <stdarg.h>
+#include <string.h>
+
+#include "bx_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void bx_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+BX_API const char *bx_last_error(void) { return g_err; }
+
+BX_API int bx_version(void) { return 100; }
+
+BX_API int bx_device_sm_count(void) {
+    int dev = 0, n = 0;
+    BX_CUDA(cudaGetDevice(&dev));
+    BX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    return n;
+}

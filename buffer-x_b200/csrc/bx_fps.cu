@@ -1,0 +1,206 @@
+// bx_fps.cu -- a1: farthest point sampling, one thread-block cluster per cloud.
+//
+// Replaces pointnet2_ops.furthest_point_sample (+gather_operation) as called at
+// /root/reference/models/BUFFERX.py:286-290 and :338-346.  The upstream kernel runs ONE CTA per
+// cloud and re-reads the cloud and a global `temp` array every iteration with ~10 barriers per
+// step.  Here the cloud (x,y,z and the running min-distance) lives in REGISTERS spread over a
+// cluster of up to 16 CTAs; an iteration is: register scan -> warp redux -> one __syncthreads ->
+// warp redux -> DSMEM all-to-all of one 20-byte candidate per CTA -> one cluster barrier.
+// The candidate carries the winner's coordinates, so no thread touches global memory in the loop.
+//
+// Result contract (bit-exact with oracle/c/bx_oracle.c::bxo_fps): idx[0] = 0; candidates with
+// |p|^2 <= 1e-3 (double compare) never win; ties are broken like the upstream 512-thread block
+// reduction: maximise (value, -(k mod bs), -k) with bs = min(512, 2^floor(log2 N)).
+// Compiled with -fmad=false: d = ((dx*dx)+(dy*dy))+(dz*dz) exactly.
+#include <cooperative_groups.h>
+
+#include "bx_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kMaxClouds = 16;
+struct FpsOffsets {
+    int v[kMaxClouds + 1];  // passed by value as a kernel argument: no device copy, no sync
+};
+
+struct Cand {
+    uint32_t hi, lo;  // hi = fp32 bits of the (non-negative) distance, lo = ~rank  (0,0) = "none" -> index 0
+    float x, y, z;    // coordinates of the candidate
+};
+
+__device__ __forceinline__ Cand warp_best(const Cand c) {
+    const uint32_t mh = __reduce_max_sync(BX_FULL, c.hi);
+    const bool in = (c.hi == mh);
+    const uint32_t ml = __reduce_max_sync(BX_FULL, in ? c.lo : 0u);
+    const unsigned b = __ballot_sync(BX_FULL, in && c.lo == ml);
+    const int src = __ffs(b) - 1;
+    Cand r;
+    r.hi = mh;
+    r.lo = ml;
+    r.x = __shfl_sync(BX_FULL, c.x, src);
+    r.y = __shfl_sync(BX_FULL, c.y, src);
+    r.z = __shfl_sync(BX_FULL, c.z, src);
+    return r;
+}
+
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, int npoint,
+                   int *__restrict__ idx_out, float *__restrict__ kpts_out) {
+    constexpr int NW = THREADS / 32;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int cloud = blockIdx.x / CL;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const int start = offsets.v[cloud];
+    const int N = offsets.v[cloud + 1] - start;
+    const float *xyz = xyz_all + 3 * (size_t)start;
+    int *idx = idx_out + (size_t)cloud * npoint;
+    float *kp = kpts_out ? kpts_out + 3 * (size_t)cloud * npoint : nullptr;
+
+    // upstream block size and the per-slot stride used for the tie rank
+    int log2bs = 0;
+    while ((2 << log2bs) <= N && log2bs < 9) ++log2bs;  // bs = min(512, 2^floor(log2 N))
+    const int bs = 1 << log2bs;
+    const int cpb = (N + bs - 1) >> log2bs;
+
+    __shared__ uint4 w_a[2][32];
+    __shared__ float w_z[2][32];
+    __shared__ uint4 c_a[2][16];
+    __shared__ float c_z[2][16];
+
+    float px[PPT], py[PPT], pz[PPT], tmp[PPT];
+    const int stride = CL * THREADS;
+    const int base = rank * THREADS + tid;
+#pragma unroll
+    for (int s = 0; s < PPT; ++s) {
+        const int k = s * stride + base;
+        if (k < N) {
+            px[s] = xyz[3 * (size_t)k];
+            py[s] = xyz[3 * (size_t)k + 1];
+            pz[s] = xyz[3 * (size_t)k + 2];
+            const float mag = ((px[s] * px[s]) + (py[s] * py[s])) + (pz[s] * pz[s]);
+            tmp[s] = ((double)mag <= 1e-3) ? -1.0f : 1e10f;
+        } else {
+            px[s] = py[s] = pz[s] = 0.0f;
+            tmp[s] = -1.0f;
+        }
+    }
+    const float p0x = xyz[0], p0y = xyz[1], p0z = xyz[2];
+    float ox = p0x, oy = p0y, oz = p0z;
+    if (rank == 0 && tid == 0 && npoint > 0) {
+        idx[0] = 0;
+        if (kp) { kp[0] = p0x; kp[1] = p0y; kp[2] = p0z; }
+    }
+    cluster.sync();  // every CTA of the cluster is resident before any DSMEM store
+
+    for (int j = 1; j < npoint; ++j) {
+        const int par = j & 1;
+        Cand best;
+        best.hi = 0u; best.lo = 0u; best.x = p0x; best.y = p0y; best.z = p0z;
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            if (tmp[s] >= 0.0f) {
+                const float d = bx_d2(px[s] - ox, py[s] - oy, pz[s] - oz);
+                const float d2 = fminf(d, tmp[s]);
+                tmp[s] = d2;
+                const int k = s * stride + base;
+                const uint32_t rk = (uint32_t)(k & (bs - 1)) * (uint32_t)cpb + (uint32_t)(k >> log2bs);
+                const uint32_t hi = __float_as_uint(d2), lo = ~rk;
+                if (hi > best.hi || (hi == best.hi && lo > best.lo)) {
+                    best.hi = hi; best.lo = lo; best.x = px[s]; best.y = py[s]; best.z = pz[s];
+                }
+            }
+        }
+        const Cand wb = warp_best(best);
+        if (lane == 0) {
+            w_a[par][warp] = make_uint4(wb.hi, wb.lo, __float_as_uint(wb.x), __float_as_uint(wb.y));
+            w_z[par][warp] = wb.z;
+        }
+        __syncthreads();
+        Cand c;
+        c.hi = 0u; c.lo = 0u; c.x = p0x; c.y = p0y; c.z = p0z;
+        if (lane < NW) {
+            const uint4 a = w_a[par][lane];
+            c.hi = a.x; c.lo = a.y; c.x = __uint_as_float(a.z); c.y = __uint_as_float(a.w); c.z = w_z[par][lane];
+        }
+        Cand cb = warp_best(c);
+        if (CL > 1) {
+            if (warp == 0 && lane < CL) {
+                uint4 *ra = cluster.map_shared_rank(&c_a[par][rank], lane);
+                float *rz = cluster.map_shared_rank(&c_z[par][rank], lane);
+                *ra = make_uint4(cb.hi, cb.lo, __float_as_uint(cb.x), __float_as_uint(cb.y));
+                *rz = cb.z;
+            }
+            cluster.sync();
+            Cand g;
+            g.hi = 0u; g.lo = 0u; g.x = p0x; g.y = p0y; g.z = p0z;
+            if (lane < CL) {
+                const uint4 a = c_a[par][lane];
+                g.hi = a.x; g.lo = a.y; g.x = __uint_as_float(a.z); g.y = __uint_as_float(a.w); g.z = c_z[par][lane];
+            }
+            cb = warp_best(g);
+        }
+        ox = cb.x; oy = cb.y; oz = cb.z;
+        if (rank == 0 && tid == 0) {
+            int k = 0;
+            if (cb.hi != 0u || cb.lo != 0u) {
+                const uint32_t rk = ~cb.lo;
+                k = (int)((rk % (uint32_t)cpb) << log2bs) + (int)(rk / (uint32_t)cpb);
+            }
+            idx[j] = k;
+            if (kp) { kp[3 * j] = ox; kp[3 * j + 1] = oy; kp[3 * j + 2] = oz; }
+        }
+    }
+    cluster.sync();  // nobody exits while a peer may still write into its shared memory
+}
+
+template <int THREADS, int PPT>
+int launch_fps(const float *xyz, const FpsOffsets off, int B, int CL, int npoint, int *idx, float *kpts, cudaStream_t st) {
+    auto kern = fps_cluster_kernel<THREADS, PPT>;
+    if (CL > 8) BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * CL));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    BX_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, off, npoint, idx, kpts));
+    return BX_OK;
+}
+
+}  // namespace
+
+BX_API int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint, int32_t *idx, float *kpts,
+                  void *stream) {
+    BX_REQUIRE(xyz && h_offsets && idx, "bx_fps: null pointer");
+    BX_REQUIRE(B >= 1 && B <= kMaxClouds, "bx_fps: B=%d out of range [1,%d]", B, kMaxClouds);
+    BX_REQUIRE(npoint >= 0, "bx_fps: npoint < 0");
+    if (npoint == 0) return BX_OK;
+    int maxN = 0;
+    for (int b = 0; b < B; ++b) {
+        const int n = h_offsets[b + 1] - h_offsets[b];
+        BX_REQUIRE(n >= 1, "bx_fps: cloud %d is empty", b);
+        if (n > maxN) maxN = n;
+    }
+    BX_REQUIRE(maxN <= 131072, "bx_fps: N=%d exceeds the 131072-point register budget of one cluster", maxN);
+    cudaStream_t st = bx_stream(stream);
+    FpsOffsets d_off;
+    for (int b = 0; b <= kMaxClouds; ++b) d_off.v[b] = h_offsets[b <= B ? b : B];
+    if (maxN <= 4096) return launch_fps<256, 2>(xyz, d_off, B, 8, npoint, idx, kpts, st);
+    if (maxN <= 8192) return launch_fps<256, 4>(xyz, d_off, B, 8, npoint, idx, kpts, st);
+    if (maxN <= 16384) return launch_fps<256, 8>(xyz, d_off, B, 8, npoint, idx, kpts, st);
+    if (maxN <= 32768) return launch_fps<256, 16>(xyz, d_off, B, 8, npoint, idx, kpts, st);
+    if (maxN <= 65536) return launch_fps<512, 16>(xyz, d_off, B, 8, npoint, idx, kpts, st);
+    return launch_fps<512, 16>(xyz, d_off, B, 16, npoint, idx, kpts, st);
+}

@@ -1,0 +1,280 @@
+// bx_patches.cu -- a3 (order-preserving radius-neighbour patch gathering) and a4+a5 (LRF, normalise).
+//
+// a3 replaces MiniSpinNet.select_patches (/root/reference/models/patch_embedder.py:92-120), i.e.
+// pointnet2_ops.ball_query (ONE CTA for the whole cloud when B=1) + grouping_operation + four
+// full-size mask temporaries.  Semantics: "the first P points of the permuted cloud, in index order,
+// inside the ball" -- not the P nearest.  One WARP per key-point scans the permuted cloud (float4,
+// coalesced 512-byte warp loads, L1/L2 resident: the cloud is 320 KB) in chunks of 128 points; a
+// ballot + popcount prefix compacts the hits in order, and the scan stops as soon as P slots are
+// filled.  Indices and gathered coordinates are written straight from the registers that just
+// tested the point.
+// a4+a5 replace axis_align / normalize (patch_embedder.py:122-148,167-170), cal_Z_axis
+// (utils/common.py:709-726: torch_batch_svd -> cuSOLVER gesvdjBatched on K 3x3 matrices) and
+// RodsRotatFormula (:501-525): one warp per patch, covariance by lane-strided sums + xor butterfly,
+// fp64 cyclic Jacobi in registers, Rodrigues from cos = z_z/|z|, sin = |z x e_z|/|z|.
+//
+// Bit contract: oracle/c/bx_oracle.c::bxo_ball_query / bxo_select_patches / bxo_lrf.  -fmad=false.
+#include "bx_common.cuh"
+
+namespace {
+
+__global__ void permute_cloud_kernel(const float *__restrict__ pts, const int *__restrict__ perm, int N,
+                                     float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int s = perm ? perm[i] : i;
+    out[i] = make_float4(pts[3 * (size_t)s], pts[3 * (size_t)s + 1], pts[3 * (size_t)s + 2], 0.0f);
+}
+
+// One warp per key-point.  UN = points tested per lane per step.
+constexpr int SP_WARPS = 8;
+constexpr int UN = 4;
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+select_patches_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ kpts, int K, float radius,
+                      const float *__restrict__ d_radius, int P, int *__restrict__ idx, float *__restrict__ patches) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
+    if (k >= K) return;
+    const float r = d_radius ? *d_radius : radius;
+    const float r2 = r * r;
+    const float qx = kpts[3 * (size_t)k], qy = kpts[3 * (size_t)k + 1], qz = kpts[3 * (size_t)k + 2];
+    int *row = idx ? idx + (size_t)k * P : nullptr;
+    float *out = patches + (size_t)k * P * 3;
+    int cnt = 0, first = 0;
+    for (int base = 0; base < N && cnt < P; base += 32 * UN) {
+        float4 p[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int i = base + u * 32 + lane;
+            p[u] = (i < N) ? pts4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int i = base + u * 32 + lane;
+            const float d2 = bx_d2(qx - p[u].x, qy - p[u].y, qz - p[u].z);
+            const bool hit = (i < N) && (d2 < r2);
+            const unsigned m = __ballot_sync(BX_FULL, hit);
+            if (m) {
+                if (cnt == 0) first = base + u * 32 + (__ffs(m) - 1);
+                const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+                if (hit && slot < P) {
+                    if (row) row[slot] = i;
+                    // slot P-1 always holds the key-point itself (patch_embedder.py:109)
+                    const bool centre = (slot == P - 1);
+                    out[3 * slot] = centre ? qx : p[u].x;
+                    out[3 * slot + 1] = centre ? qy : p[u].y;
+                    out[3 * slot + 2] = centre ? qz : p[u].z;
+                }
+                cnt += __popc(m);
+            }
+        }
+    }
+    if (cnt > P) cnt = P;
+    // padding: ball_query repeats the first hit; the fix-up replaces those slots by the key-point.
+    // No hit at all: index row = 0, slot 0 = point 0 of the permuted cloud, every other slot = key-point.
+    for (int s = cnt + lane; s < P; s += 32) {
+        if (row) row[s] = first;
+        float x = qx, y = qy, z = qz;
+        if (cnt == 0 && s == 0 && P > 1) {
+            const float4 p0 = pts4[0];
+            x = p0.x; y = p0.y; z = p0.z;
+        }
+        out[3 * s] = x;
+        out[3 * s + 1] = y;
+        out[3 * s + 2] = z;
+    }
+}
+
+// plain ordered ball query over a packed [n,3] cloud (pointnet2_ops.ball_query semantics)
+__global__ void __launch_bounds__(SP_WARPS * 32)
+ball_query_kernel(const float *__restrict__ xyz, int n, const float *__restrict__ qry, int m, float radius, int nsample,
+                  int *__restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
+    if (j >= m) return;
+    const float r2 = radius * radius;
+    const float qx = qry[3 * (size_t)j], qy = qry[3 * (size_t)j + 1], qz = qry[3 * (size_t)j + 2];
+    int *row = idx + (size_t)j * nsample;
+    int cnt = 0, first = 0;
+    for (int base = 0; base < n && cnt < nsample; base += 32) {
+        const int i = base + lane;
+        bool hit = false;
+        if (i < n) {
+            const float d2 = bx_d2(qx - xyz[3 * (size_t)i], qy - xyz[3 * (size_t)i + 1], qz - xyz[3 * (size_t)i + 2]);
+            hit = d2 < r2;
+        }
+        const unsigned msk = __ballot_sync(BX_FULL, hit);
+        if (msk) {
+            if (cnt == 0) first = base + (__ffs(msk) - 1);
+            const int slot = cnt + __popc(msk & ((1u << lane) - 1u));
+            if (hit && slot < nsample) row[slot] = i;
+            cnt += __popc(msk);
+        }
+    }
+    if (cnt > nsample) cnt = nsample;
+    for (int s = cnt + lane; s < nsample; s += 32) row[s] = first;
+}
+
+// ---- LRF ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jacobi_rot3(double (&A)[3][3], double (&V)[3][3], const int p, const int q) {
+    const double apq = A[p][q];
+    if (apq == 0.0) return;
+    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+    const double at = fabs(theta);
+    double t = 1.0 / (at + sqrt((theta * theta) + 1.0));
+    if (theta < 0.0) t = -t;
+    const double c = 1.0 / sqrt((t * t) + 1.0);
+    const double s = t * c;
+    const double app = A[p][p], aqq = A[q][q];
+    A[p][p] = app - (t * apq);
+    A[q][q] = aqq + (t * apq);
+    A[p][q] = 0.0;
+    A[q][p] = 0.0;
+    const int r = 3 - p - q;
+    const double arp = A[r][p], arq = A[r][q];
+    A[r][p] = (c * arp) - (s * arq);
+    A[p][r] = A[r][p];
+    A[r][q] = (s * arp) + (c * arq);
+    A[q][r] = A[r][q];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double vkp = V[k][p], vkq = V[k][q];
+        V[k][p] = (c * vkp) - (s * vkq);
+        V[k][q] = (s * vkp) + (c * vkq);
+    }
+}
+
+constexpr int LRF_WARPS = 4;
+
+__global__ void __launch_bounds__(LRF_WARPS * 32)
+lrf_kernel(const float *__restrict__ patches, int K, int P, float des_r_v, const float *__restrict__ d_des_r, int aligned,
+           float *__restrict__ delta, float *__restrict__ Rt, float *__restrict__ rand_axis) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * LRF_WARPS + (threadIdx.x >> 5);
+    if (k >= K) return;
+    const float des_r = d_des_r ? *d_des_r : des_r_v;
+    const float *pt = patches + (size_t)k * P * 3;
+    float *dl = delta + (size_t)k * P * 3;
+    const float cx = pt[3 * (P - 1)], cy = pt[3 * (P - 1) + 1], cz = pt[3 * (P - 1) + 2];
+    float R[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+    float ra0 = 1.0f, ra1 = 0.0f, ra2 = 0.0f;
+    if (!aligned) {
+        float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+        for (int s = lane; s < P; s += 32) {
+            const float x = pt[3 * s] - cx, y = pt[3 * s + 1] - cy, z = pt[3 * s + 2] - cz;
+            c00 = c00 + (x * x);
+            c01 = c01 + (x * y);
+            c02 = c02 + (x * z);
+            c11 = c11 + (y * y);
+            c12 = c12 + (y * z);
+            c22 = c22 + (z * z);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            c00 = c00 + __shfl_xor_sync(BX_FULL, c00, off);
+            c01 = c01 + __shfl_xor_sync(BX_FULL, c01, off);
+            c02 = c02 + __shfl_xor_sync(BX_FULL, c02, off);
+            c11 = c11 + __shfl_xor_sync(BX_FULL, c11, off);
+            c12 = c12 + __shfl_xor_sync(BX_FULL, c12, off);
+            c22 = c22 + __shfl_xor_sync(BX_FULL, c22, off);
+        }
+        double A[3][3], V[3][3];
+        A[0][0] = c00; A[0][1] = c01; A[0][2] = c02;
+        A[1][0] = c01; A[1][1] = c11; A[1][2] = c12;
+        A[2][0] = c02; A[2][1] = c12; A[2][2] = c22;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+        for (int sweep = 0; sweep < 8; ++sweep) {
+            jacobi_rot3(A, V, 0, 1);
+            jacobi_rot3(A, V, 0, 2);
+            jacobi_rot3(A, V, 1, 2);
+        }
+        // smallest eigenvalue, first minimum wins (fully unrolled selects: no dynamic register indexing)
+        double em = A[0][0];
+        double v0 = V[0][0], v1 = V[1][0], v2 = V[2][0];
+        if (A[1][1] < em) { em = A[1][1]; v0 = V[0][1]; v1 = V[1][1]; v2 = V[2][1]; }
+        if (A[2][2] < em) { em = A[2][2]; v0 = V[0][2]; v1 = V[1][2]; v2 = V[2][2]; }
+        float z0 = (float)v0, z1 = (float)v1, z2 = (float)v2;
+        const float sgn = (((-z0) * cx) + ((-z1) * cy)) + ((-z2) * cz);
+        if (sgn < 0.0f) { z0 = -z0; z1 = -z1; z2 = -z2; }
+        const float nz = sqrtf(((z0 * z0) + (z1 * z1)) + (z2 * z2));
+        z0 = z0 / nz; z1 = z1 / nz; z2 = z2 / nz;
+        const float n = sqrtf(((z0 * z0) + (z1 * z1)) + (z2 * z2));
+        const float sn = sqrtf((z0 * z0) + (z1 * z1));
+        const float ct = z2 / n, st = sn / n;
+        const float den = sn > 1e-12f ? sn : 1e-12f;
+        const float a0 = z1 / den, a1 = (-z0) / den;
+        const float kk = 1.0f - ct;
+        R[0][0] = 1.0f - (kk * (a1 * a1)); R[0][1] = kk * (a0 * a1);          R[0][2] = st * a1;
+        R[1][0] = kk * (a0 * a1);          R[1][1] = 1.0f - (kk * (a0 * a0)); R[1][2] = -(st * a0);
+        R[2][0] = -(st * a1);              R[2][1] = st * a0;                 R[2][2] = 1.0f - (kk * ((a0 * a0) + (a1 * a1)));
+        ra0 = a0; ra1 = a1; ra2 = 0.0f;
+    }
+    for (int s = lane; s < P; s += 32) {
+        const float x = pt[3 * s] - cx, y = pt[3 * s + 1] - cy, z = pt[3 * s + 2] - cz;
+        float ox = x, oy = y, oz = z;
+        if (!aligned) {
+            ox = ((R[0][0] * x) + (R[0][1] * y)) + (R[0][2] * z);
+            oy = ((R[1][0] * x) + (R[1][1] * y)) + (R[1][2] * z);
+            oz = ((R[2][0] * x) + (R[2][1] * y)) + (R[2][2] * z);
+        }
+        dl[3 * s] = ox / des_r;
+        dl[3 * s + 1] = oy / des_r;
+        dl[3 * s + 2] = oz / des_r;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Rt[(size_t)k * 9 + 3 * i + j] = R[j][i];
+        rand_axis[3 * (size_t)k] = ra0;
+        rand_axis[3 * (size_t)k + 1] = ra1;
+        rand_axis[3 * (size_t)k + 2] = ra2;
+    }
+}
+
+}  // namespace
+
+BX_API int bx_permute_cloud(const float *pts, const int32_t *perm, int N, float *out4, void *stream) {
+    BX_REQUIRE(pts && out4 && N >= 1, "bx_permute_cloud: bad arguments");
+    BX_REQUIRE((reinterpret_cast<uintptr_t>(out4) & 15) == 0, "bx_permute_cloud: out4 must be 16-byte aligned");
+    permute_cloud_kernel<<<(N + 255) / 256, 256, 0, bx_stream(stream)>>>(pts, perm, N, reinterpret_cast<float4 *>(out4));
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
+BX_API int bx_select_patches(const float *pts4, int N, const float *kpts, int K, float radius, const float *d_radius,
+                             int P, int32_t *idx, float *patches, void *stream) {
+    BX_REQUIRE(pts4 && kpts && patches, "bx_select_patches: null pointer");
+    BX_REQUIRE(N >= 1 && K >= 0 && P >= 1, "bx_select_patches: bad sizes N=%d K=%d P=%d", N, K, P);
+    BX_REQUIRE((reinterpret_cast<uintptr_t>(pts4) & 15) == 0, "bx_select_patches: pts4 must be 16-byte aligned");
+    if (K == 0) return BX_OK;
+    select_patches_kernel<<<(K + SP_WARPS - 1) / SP_WARPS, SP_WARPS * 32, 0, bx_stream(stream)>>>(
+        reinterpret_cast<const float4 *>(pts4), N, kpts, K, radius, d_radius, P, idx, patches);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
+BX_API int bx_ball_query(const float *xyz, int n, const float *qry, int m, float radius, int nsample, int32_t *idx,
+                         void *stream) {
+    BX_REQUIRE(xyz && qry && idx && n >= 1 && m >= 0 && nsample >= 1, "bx_ball_query: bad arguments");
+    if (m == 0) return BX_OK;
+    ball_query_kernel<<<(m + SP_WARPS - 1) / SP_WARPS, SP_WARPS * 32, 0, bx_stream(stream)>>>(xyz, n, qry, m, radius,
+                                                                                                nsample, idx);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
+BX_API int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r, int aligned, float *delta,
+                  float *Rt, float *rand_axis, void *stream) {
+    BX_REQUIRE(patches && delta && Rt && rand_axis, "bx_lrf: null pointer");
+    BX_REQUIRE(K >= 0 && P >= 1, "bx_lrf: bad sizes");
+    if (K == 0) return BX_OK;
+    lrf_kernel<<<(K + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, 0, bx_stream(stream)>>>(patches, K, P, des_r, d_des_r,
+                                                                                           aligned, delta, Rt, rand_axis);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}

@@ -1,0 +1,219 @@
+"""BufferX on B200: the per-pair registration ``forward()``.
+
+Mirrors ``BufferX`` of /root/reference/models/BUFFERX.py (constructor :72-84, inference branch of
+``forward`` :257-467, ``mutual_matching`` :469-496, ``post_refinement`` :522-556): same attribute names
+(``Desc``, ``Pose``, ``equi_match``, ``pose_estimator``), same ``state_dict()`` keys, same return tuple
+``(pose 4x4, [desc_s, pose_s, pose_optim_s], num_inliers, num_mutual_inliers, num_inlier_ind,
+scales_used)``.  Differences that do not change results:
+  * FPS runs once per cloud for max(num_points_radius_estimate, num_fps) points -- the reference's
+    per-scale calls return the same indices and FPS(k) is a prefix of FPS(k');
+  * the radius histogram is built once and serves every scale's bisection, on the device;
+  * data-dependent sizes stay in device counters, so the whole pair is enqueued without a host round
+    trip; the host reads one small result block at the end (early-exit mode adds one read after scale 0).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from bufferx_b200 import ops
+from . import patchnet as pn
+from .patch_embedder import MiniSpinNet
+from .pose_estimator import PoseEstimator
+
+
+def _azimuth_index_list(azi_n):
+    init = np.arange(azi_n)
+    return np.array([np.concatenate([init[azi_n - i:], init[:azi_n - i]]) for i in range(azi_n)])
+
+
+class EquiMatch(nn.Module):
+    """Training-time SO(2) matching score (reference BUFFERX.py:16-36); kept for API parity, plain torch."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.azi_n = config.patch.azi_n
+        self.index_list = _azimuth_index_list(self.azi_n)
+
+    def forward(self, Des1, Des2):
+        B, C, K, L = Des1.shape
+        idx = torch.from_numpy(self.index_list).to(Des1.device).reshape(-1)
+        d1 = Des1[:, :, :, idx].reshape(B, C, K, self.azi_n, self.azi_n).permute(0, 1, 3, 2, 4).reshape(B, C, -1, K * L)
+        return torch.einsum("bfag,bfg->ba", d1, Des2.reshape(B, C, K * L))
+
+
+class CostVolume(nn.Module):
+    """SO(2) cost volume + CostNet (reference BUFFERX.py:39-69); state_dict prefix ``conv.``."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.azi_n = config.patch.azi_n
+        self.index_list = _azimuth_index_list(self.azi_n)
+        self.conv = pn.CostNet(inchan=32, dim=20)
+
+    def logits(self, equi_s, equi_t, s_mids, t_mids, d_M, maxM):
+        """Full-height maps [K,32,7,20] + match lists; rows 1..ele_n-2 are sliced inside the kernel."""
+        return self.conv.forward_matches(equi_s, equi_t, s_mids, t_mids, d_M, maxM)
+
+
+class _Timer:
+    def __init__(self, enabled):
+        self.enabled = enabled
+        self.total = 0.0
+        if enabled:
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def tic(self):
+        if self.enabled:
+            self.a.record()
+
+    def toc(self):
+        if self.enabled:
+            self.b.record()
+            self.b.synchronize()
+            self.total += self.a.elapsed_time(self.b) / 1000.0
+
+
+class BufferX(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.config.stage = config.stage
+        self.Desc = MiniSpinNet(config)
+        self.Pose = CostVolume(config)
+        self.equi_match = EquiMatch(config)
+        if config.stage == "test":
+            self.pose_estimator = PoseEstimator(config)
+        self._host = None
+
+    def get_parameter(self):
+        return list(self.parameters())
+
+    # ------------------------------------------------------------------------------------------------
+    def mutual_matching(self, src_des, tgt_des):
+        """[M,C],[N,C] -> (s_mids, t_mids) int64, like the reference (one device->host read for M)."""
+        s, t, dM, _, _ = ops.mutual_nn(src_des.contiguous(), tgt_des.contiguous())
+        M = int(dM.item())
+        return s[:M].long(), t[:M].long()
+
+    def post_refinement(self, initial_trans, src_keypts, tgt_keypts, weights=None):
+        """[1,4,4], [1,n,3], [1,n,3] -> [1,4,4] (reference BUFFERX.py:522-556)."""
+        assert initial_trans.shape[0] == 1
+        ss, tt = src_keypts[0].contiguous(), tgt_keypts[0].contiguous()
+        n = ss.shape[0]
+        d_n = torch.tensor([n], dtype=torch.int32, device=ss.device)
+        T_in = initial_trans[0].to(torch.float64).reshape(16).contiguous()
+        T, _ = ops.refine(ss, tt, d_n, n, T_in, self.config.match.dist_th)
+        return T.view(1, 4, 4)
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, data_source, perms=None, ransac_seed=None, debug=False):
+        cfg = self.config
+        if cfg.stage != "test":
+            raise NotImplementedError("bufferx_b200 implements the inference hot path (cfg.stage == 'test')")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise ops.BufferXError("BufferX.forward needs the model on a CUDA device: there is no CPU path")
+
+        def _cloud(x):
+            x = torch.as_tensor(x)
+            return x.to(dev, dtype=torch.float32, non_blocking=True).reshape(-1, 3).contiguous()
+
+        src, tgt = _cloud(data_source["src_fds_pcd"]), _cloud(data_source["tgt_fds_pcd"])
+        aligned = bool(data_source["is_aligned_to_global_z"])
+        Ns, Nt = src.shape[0], tgt.shape[0]
+        Kr, K = cfg.patch.num_points_radius_estimate, cfg.patch.num_fps
+        S = cfg.patch.num_scales
+        thresholds = cfg.patch.search_radius_thresholds
+        assert S == len(thresholds), f"num_scales {S} != num_thresholds {len(thresholds)}"
+        enable_early_exit = cfg.match.get("enable_early_exit", True)
+        enable_timing = cfg.test.get("enable_timing", False)
+        desc_t, pose_t, opt_t = _Timer(enable_timing), _Timer(enable_timing), _Timer(enable_timing)
+        azi_n = cfg.patch.azi_n
+
+        desc_t.tic()
+        # ---- key-points: one FPS per cloud, both clouds in one launch --------------------------------
+        xyz = torch.cat([src, tgt], dim=0)
+        nfps = max(Kr, K)
+        fidx, fk = ops.fps(xyz, [0, Ns, Ns + Nt], nfps)
+        kpts1, kpts2 = fk[0, :Kr].contiguous(), fk[1, :Kr].contiguous()
+        src_kpts, tgt_kpts = fk[0, :K].contiguous(), fk[1, :K].contiguous()
+        # ---- density-aware radii of every scale from one histogram ------------------------------------
+        pts_r, kpts_r = (src, kpts1) if Ns > Nt else (tgt, kpts2)
+        denom = pts_r.shape[0] * Kr
+        if pts_r.shape[0] > 200000:  # reference BUFFERX.py:664-665 (denominator keeps the original size)
+            pts_r = pts_r[torch.randint(0, pts_r.shape[0], (200000,), device=dev)].contiguous()
+        r_dev, m_dev, _ = ops.radius_estimate(kpts_r, pts_r, thresholds, denom=denom)
+        desc_t.toc()
+
+        maxMc = S * K
+        R_acc = torch.empty((maxMc, 3, 3), dtype=torch.float32, device=dev)
+        t_acc = torch.empty((maxMc, 3), dtype=torch.float32, device=dev)
+        ss_acc = torch.empty((maxMc, 3), dtype=torch.float32, device=dev)
+        tt_acc = torch.empty((maxMc, 3), dtype=torch.float32, device=dev)
+        offs = torch.zeros(S + 1, dtype=torch.int32, device=dev)
+        ind_dbg = [] if debug else None
+        dbg = dict(scales=[]) if debug else None
+
+        init_pose, num_inliers, num_inlier_ind, scales_used = None, 0, 0, 0
+        should_exit = False
+        res_block = None
+        inl = dI = None
+        for i in range(S):
+            desc_t.tic()
+            des_r = r_dev[i:i + 1]
+            ps = None if perms is None else perms[i][0]
+            pt = None if perms is None else perms[i][1]
+            sd = self.Desc(src[None], src_kpts[None], des_r, aligned, perm=ps, debug=debug)
+            td = self.Desc(tgt[None], tgt_kpts[None], des_r, aligned, perm=pt, debug=debug)
+            s_mids, t_mids, dM, snn, tnn = ops.mutual_nn(sd["desc"], td["desc"], want_nn=debug)
+            desc_t.toc()
+
+            pose_t.tic()
+            logits = self.Pose.logits(sd["equi"], td["equi"], s_mids, t_mids, dM, K)
+            ind = torch.empty(K, dtype=torch.float32, device=dev) if debug else None
+            ops.hypotheses(logits, azi_n, src_kpts, tgt_kpts, sd["R"], td["R"], s_mids, t_mids, dM, K,
+                           offs[i:i + 1], offs[i + 1:i + 2], ind, R_acc, t_acc, ss_acc, tt_acc)
+            scales_used = i + 1
+            need_consensus = (i == S - 1) or (enable_early_exit and i == 0) or debug
+            if need_consensus:
+                inl, dI, dbest, counts = ops.consensus(ss_acc, tt_acc, R_acc, t_acc, offs[i + 1:i + 2], (i + 1) * K, azi_n,
+                                                       cfg.match.inlier_th)
+            pose_t.toc()
+            if debug:
+                dbg["scales"].append(dict(s=sd, t=td, s_mids=s_mids, t_mids=t_mids, dM=dM, snn=snn, tnn=tnn, logits=logits,
+                                          ind=ind, inlier_ind=inl.clone(), dI=dI.clone(), best=dbest.clone()))
+            if enable_early_exit and i == 0:
+                opt_t.tic()
+                res_block = self.pose_estimator.enqueue(ss_acc, tt_acc, inl, dI, (i + 1) * K, ransac_seed)
+                init_pose, num_inliers, _, _ = ops.decode_ransac_result(res_block.cpu())   # one host read
+                opt_t.toc()
+                should_exit = self.pose_estimator.compute_confidence_score(num_inliers)
+                if should_exit:
+                    break
+
+        opt_t.tic()
+        ran_final = (not enable_early_exit) or (enable_early_exit and not should_exit)
+        if ran_final:
+            res_block = self.pose_estimator.enqueue(ss_acc, tt_acc, inl, dI, scales_used * K, ransac_seed)
+        d_Mc = offs[scales_used:scales_used + 1]
+        refined = None
+        if cfg.test.pose_refine is True:
+            refined, _ = ops.refine(ss_acc, tt_acc, d_Mc, scales_used * K, res_block[:16], cfg.match.dist_th)
+        # ---- one small device->host read for everything the caller needs -----------------------------
+        tail = torch.cat([res_block, offs.double(), dI.double(),
+                          refined.double() if refined is not None else torch.zeros(16, dtype=torch.float64, device=dev)]).cpu()
+        opt_t.toc()
+        init_pose, num_inliers, best_itr, iters = ops.decode_ransac_result(tail[:18])
+        offs_h = tail[18:18 + S + 1].numpy().astype(np.int64)
+        num_inlier_ind = int(tail[18 + S + 1].item())
+        num_mutual_inliers = int(offs_h[scales_used])
+        if cfg.test.pose_refine is True:
+            pose = tail[18 + S + 2:].numpy().astype(np.float32).reshape(4, 4)
+        else:
+            pose = init_pose
+        times = [desc_t.total, pose_t.total, opt_t.total]
+        if debug:
+            dbg.update(fps_idx=fidx, kpts=fk, des_r=r_dev, des_m=m_dev, offs=offs_h, init_pose=init_pose, best_itr=best_itr,
+                       iters=iters, ss=ss_acc, tt=tt_acc, R=R_acc, t=t_acc)
+            self.last_debug = dbg
+        return pose, times, num_inliers, num_mutual_inliers, num_inlier_ind, scales_used

@@ -1,0 +1,111 @@
+"""Mini-SpinNet patch descriptor on B200 kernels.
+
+Mirrors ``MiniSpinNet`` of /root/reference/models/patch_embedder.py (constructor :16-42, forward :44-90,
+same sub-module names -> same state_dict keys ``pnt_layer.{0,1}``, ``pool_layer.{0,1,3,4}``,
+``conv_net.ops.*``).  Inference only: select_patches -> axis_align -> normalize -> SPT -> pnt_layer+max ->
+Cylindrical_Net -> attention pooling, every stage a hand-written CUDA kernel behind the C-ABI.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from bufferx_b200 import ops
+from . import patchnet as pn
+
+
+def voxel_table(rad_n, azi_n, ele_n):
+    """[rad_n*ele_n*azi_n,3] fp32 voxel centres, fp64 on the host then one cast -- the arithmetic of
+    get_voxel_coordinate (/root/reference/utils/common.py:422-428; s2_grid :248-262, change_coordinates
+    :392-405) for radius 1 (patch_embedder.py:70)."""
+    beta = np.linspace(0, np.pi, num=ele_n, endpoint=False) + np.pi / ele_n / 2
+    alpha = np.linspace(0, 2 * np.pi, num=azi_n, endpoint=False) + np.pi / azi_n
+    Bm, Am = np.meshgrid(beta, alpha, indexing="ij")
+    Bm, Am = Bm.flatten(), Am.flatten()
+    s2 = np.stack([np.sin(Bm) * np.cos(Am), np.sin(Bm) * np.sin(Am), np.cos(Bm)], axis=1)
+    shells = (np.arange(rad_n) / rad_n + 1 / (2 * rad_n)).reshape(rad_n, 1, 1)
+    return (shells * s2[None]).reshape(-1, 3).astype(np.float32)
+
+
+def derotation_table(azi_n):
+    """(cos, sin) of -a*2pi/azi_n, fp64 then fp32 (var_to_invar, utils/common.py:483-491)."""
+    ang = -1.0 * np.arange(azi_n) * (2 * np.pi / azi_n)
+    return np.stack([np.cos(ang), np.sin(ang)], axis=1).astype(np.float32)
+
+
+class MiniSpinNet(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.patch_sample = config.patch.num_points_per_patch
+        self.rad_n = config.patch.rad_n
+        self.azi_n = config.patch.azi_n
+        self.ele_n = config.patch.ele_n
+        self.delta = config.patch.delta
+        self.voxel_sample = config.patch.voxel_sample
+        self.pnt_layer = nn.Sequential(nn.Conv2d(3, 16, kernel_size=(1, 1)), nn.BatchNorm2d(16), nn.ReLU(True))
+        self.pool_layer = nn.Sequential(nn.Conv2d(32, 16, kernel_size=(1, 1)), nn.BatchNorm2d(16), nn.ReLU(True),
+                                        nn.Conv2d(16, 1, kernel_size=(1, 1)), nn.BatchNorm2d(1), nn.ReLU(True))
+        self.conv_net = pn.Cylindrical_Net(inchan=16, dim=32)
+        self._prep = None
+
+    # ---- folded small layers + geometry tables, cached per device -------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._prep = None
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._prep = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def prepared(self, device):
+        if self._prep is None or self._prep["device"] != device:
+            bn = self.pnt_layer[1]
+            Wt, b = pn.fold_conv_bn(self.pnt_layer[0].weight, self.pnt_layer[0].bias, bn.running_mean, bn.running_var,
+                                    bn.weight, bn.bias, bn.eps)          # [1,3,16]
+            w_pnt = Wt[0].t().contiguous()                                 # [16,3]
+            b1n, b2n = self.pool_layer[1], self.pool_layer[4]
+            W1, b1 = pn.fold_conv_bn(self.pool_layer[0].weight, self.pool_layer[0].bias, b1n.running_mean, b1n.running_var,
+                                     b1n.weight, b1n.bias, b1n.eps)        # [1,32,16]
+            W2, b2 = pn.fold_conv_bn(self.pool_layer[3].weight, self.pool_layer[3].bias, b2n.running_mean, b2n.running_var,
+                                     b2n.weight, b2n.bias, b2n.eps)        # [1,16,1]
+            self._prep = dict(
+                device=device,
+                w_pnt=w_pnt.to(device), b_pnt=b.to(device),
+                w1=W1[0].contiguous().to(device), b1=b1.to(device),
+                w2=W2[0, :, 0].contiguous().to(device), b2=b2.to(device),
+                voxels=torch.from_numpy(voxel_table(self.rad_n, self.azi_n, self.ele_n)).to(device),
+                rot=torch.from_numpy(derotation_table(self.azi_n)).to(device),
+            )
+        return self._prep
+
+    def forward(self, pts, kpts, des_r, is_aligned_to_global_z, z_axis=None, is_aug=False, perm=None, debug=False):
+        """pts [1,N,3], kpts [1,K,3] CUDA f32; des_r python float or 1-element CUDA tensor.
+        ``perm`` (optional int32 [N]) replaces the host draw of the reference (patch_embedder.py:96)."""
+        if z_axis is not None or is_aug:
+            raise NotImplementedError("training-time options (z_axis / SO(2) augmentation) are outside the inference hot path")
+        pts = pts[0].contiguous()
+        kpts = kpts[0].contiguous()
+        dev = pts.device
+        N = pts.shape[0]
+        if perm is None:
+            # the reference consumes NumPy's GLOBAL RNG here, once per call: keep that coupling
+            perm = np.random.choice(N, N, replace=False)
+        if not isinstance(perm, torch.Tensor):
+            perm = torch.from_numpy(np.ascontiguousarray(perm, dtype=np.int32)).to(dev, non_blocking=True)
+        prep = self.prepared(dev)
+        pts4 = ops.permute_cloud(pts, perm)
+        patches, idx = ops.select_patches(pts4, kpts, des_r, self.patch_sample, want_idx=debug)
+        delta, R, rand_axis = ops.lrf(patches, des_r, bool(is_aligned_to_global_z))
+        res = ops.spt_pnt(delta, prep["voxels"], prep["rot"], self.delta / self.rad_n, self.voxel_sample, prep["w_pnt"],
+                          prep["b_pnt"], self.azi_n, debug=debug)
+        feat = res[0] if debug else res
+        K = kpts.shape[0]
+        x, _ = self.conv_net(feat.view(K, 16, self.rad_n, self.ele_n, self.azi_n))
+        desc, equi = ops.pool_desc(x, prep["w1"], prep["b1"], prep["w2"], prep["b2"])
+        out = {"desc": desc, "equi": equi, "rand_axis": rand_axis, "R": R, "patches": delta, "aug_rotation": None}
+        if debug:
+            out.update(idx=idx, raw_patches=patches, vidx=res[1], inv=res[2], feat=feat, x=x)
+        return out
+
+    def get_parameter(self):
+        return list(self.parameters())

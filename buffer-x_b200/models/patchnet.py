@@ -1,0 +1,137 @@
+"""Parameter containers + weight folding for the two convolution stacks.
+
+Mirrors the state_dict layout of /root/reference/models/patchnet.py: ``Cylindrical_Net``
+(:68-84, ops.{0,1,3,4,...,21}) and ``CostNet`` (:192-210, ops.{0,1,...,27}); BatchNorm layers in the
+stacks have ``affine=False`` (:28,31).  The modules hold parameters only -- the arithmetic runs in
+``bx_conv_layer`` (buffer-x_b200/csrc/bx_conv.cu).  ``folded()`` returns, per conv layer, the weight
+re-laid as [tap][Cin][Cout] with the eval-mode BatchNorm folded in (computed in fp64, stored fp32).
+"""
+import torch
+import torch.nn as nn
+
+from bufferx_b200 import ops
+
+
+def fold_conv_bn(conv_w, conv_b, bn_mean=None, bn_var=None, bn_w=None, bn_b=None, eps=1e-5):
+    """-> (Wt [T, Cin, Cout] f32 contiguous, bias [Cout] f32).  Works for 1x1/2-D/3-D kernels."""
+    W = conv_w.detach().double()
+    b = conv_b.detach().double()
+    Cout, Cin = W.shape[0], W.shape[1]
+    W = W.reshape(Cout, Cin, -1)
+    if bn_mean is not None:
+        s = 1.0 / torch.sqrt(bn_var.detach().double() + eps)
+        if bn_w is not None:
+            s = s * bn_w.detach().double()
+        W = W * s[:, None, None]
+        b = (b - bn_mean.detach().double()) * s
+        if bn_b is not None:
+            b = b + bn_b.detach().double()
+    Wt = W.permute(2, 1, 0).contiguous().float()
+    return Wt, b.float().contiguous()
+
+
+class _ConvStack(nn.Module):
+    """ModuleList ``ops`` with the reference's index layout: conv, [bn], [relu], conv, ..."""
+
+    def __init__(self, spec, bn_affine=False):
+        super().__init__()
+        self.ops = nn.ModuleList([])
+        self.layers = []  # (conv index, bn index or None, relu?)
+        for (cin, cout, k, bn, relu) in spec:
+            ci = len(self.ops)
+            if len(k) == 3:
+                self.ops.append(nn.Conv3d(cin, cout, kernel_size=tuple(k)))
+            else:
+                self.ops.append(nn.Conv2d(cin, cout, kernel_size=tuple(k)))
+            bi = None
+            if bn:
+                bi = len(self.ops)
+                self.ops.append((nn.BatchNorm3d if len(k) == 3 else nn.BatchNorm2d)(cout, affine=bn_affine))
+            if relu:
+                self.ops.append(nn.ReLU(inplace=True))
+            self.layers.append((ci, bi, relu))
+        self._folded = None
+
+    def invalidate(self):
+        self._folded = None
+
+    def _apply(self, fn, *a, **k):
+        self._folded = None
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._folded = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def folded(self):
+        if self._folded is None:
+            out = []
+            for (ci, bi, relu) in self.layers:
+                conv = self.ops[ci]
+                bn = self.ops[bi] if bi is not None else None
+                Wt, b = fold_conv_bn(conv.weight, conv.bias,
+                                     None if bn is None else bn.running_mean, None if bn is None else bn.running_var,
+                                     None if bn is None or not bn.affine else bn.weight,
+                                     None if bn is None or not bn.affine else bn.bias,
+                                     eps=1e-5 if bn is None else bn.eps)
+                ks = tuple(conv.kernel_size)
+                out.append(dict(w=Wt, b=b, cin=conv.in_channels, cout=conv.out_channels,
+                                k=ks if len(ks) == 3 else (1,) + ks, relu=relu))
+            self._folded = out
+        return self._folded
+
+
+class Cylindrical_Net(_ConvStack):
+    """[K,16,3,7,20] -> [K,32,7,20]  (reference: models/patchnet.py:68-84)."""
+
+    def __init__(self, inchan=16, dim=32):
+        spec = [(inchan, 64, (3, 3, 3), True, True), (64, 64, (3, 3), True, True), (64, 128, (3, 3), True, True),
+                (128, 128, (3, 3), True, True), (128, 64, (3, 3), True, True), (64, 64, (3, 3), True, True),
+                (64, 32, (3, 3), True, True), (32, dim, (3, 3), False, False)]
+        super().__init__(spec)
+        self.out_dim = dim
+
+    def forward(self, x):
+        """x: [K,16,3,7,20] CUDA f32 -> (x_out [K,32,7,20], None)."""
+        K = x.shape[0]
+        dev = x.device
+        L = self.folded()
+        cur = x.contiguous()
+        for i, l in enumerate(L):
+            out = torch.empty((K, l["cout"], 140), dtype=torch.float32, device=dev)
+            if i == 0:
+                ops.conv_layer(ops.GEOM_CYL3D, cur, l["w"], l["b"], out, K, l["cin"], l["cout"], 3, 7, 20, 3, 3, 3, l["relu"])
+            else:
+                ops.conv_layer(ops.GEOM_CYL2D, cur, l["w"], l["b"], out, K, l["cin"], l["cout"], 1, 7, 20, 1, 3, 3, l["relu"])
+            cur = out
+        return cur.view(K, L[-1]["cout"], 7, 20), None
+
+
+class CostNet(_ConvStack):
+    """[M,32,20,5,20] cost volume -> [M,20] logits (reference: models/patchnet.py:192-210)."""
+
+    def __init__(self, inchan=32, dim=1):
+        spec = [(inchan, 32, (3, 3, 3), True, True), (32, 64, (3, 3, 3), True, True), (64, 64, (3, 1, 3), True, True),
+                (64, 128, (3, 1, 3), True, True), (128, 128, (3, 1, 3), True, True), (128, 64, (3, 1, 3), True, True),
+                (64, 64, (3, 1, 3), True, True), (64, 32, (3, 1, 3), True, True), (32, 32, (3, 1, 3), True, True),
+                (32, dim, (2, 1, 2), False, False)]
+        super().__init__(spec)
+        self.out_dim = dim
+
+    def forward_matches(self, equi_s, equi_t, s_mids, t_mids, d_M, maxM):
+        """equi_* [K,32,7,20]; match lists + device count -> logits [maxM, dim] (rows >= *d_M undefined)."""
+        dev = equi_s.device
+        L = self.folded()
+        D, H, W = 20, 5, 20
+        cur = None
+        for i, l in enumerate(L):
+            kd, kh, kw = l["k"]
+            OD, OH, OW = D - kd + 1, H - kh + 1, W - kw + 1
+            out = torch.empty((maxM, l["cout"], OD * OH * OW), dtype=torch.float32, device=dev)
+            if i == 0:
+                ops.conv_layer(ops.GEOM_COSTVOL, None, l["w"], l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"],
+                               d_n=d_M, equi_s=equi_s, equi_t=equi_t, s_mids=s_mids, t_mids=t_mids)
+            else:
+                ops.conv_layer(ops.GEOM_VALID3D, cur, l["w"], l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"], d_n=d_M)
+            cur, D, H, W = out, OD, OH, OW
+        return cur.view(maxM, L[-1]["cout"])

@@ -1,0 +1,277 @@
+"""Torch-tensor front end of the C-ABI library (``include/bufferx_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every kernel lives in
+``libbufferx_b200.so`` and is reached through ctypes with raw ``data_ptr()`` values -- no torch types
+cross the boundary.  There is NO fallback: if the shared library is missing or a tensor is not on a
+CUDA device the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int, c_int64, c_uint64, c_void_p
+
+import numpy as np
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbufferx_b200.so")
+
+SYMBOLS = [
+    "bx_last_error", "bx_version", "bx_device_sm_count", "bx_fps", "bx_radius_estimate", "bx_permute_cloud",
+    "bx_select_patches", "bx_ball_query", "bx_lrf", "bx_spt_pnt", "bx_conv_layer", "bx_pool_desc", "bx_mutual_nn",
+    "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine",
+]
+
+GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL = 0, 1, 2, 3
+RADIUS_BINS = 8192
+
+_lib = None
+
+
+class BufferXError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load the CUDA library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BufferXError(
+            f"{LIB_PATH} not found: build it with `python buffer-x_b200/csrc/build.py` "
+            "(or __graft_entry__.build()); bufferx_b200 has no CPU / eager fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    missing = [s for s in SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise BufferXError(f"{LIB_PATH} lacks symbols {missing}")
+    lib.bx_last_error.restype = ctypes.c_char_p
+    lib.bx_ransac_workspace_bytes.restype = c_int64
+    lib.bx_ransac_workspace_bytes.argtypes = [c_int]
+    P = c_void_p
+    lib.bx_fps.argtypes = [P, P, c_int, c_int, P, P, P]
+    lib.bx_radius_estimate.argtypes = [P, c_int, P, c_int, c_int64, P, c_int, c_double, P, P, P, P, P]
+    lib.bx_permute_cloud.argtypes = [P, P, c_int, P, P]
+    lib.bx_select_patches.argtypes = [P, c_int, P, c_int, c_float, P, c_int, P, P, P]
+    lib.bx_ball_query.argtypes = [P, c_int, P, c_int, c_float, c_int, P, P]
+    lib.bx_lrf.argtypes = [P, c_int, c_int, c_float, P, c_int, P, P, P, P]
+    lib.bx_spt_pnt.argtypes = [P, c_int, c_int, P, c_int, c_int, P, c_float, c_int, P, P, P, P, P, P]
+    lib.bx_conv_layer.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
+    lib.bx_pool_desc.argtypes = [P, c_int, c_int, c_int, P, P, P, P, P, P, P]
+    lib.bx_mutual_nn.argtypes = [P, c_int, P, c_int, c_int, P, P, P, P, P, P, P]
+    lib.bx_hypotheses.argtypes = [P, c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P]
+    lib.bx_consensus.argtypes = [P, P, P, P, P, c_int, c_int, c_float, P, P, P, P, P]
+    lib.bx_ransac.argtypes = [P, P, P, P, c_int, c_double, c_double, c_double, c_int, c_uint64, P, P, P]
+    lib.bx_refine.argtypes = [P, P, P, c_int, P, c_float, P, P, P]
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise BufferXError(f"{what} failed ({rc}): {load_library().bx_last_error().decode()}")
+
+
+def _dp(t, dtype=None, name="tensor"):
+    """device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise BufferXError(f"{name}: expected a CUDA tensor (bufferx_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise BufferXError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise BufferXError(f"{name}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+F32, I32 = torch.float32, torch.int32
+
+
+# --------------------------------------------------------------------------- #
+def sm_count() -> int:
+    return int(load_library().bx_device_sm_count())
+
+
+def fps(xyz: torch.Tensor, offsets, npoint: int, want_kpts=True):
+    """xyz [sumN,3] f32 cuda; offsets: host sequence of B+1 ints.  Returns idx [B,npoint] i32, kpts [B,npoint,3]."""
+    lib = load_library()
+    off = np.ascontiguousarray(offsets, dtype=np.int32)
+    B = len(off) - 1
+    idx = torch.empty((B, npoint), dtype=I32, device=xyz.device)
+    kp = torch.empty((B, npoint, 3), dtype=F32, device=xyz.device) if want_kpts else None
+    _check(lib.bx_fps(_dp(xyz, F32, "xyz"), off.ctypes.data_as(c_void_p), B, npoint, _dp(idx), _dp(kp), _stream()), "bx_fps")
+    return idx, kp
+
+
+_round_tables = {}
+
+
+def radius_round_table(device) -> torch.Tensor:
+    """round(5*m/8192, 2) for every radius the reference's bisection can probe (models/BUFFERX.py:694)."""
+    key = str(device)
+    if key not in _round_tables:
+        tab = np.array([round(5.0 * m / RADIUS_BINS, 2) for m in range(RADIUS_BINS + 1)], dtype=np.float32)
+        _round_tables[key] = torch.from_numpy(tab).to(device)
+    return _round_tables[key]
+
+
+def radius_estimate(kpts: torch.Tensor, pts: torch.Tensor, thresholds, denom=None, tolerance=0.01, hist=None):
+    """kpts [Kr,3], pts [N,3] (the larger cloud and its key-points).  Returns (r [n_thr] f32 device, m [n_thr] i32 device)."""
+    lib = load_library()
+    th = np.ascontiguousarray(thresholds, dtype=np.float64)
+    Kr, N = kpts.shape[0], pts.shape[0]
+    if hist is None:
+        hist = torch.empty(RADIUS_BINS + 2, dtype=I32, device=pts.device)
+    out_r = torch.empty(len(th), dtype=F32, device=pts.device)
+    out_m = torch.empty(len(th), dtype=I32, device=pts.device)
+    denom = int(N) * int(Kr) if denom is None else int(denom)
+    _check(lib.bx_radius_estimate(_dp(kpts, F32, "kpts"), Kr, _dp(pts, F32, "pts"), N, denom, th.ctypes.data_as(c_void_p),
+                                  len(th), float(tolerance), _dp(radius_round_table(pts.device)), _dp(hist), _dp(out_r),
+                                  _dp(out_m), _stream()), "bx_radius_estimate")
+    return out_r, out_m, hist
+
+
+def permute_cloud(pts: torch.Tensor, perm: torch.Tensor | None, out4: torch.Tensor | None = None):
+    N = pts.shape[0]
+    if out4 is None:
+        out4 = torch.empty((N, 4), dtype=F32, device=pts.device)
+    _check(load_library().bx_permute_cloud(_dp(pts, F32, "pts"), _dp(perm, I32, "perm"), N, _dp(out4), _stream()), "bx_permute_cloud")
+    return out4
+
+
+def select_patches(pts4: torch.Tensor, kpts: torch.Tensor, radius, P: int, want_idx=False, patches=None):
+    """radius: python float or a 1-element CUDA f32 tensor (device-side radius, no sync)."""
+    K, N = kpts.shape[0], pts4.shape[0]
+    if patches is None:
+        patches = torch.empty((K, P, 3), dtype=F32, device=pts4.device)
+    idx = torch.empty((K, P), dtype=I32, device=pts4.device) if want_idx else None
+    rv, rp = (0.0, _dp(radius, F32, "radius")) if isinstance(radius, torch.Tensor) else (float(radius), None)
+    _check(load_library().bx_select_patches(_dp(pts4, F32, "pts4"), N, _dp(kpts, F32, "kpts"), K, rv, rp, P, _dp(idx), _dp(patches), _stream()),
+           "bx_select_patches")
+    return patches, idx
+
+
+def ball_query(xyz: torch.Tensor, qry: torch.Tensor, radius: float, nsample: int):
+    idx = torch.empty((qry.shape[0], nsample), dtype=I32, device=xyz.device)
+    _check(load_library().bx_ball_query(_dp(xyz, F32, "xyz"), xyz.shape[0], _dp(qry, F32, "qry"), qry.shape[0], float(radius), nsample,
+                                        _dp(idx), _stream()), "bx_ball_query")
+    return idx
+
+
+def lrf(patches: torch.Tensor, des_r, aligned: bool, delta=None):
+    K, P, _ = patches.shape
+    dev = patches.device
+    if delta is None:
+        delta = torch.empty_like(patches)
+    Rt = torch.empty((K, 3, 3), dtype=F32, device=dev)
+    ra = torch.empty((K, 3), dtype=F32, device=dev)
+    rv, rp = (0.0, _dp(des_r, F32, "des_r")) if isinstance(des_r, torch.Tensor) else (float(des_r), None)
+    _check(load_library().bx_lrf(_dp(patches, F32, "patches"), K, P, rv, rp, int(bool(aligned)), _dp(delta), _dp(Rt), _dp(ra), _stream()), "bx_lrf")
+    return delta, Rt, ra
+
+
+def spt_pnt(delta, voxels, rot, voxel_r: float, nv: int, w, b, azi_n: int, debug=False, feat=None):
+    K, P, _ = delta.shape
+    V = voxels.shape[0]
+    dev = delta.device
+    if feat is None:
+        feat = torch.empty((K, 16, V), dtype=F32, device=dev)
+    vidx = torch.empty((K, V, nv), dtype=I32, device=dev) if debug else None
+    inv = torch.empty((K, V, nv, 3), dtype=F32, device=dev) if debug else None
+    _check(load_library().bx_spt_pnt(_dp(delta, F32, "delta"), K, P, _dp(voxels, F32), V, azi_n, _dp(rot, F32), float(voxel_r), nv,
+                                     _dp(w, F32), _dp(b, F32), _dp(feat), _dp(vidx), _dp(inv), _stream()), "bx_spt_pnt")
+    return (feat, vidx, inv) if debug else feat
+
+
+def conv_layer(geom, x, w, bias, out, n, Cin, Cout, D, H, W, kd, kh, kw, relu, d_n=None, equi_s=None, equi_t=None,
+               s_mids=None, t_mids=None):
+    _check(load_library().bx_conv_layer(geom, _dp(x, F32, "x"), _dp(w, F32, "w"), _dp(bias, F32, "bias"), _dp(out, F32, "out"), int(n),
+                                        _dp(d_n, I32, "d_n"), Cin, Cout, D, H, W, kd, kh, kw, int(bool(relu)), _dp(equi_s, F32), _dp(equi_t, F32),
+                                        _dp(s_mids, I32), _dp(t_mids, I32), _stream()), "bx_conv_layer")
+    return out
+
+
+def pool_desc(x, w1, b1, w2, b2, desc=None, equi=None):
+    K, C = x.shape[0], x.shape[1]
+    S = x.numel() // max(K * C, 1) if K > 0 else 140
+    dev = x.device
+    if desc is None:
+        desc = torch.empty((K, C), dtype=F32, device=dev)
+    if equi is None:
+        equi = torch.empty_like(x)
+    _check(load_library().bx_pool_desc(_dp(x, F32, "x"), K, C, S, _dp(w1, F32), _dp(b1, F32), _dp(w2, F32), _dp(b2, F32), _dp(desc), _dp(equi), _stream()),
+           "bx_pool_desc")
+    return desc, equi
+
+
+def mutual_nn(a, b, want_nn=False):
+    Ka, Kb, C = a.shape[0], b.shape[0], a.shape[1]
+    dev = a.device
+    keys = torch.empty(Ka + Kb + 1, dtype=torch.int64, device=dev)
+    s = torch.empty(max(Ka, 1), dtype=I32, device=dev)
+    t = torch.empty(max(Ka, 1), dtype=I32, device=dev)
+    dM = torch.zeros(1, dtype=I32, device=dev)
+    snn = torch.empty(max(Ka, 1), dtype=I32, device=dev) if want_nn else None
+    tnn = torch.empty(max(Kb, 1), dtype=I32, device=dev) if want_nn else None
+    _check(load_library().bx_mutual_nn(_dp(a, F32, "a"), Ka, _dp(b, F32, "b"), Kb, C, _dp(keys), _dp(s), _dp(t), _dp(dM), _dp(snn), _dp(tnn), _stream()),
+           "bx_mutual_nn")
+    return s, t, dM, snn, tnn
+
+
+def hypotheses(logits, azi_n, kpts_s, kpts_t, Rt_s, Rt_t, s_mids, t_mids, d_M, maxM, d_off, d_off_out, ind_out, R_acc, t_acc,
+               ss_acc, tt_acc):
+    _check(load_library().bx_hypotheses(_dp(logits, F32), azi_n, _dp(kpts_s, F32), _dp(kpts_t, F32), _dp(Rt_s, F32), _dp(Rt_t, F32), _dp(s_mids, I32),
+                                        _dp(t_mids, I32), _dp(d_M, I32), int(maxM), _dp(d_off, I32), _dp(d_off_out, I32), _dp(ind_out, F32),
+                                        _dp(R_acc, F32), _dp(t_acc, F32), _dp(ss_acc, F32), _dp(tt_acc, F32), _stream()), "bx_hypotheses")
+
+
+def consensus(ss, tt, R, t, d_Mc, maxMc, azi_n, inlier_th):
+    dev = ss.device
+    counts = torch.empty(max(maxMc, 1), dtype=I32, device=dev)
+    ind = torch.empty(max(maxMc, 1), dtype=I32, device=dev)
+    dI = torch.zeros(1, dtype=I32, device=dev)
+    dbest = torch.zeros(1, dtype=I32, device=dev)
+    _check(load_library().bx_consensus(_dp(ss, F32), _dp(tt, F32), _dp(R, F32), _dp(t, F32), _dp(d_Mc, I32), int(maxMc), azi_n, float(inlier_th),
+                                       _dp(counts), _dp(ind), _dp(dI), _dp(dbest), _stream()), "bx_consensus")
+    return ind, dI, dbest, counts
+
+
+def ransac_workspace(max_iter, device):
+    n = int(load_library().bx_ransac_workspace_bytes(int(max_iter)))
+    return torch.empty((n + 7) // 8, dtype=torch.int64, device=device)
+
+
+def ransac(ss, tt, inlier_ind, d_I, maxI, dist_th, similar_th, confidence, max_iter, seed, workspace=None, result=None):
+    """result: 18-element float64 CUDA tensor = T (16 doubles) + {num_inliers, best_itr, iters_run, 0} as int32 pairs."""
+    dev = ss.device
+    if workspace is None:
+        workspace = ransac_workspace(max_iter, dev)
+    if result is None:
+        result = torch.empty(18, dtype=torch.float64, device=dev)
+    _check(load_library().bx_ransac(_dp(ss, F32), _dp(tt, F32), _dp(inlier_ind, I32), _dp(d_I, I32), int(maxI), float(dist_th), float(similar_th),
+                                    float(confidence), int(max_iter), int(seed) & 0xFFFFFFFFFFFFFFFF, _dp(workspace), _dp(result), _stream()),
+           "bx_ransac")
+    return result
+
+
+def decode_ransac_result(result_cpu: torch.Tensor):
+    T = result_cpu[:16].reshape(4, 4).numpy().copy()
+    ints = result_cpu[16:18].numpy().view(np.int32)
+    return T, int(ints[0]), int(ints[1]), int(ints[2])
+
+
+def refine(ss, tt, d_n, maxn, T_in, dist_th, T_out=None, d_rounds=None):
+    dev = ss.device
+    if T_out is None:
+        T_out = torch.empty(16, dtype=F32, device=dev)
+    if d_rounds is None:
+        d_rounds = torch.zeros(1, dtype=I32, device=dev)
+    _check(load_library().bx_refine(_dp(ss, F32), _dp(tt, F32), _dp(d_n, I32), int(maxn), _dp(T_in, torch.float64, "T_in"), float(dist_th), _dp(T_out),
+                                    _dp(d_rounds), _stream()), "bx_refine")
+    return T_out, d_rounds

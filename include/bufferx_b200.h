@@ -1,0 +1,163 @@
+/*
+ * bufferx_b200.h -- C-ABI of the B200-native (sm_100a) BUFFER-X per-pair registration hot path.
+ *
+ * Boundary contract
+ *   - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer unless the
+ *     parameter name starts with `h_`.  No ownership transfer: the caller allocates every input,
+ *     output and workspace buffer (PyTorch does, in the host mirror buffer-x_b200/ops.py).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Every call only
+ *     ENQUEUES work; none synchronises the host.  Data-dependent sizes (number of mutual matches,
+ *     consensus inliers, RANSAC early stop) live in device memory as int32 counters so that a
+ *     whole pair can be enqueued without a host round trip.
+ *   - Return value: 0 = ok, negative = error (BX_ERR_*); bx_last_error() gives the message for
+ *     the calling thread.
+ *   - Layouts are row-major, fp32 / int32 unless stated.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to /root/reference;
+ * third-party ops that the reference calls but does not vendor are named with their package).
+ * The in-tree precedent for this ABI style is the reference's dead CPython modules
+ * cpp_wrappers/cpp_neighbors/wrapper.cpp:58-239 and cpp_wrappers/cpp_subsampling/wrapper.cpp:631-859
+ * (C-contiguous float32/int32 arrays in, arrays out, error on bad shapes).
+ */
+#ifndef BUFFERX_B200_H_
+#define BUFFERX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BX_OK 0
+#define BX_ERR_INVALID_ARG (-1)
+#define BX_ERR_CUDA (-2)
+#define BX_ERR_UNSUPPORTED (-3)
+
+#define BX_RADIUS_BINS 8192 /* candidate radii r_m = 5*m/8192 probed by the reference's bisection */
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char *bx_last_error(void);
+int bx_version(void);          /* 10000*major + 100*minor + patch */
+int bx_device_sm_count(void);  /* SM count of the current device (148 on B200), <0 on error */
+
+/* ---- a1: farthest point sampling ------------------------------------------------------------
+ * Replaces pointnet2_ops.furthest_point_sample + gather_operation
+ * (models/BUFFERX.py:286-290, 338-346).  B clouds stored back to back in `xyz` ([sum N,3]);
+ * `h_offsets` (HOST, B+1 ints) gives each cloud's first point.  Starts at index 0, skips
+ * candidates with |p|^2 <= 1e-3, tie rule of the upstream 512-thread block reduction.
+ * One thread-block cluster per cloud; the cloud lives in registers across the cluster.
+ * idx: [B,npoint] int32 (index inside the cloud); kpts: [B,npoint,3] (may be NULL).
+ * Limit: N <= 131072 per cloud. */
+int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint, int32_t *idx, float *kpts, void *stream);
+
+/* ---- a2: density-aware radius estimation ----------------------------------------------------
+ * Replaces density_aware_radius_estimation + squared_cdist (models/BUFFERX.py:610-696) without
+ * the [Kr,N] distance matrix and without host syncs: one pass builds the histogram of d2 over
+ * the 8192 radii the bisection can probe, then the bisection runs on the device.
+ * hist: [BX_RADIUS_BINS+2] uint32 workspace (zeroed by the call).
+ * round_table: [BX_RADIUS_BINS+1] fp32, round(5*m/8192, 2) as computed by Python on the host.
+ * thresholds: HOST array of n_thr percentages; out_r: [n_thr] fp32 radii; out_m: [n_thr] int32 (may be NULL).
+ * denom = (original cloud size) * Kr as in the reference. */
+int bx_radius_estimate(const float *kpts, int Kr, const float *pts, int N, int64_t denom,
+                       const double *h_thresholds, int n_thr, double tolerance, const float *round_table,
+                       uint32_t *hist, float *out_r, int32_t *out_m, void *stream);
+
+/* ---- a3: order-preserving radius-neighbour patch gathering ----------------------------------
+ * Replaces MiniSpinNet.select_patches (models/patch_embedder.py:92-120) =
+ * pointnet2_ops.ball_query + grouping_operation + the centre fix-up, and (as the GPU
+ * counterpart) the reference's CPU radius search cpp_wrappers/cpp_neighbors.
+ * bx_permute_cloud: out4[i] = (pts[perm[i]], 0) as float4 (perm may be NULL = identity).
+ * bx_select_patches: for each key-point the FIRST P points of the permuted cloud (index order)
+ * with d2 < r*r; r = *d_radius if d_radius != NULL else `radius`.
+ * idx: [K,P] int32 raw ball-query indices (may be NULL); patches: [K,P,3]. */
+int bx_permute_cloud(const float *pts, const int32_t *perm, int N, float *out4, void *stream);
+int bx_select_patches(const float *pts4, int N, const float *kpts, int K, float radius, const float *d_radius,
+                      int P, int32_t *idx, float *patches, void *stream);
+
+/* Plain ordered ball query (pointnet2_ops.ball_query; utils/common.py:442): xyz [n,3] packed. */
+int bx_ball_query(const float *xyz, int n, const float *qry, int m, float radius, int nsample, int32_t *idx,
+                  void *stream);
+
+/* ---- a4+a5: local reference frame + normalisation -------------------------------------------
+ * Replaces MiniSpinNet.axis_align / normalize (models/patch_embedder.py:122-148, 167-170),
+ * cal_Z_axis (utils/common.py:709-726, torch_batch_svd) and RodsRotatFormula (:501-525).
+ * delta: [K,P,3]; Rt: [K,3,3] (the reference's returned "R"); rand_axis: [K,3]. */
+int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r, int aligned, float *delta,
+           float *Rt, float *rand_axis, void *stream);
+
+/* ---- a6+a7: spherical-voxel transformer + point layer ---------------------------------------
+ * Replaces MiniSpinNet.SPT (models/patch_embedder.py:150-165: get_voxel_coordinate,
+ * sphere_query, var_to_invar of utils/common.py:422-498) fused with pnt_layer + max-pool
+ * (patch_embedder.py:26-30, 73-77); the [K,420,10,3] tensor is never written.
+ * voxels: [V,3] (V = rad_n*ele_n*azi_n, azimuth fastest); rot: [azi_n,2] (cos,sin of -a*2pi/azi_n);
+ * w: [16,3], b: [16] = 1x1 conv with BatchNorm folded in.  feat: [K,16,V].
+ * dbg_vidx [K,V,nv] / dbg_inv [K,V,nv,3] are optional parity taps (NULL in production). */
+int bx_spt_pnt(const float *delta, int K, int P, const float *voxels, int V, int azi_n, const float *rot,
+               float voxel_r, int nv, const float *w, const float *b, float *feat, int32_t *dbg_vidx,
+               float *dbg_inv, void *stream);
+
+/* ---- a8/a11: convolution stacks -------------------------------------------------------------
+ * One implicit-GEMM kernel serves every conv layer of Cylindrical_Net (models/patchnet.py:16-84,
+ * circular-azimuth / zero-elevation padding of utils/common.py:265-310) and CostNet
+ * (models/patchnet.py:151-210, un-padded).  Weights are [taps][Cin][Cout] with BatchNorm folded.
+ * geom: BX_GEOM_*; in: [n][Cin][S_in]; out: [n][Cout][S_out]; n = *d_n if d_n != NULL else n. */
+#define BX_GEOM_CYL3D 0    /* in [C,3,7,20] -> out [C,7,20], taps 27 */
+#define BX_GEOM_CYL2D 1    /* in [C,7,20]   -> out [C,7,20], taps 9  */
+#define BX_GEOM_VALID3D 2  /* in [C,D,H,W]  -> out [C,D-kd+1,H-kh+1,W-kw+1] */
+#define BX_GEOM_COSTVOL 3  /* VALID3D 3x3x3 whose input is the on-the-fly cost volume (models/BUFFERX.py:51-65) */
+int bx_conv_layer(int geom, const float *in, const float *w, const float *bias, float *out, int n, const int32_t *d_n,
+                  int Cin, int Cout, int D, int H, int W, int kd, int kh, int kw, int relu,
+                  const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
+                  void *stream);
+
+/* ---- a9: attention pooling + normalisation --------------------------------------------------
+ * Replaces pool_layer / avg-pool / F.normalize (models/patch_embedder.py:32-39, 80-83).
+ * x: [K,32,S]; w1 [32,16] (in-major), b1 [16], w2 [16], b2 [1] (BatchNorm folded);
+ * desc: [K,32]; equi: [K,32,S]. */
+int bx_pool_desc(const float *x, int K, int C, int S, const float *w1, const float *b1, const float *w2,
+                 const float *b2, float *desc, float *equi, void *stream);
+
+/* ---- a10: mutual nearest-neighbour matching -------------------------------------------------
+ * Replaces BufferX.mutual_matching (models/BUFFERX.py:469-496) -> knn_cuda.KNN(k=1) both ways.
+ * keys: [Ka+Kb] uint64 workspace.  s_mids/t_mids: [Ka] int32 (ascending s); d_M: [1] int32;
+ * snn [Ka] / tnn [Kb] optional. */
+int bx_mutual_nn(const float *a, int Ka, const float *b, int Kb, int C, unsigned long long *keys, int32_t *s_mids,
+                 int32_t *t_mids, int32_t *d_M, int32_t *snn, int32_t *tnn, void *stream);
+
+/* ---- a11 tail + a12: soft arg-max and pose hypotheses ---------------------------------------
+ * Replaces softmax/expectation of CostVolume.forward (models/BUFFERX.py:66-69) and the hypothesis
+ * build (:382-389, kornia axis_angle_to_rotation_matrix).  logits: [maxM, azi_n].
+ * Appends M = *d_M rows at row offset *d_off of the accumulators and writes *d_off_out = off + M. */
+int bx_hypotheses(const float *logits, int azi_n, const float *kpts_s, const float *kpts_t, const float *Rt_s,
+                  const float *Rt_t, const int32_t *s_mids, const int32_t *t_mids, const int32_t *d_M, int maxM,
+                  const int32_t *d_off, int32_t *d_off_out, float *ind_out, float *R_acc, float *t_acc,
+                  float *ss_acc, float *tt_acc, void *stream);
+
+/* ---- a13: cross-scale consensus -------------------------------------------------------------
+ * Replaces models/BUFFERX.py:404-417.  Mc = *d_Mc (<= maxMc).  counts: [maxMc] int32 workspace;
+ * inlier_ind: [maxMc] int32 ascending; d_I: [1]; d_best: [1]. */
+int bx_consensus(const float *ss, const float *tt, const float *R, const float *t, const int32_t *d_Mc, int maxMc,
+                 int azi_n, float inlier_th, int32_t *counts, int32_t *inlier_ind, int32_t *d_I, int32_t *d_best,
+                 void *stream);
+
+/* ---- a14: RANSAC ----------------------------------------------------------------------------
+ * Replaces PoseEstimator._estimate_ransac (models/pose_estimator.py:84-117) -> Open3D 0.18
+ * registration_ransac_based_on_correspondence (3-point, EdgeLength + Distance checkers,
+ * confidence early stop).  Sampling is an explicit function of (seed, iteration): Philox4x32-10.
+ * workspace: bx_ransac_workspace_bytes(max_iter) bytes.  result: 16 doubles T (row-major 4x4)
+ * followed by int32 {num_inliers, best_itr, iters_run, reserved} = 144 bytes. */
+int64_t bx_ransac_workspace_bytes(int max_iter);
+int bx_ransac(const float *ss, const float *tt, const int32_t *inlier_ind, const int32_t *d_I, int maxI,
+              double dist_th, double similar_th, double confidence, int max_iter, uint64_t seed, void *workspace,
+              void *result, void *stream);
+
+/* ---- a15: post refinement -------------------------------------------------------------------
+ * Replaces BufferX.post_refinement + rigid_transform_3d (models/BUFFERX.py:522-603).
+ * T_in: 16 doubles (the RANSAC result) cast to fp32 like the reference; T_out: 16 fp32. */
+int bx_refine(const float *ss, const float *tt, const int32_t *d_n, int maxn, const double *T_in, float dist_th,
+              float *T_out, int32_t *d_rounds, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BUFFERX_B200_H_ */
