@@ -5,6 +5,7 @@
 #include "bx_common.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_bx_launches = 0;
 
 void bx_set_error(const char *fmt, ...) {
     va_list ap;
@@ -16,6 +17,8 @@ void bx_set_error(const char *fmt, ...) {
 BX_API const char *bx_last_error(void) { return g_err; }
 
 BX_API int bx_version(void) { return 100; }
+
+BX_API unsigned long long bx_launch_count(void) { return g_bx_launches; }
 
 BX_API int bx_device_sm_count(void) {
     int dev = 0, n = 0;

@@ -13,6 +13,7 @@
 #define BX_API extern "C" __attribute__((visibility("default")))
 
 void bx_set_error(const char *fmt, ...);
+extern unsigned long long g_bx_launches;  // kernels launched by this library since load (host-side count)
 
 #define BX_REQUIRE(cond, ...)            \
     do {                                 \
@@ -33,6 +34,7 @@ void bx_set_error(const char *fmt, ...);
 
 #define BX_LAUNCH_CHECK()                                                                      \
     do {                                                                                       \
+        ++g_bx_launches;                                                                       \
         cudaError_t _e = cudaGetLastError();                                                   \
         if (_e != cudaSuccess) {                                                               \
             bx_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

@@ -10,7 +10,8 @@
 //
 // Result contract (bit-exact with oracle/c/bx_oracle.c::bxo_fps): idx[0] = 0; candidates with
 // |p|^2 <= 1e-3 (double compare) never win; ties are broken like the upstream 512-thread block
-// reduction: maximise (value, -(k mod bs), -k) with bs = min(512, 2^floor(log2 N)).
+// reduction (each tree step keeps the lower position, so the smallest BIT-REVERSED slot wins):
+// maximise (value, -bitrev(k mod bs), -k) with bs = min(512, 2^floor(log2 N)).
 // Compiled with -fmad=false: d = ((dx*dx)+(dy*dy))+(dz*dz) exactly.
 #include <cooperative_groups.h>
 
@@ -109,7 +110,8 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
                 const float d2 = fminf(d, tmp[s]);
                 tmp[s] = d2;
                 const int k = s * stride + base;
-                const uint32_t rk = (uint32_t)(k & (bs - 1)) * (uint32_t)cpb + (uint32_t)(k >> log2bs);
+                const uint32_t tr = log2bs ? (__brev((uint32_t)(k & (bs - 1))) >> (32 - log2bs)) : 0u;
+                const uint32_t rk = tr * (uint32_t)cpb + (uint32_t)(k >> log2bs);
                 const uint32_t hi = __float_as_uint(d2), lo = ~rk;
                 if (hi > best.hi || (hi == best.hi && lo > best.lo)) {
                     best.hi = hi; best.lo = lo; best.x = px[s]; best.y = py[s]; best.z = pz[s];
@@ -150,7 +152,9 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
             int k = 0;
             if (cb.hi != 0u || cb.lo != 0u) {
                 const uint32_t rk = ~cb.lo;
-                k = (int)((rk % (uint32_t)cpb) << log2bs) + (int)(rk / (uint32_t)cpb);
+                const uint32_t tr = rk / (uint32_t)cpb;
+                const uint32_t t = log2bs ? (__brev(tr) >> (32 - log2bs)) : 0u;
+                k = (int)((rk % (uint32_t)cpb) << log2bs) + (int)t;
             }
             idx[j] = k;
             if (kp) { kp[3 * j] = ox; kp[3 * j + 1] = oy; kp[3 * j + 2] = oz; }
@@ -176,6 +180,7 @@ int launch_fps(const float *xyz, const FpsOffsets off, int B, int CL, int npoint
     cfg.attrs = at;
     cfg.numAttrs = 1;
     BX_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, off, npoint, idx, kpts));
+    ++g_bx_launches;
     return BX_OK;
 }
 

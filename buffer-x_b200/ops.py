@@ -18,7 +18,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libbufferx_b200.so")
 
 SYMBOLS = [
-    "bx_last_error", "bx_version", "bx_device_sm_count", "bx_fps", "bx_radius_estimate", "bx_permute_cloud",
+    "bx_last_error", "bx_version", "bx_device_sm_count", "bx_launch_count", "bx_fps", "bx_radius_estimate", "bx_permute_cloud",
     "bx_select_patches", "bx_ball_query", "bx_lrf", "bx_spt_pnt", "bx_conv_layer", "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine",
 ]
@@ -47,6 +47,7 @@ def load_library():
     if missing:
         raise BufferXError(f"{LIB_PATH} lacks symbols {missing}")
     lib.bx_last_error.restype = ctypes.c_char_p
+    lib.bx_launch_count.restype = ctypes.c_ulonglong
     lib.bx_ransac_workspace_bytes.restype = c_int64
     lib.bx_ransac_workspace_bytes.argtypes = [c_int]
     P = c_void_p
@@ -96,6 +97,34 @@ F32, I32 = torch.float32, torch.int32
 # --------------------------------------------------------------------------- #
 def sm_count() -> int:
     return int(load_library().bx_device_sm_count())
+
+
+def launch_count() -> int:
+    """Kernels launched by libbufferx_b200.so since it was loaded (host-side counter)."""
+    return int(load_library().bx_launch_count())
+
+
+class Profiler:
+    """Optional CUDA-event brackets around selected C-ABI calls (bench.py roofline figures).
+    Events are recorded on the current stream -- the stream the kernels are launched on."""
+
+    def __init__(self):
+        self.spans = {}   # name -> list of (start_event, end_event, work)
+
+    def span(self, name, work=0.0):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.spans.setdefault(name, []).append((a, b, work))
+        return a, b
+
+    def summary(self):
+        out = {}
+        for name, lst in self.spans.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in lst)
+            out[name] = dict(launches=len(lst), ms=ms, work=sum(w for _, _, w in lst))
+        return out
+
+
+profiler = None  # set to a Profiler() to record spans
 
 
 def fps(xyz: torch.Tensor, offsets, npoint: int, want_kpts=True):
@@ -152,8 +181,13 @@ def select_patches(pts4: torch.Tensor, kpts: torch.Tensor, radius, P: int, want_
         patches = torch.empty((K, P, 3), dtype=F32, device=pts4.device)
     idx = torch.empty((K, P), dtype=I32, device=pts4.device) if want_idx else None
     rv, rp = (0.0, _dp(radius, F32, "radius")) if isinstance(radius, torch.Tensor) else (float(radius), None)
+    ev = profiler.span("select_patches", 16.0 * N + 12.0 * K + K * P * (12.0 + (4.0 if want_idx else 0.0))) if profiler else None
+    if ev:
+        ev[0].record()
     _check(load_library().bx_select_patches(_dp(pts4, F32, "pts4"), N, _dp(kpts, F32, "kpts"), K, rv, rp, P, _dp(idx), _dp(patches), _stream()),
            "bx_select_patches")
+    if ev:
+        ev[1].record()
     return patches, idx
 
 
@@ -191,9 +225,19 @@ def spt_pnt(delta, voxels, rot, voxel_r: float, nv: int, w, b, azi_n: int, debug
 
 def conv_layer(geom, x, w, bias, out, n, Cin, Cout, D, H, W, kd, kh, kw, relu, d_n=None, equi_s=None, equi_t=None,
                s_mids=None, t_mids=None):
+    ev = None
+    if profiler is not None and d_n is None:
+        OD, OH, OW = (1, 7, 20) if geom in (GEOM_CYL3D, GEOM_CYL2D) else (D - kd + 1, H - kh + 1, W - kw + 1)
+        ev = profiler.span("conv_desc", 2.0 * n * OD * OH * OW * Cout * Cin * kd * kh * kw)
+        ev[0].record()
+    elif profiler is not None:
+        ev = profiler.span("conv_cost", 0.0)
+        ev[0].record()
     _check(load_library().bx_conv_layer(geom, _dp(x, F32, "x"), _dp(w, F32, "w"), _dp(bias, F32, "bias"), _dp(out, F32, "out"), int(n),
                                         _dp(d_n, I32, "d_n"), Cin, Cout, D, H, W, kd, kh, kw, int(bool(relu)), _dp(equi_s, F32), _dp(equi_t, F32),
                                         _dp(s_mids, I32), _dp(t_mids, I32), _stream()), "bx_conv_layer")
+    if ev:
+        ev[1].record()
     return out
 
 
@@ -254,9 +298,14 @@ def ransac(ss, tt, inlier_ind, d_I, maxI, dist_th, similar_th, confidence, max_i
         workspace = ransac_workspace(max_iter, dev)
     if result is None:
         result = torch.empty(18, dtype=torch.float64, device=dev)
+    ev = profiler.span("ransac", 0.0) if profiler else None
+    if ev:
+        ev[0].record()
     _check(load_library().bx_ransac(_dp(ss, F32), _dp(tt, F32), _dp(inlier_ind, I32), _dp(d_I, I32), int(maxI), float(dist_th), float(similar_th),
                                     float(confidence), int(max_iter), int(seed) & 0xFFFFFFFFFFFFFFFF, _dp(workspace), _dp(result), _stream()),
            "bx_ransac")
+    if ev:
+        ev[1].record()
     return result
 
 

@@ -246,3 +246,38 @@ def make_pair(name: str = "C2", seed: int = 0, n_src: int | None = None, n_tgt: 
         "sphericity": np.array([0.0], dtype=np.float32),
         "is_aligned_to_global_z": aligned,
     }
+
+
+def init_synthetic_weights(model, seed: int = 123, logit_gain: float = 4.0):
+    """Deterministic stand-in for the (unavailable offline) trained checkpoint.
+
+    Seeded He-uniform initialisation of every Conv layer (variance preserving through the ReLU stacks:
+    with torch's default init the signal decays below the biases after a few layers and every patch gets
+    the same descriptor), non-trivial BatchNorm running statistics (mean ~ N(0, 0.1), var ~ U(0.5, 1.5),
+    affine weight ~ U(0.5, 1.5), bias ~ N(0, 0.1)) so that BN folding is exercised, and a gain on
+    CostNet's last layer so that the soft arg-max is not degenerate.
+    """
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, (torch.nn.Conv2d, torch.nn.Conv3d)):
+                fan_in = mod.in_channels * int(np.prod(mod.kernel_size))
+                bound = math.sqrt(6.0 / fan_in)
+                mod.weight.copy_((torch.rand(mod.weight.shape, generator=g) * 2 - 1) * bound)
+                mod.bias.copy_((torch.rand(mod.bias.shape, generator=g) * 2 - 1) * 0.05)
+            elif isinstance(mod, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+                mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+                if mod.affine:
+                    mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+                    mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
+        last = model.Pose.conv.ops[27]
+        last.weight.mul_(logit_gain)
+        last.bias.mul_(logit_gain)
+    model.eval()
+    for m in model.modules():
+        if hasattr(m, "invalidate"):
+            m.invalidate()
+    return model

@@ -39,6 +39,7 @@ extern "C" {
 const char *bx_last_error(void);
 int bx_version(void);          /* 10000*major + 100*minor + patch */
 int bx_device_sm_count(void);  /* SM count of the current device (148 on B200), <0 on error */
+unsigned long long bx_launch_count(void); /* kernels launched by this library since it was loaded */
 
 /* ---- a1: farthest point sampling ------------------------------------------------------------
  * Replaces pointnet2_ops.furthest_point_sample + gather_operation

@@ -41,8 +41,10 @@
  *   idx[0] = 0; temp[k] = 1e10; each step: for every k with mag = x*x+y*y+z*z > 1e-3 (the
  *   comparison is done in double, the literal is a double): d = dx*dx+dy*dy+dz*dz,
  *   temp[k] = min(d, temp[k]); thread t of a block of `bs` threads keeps the FIRST strict
- *   maximum over k = t, t+bs, ...; the tree reduction keeps the LOWER slot on ties.  Hence
- *   the winner maximises (value, -(k mod bs), -k).  bs = min(512, 2^floor(log2 N)).
+ *   maximum over k = t, t+bs, ...; every step of the shared-memory tree (stride bs/2 ... 1) keeps
+ *   the lower position on ties, so across slots the winner is the one whose BIT-REVERSED slot
+ *   index is smallest (the stride-1 step decides on bit 0 last, i.e. with highest priority).
+ *   Hence the winner maximises (value, -bitrev(k mod bs), -k).  bs = min(512, 2^floor(log2 N)).
  *   A thread without candidates contributes (-1, index 0).
  * ------------------------------------------------------------------------------------------ */
 static int fps_block_size(int n) {
@@ -53,10 +55,18 @@ static int fps_block_size(int n) {
     return p;
 }
 
+static int bitrev(int t, int bits) {
+    int r = 0;
+    for (int b = 0; b < bits; ++b) r |= ((t >> b) & 1) << (bits - 1 - b);
+    return r;
+}
+
 BX_EXPORT int bxo_fps(const float *xyz, int n, int m, int32_t *idx) {
     if (m <= 0) return 0;
     if (n <= 0) return -1;
     const int bs = fps_block_size(n);
+    int bits = 0;
+    while ((1 << bits) < bs) ++bits;
     float *temp = (float *)malloc(sizeof(float) * (size_t)n);
     unsigned char *valid = (unsigned char *)malloc((size_t)n);
     if (!temp || !valid) return -2;
@@ -78,9 +88,9 @@ BX_EXPORT int bxo_fps(const float *xyz, int n, int m, int32_t *idx) {
             const float d = ((dx * dx) + (dy * dy)) + (dz * dz);
             const float d2 = d < temp[k] ? d : temp[k]; /* min(d, temp) */
             temp[k] = d2;
-            const int t = k % bs;
+            const int t = bitrev(k % bs, bits);
             /* k ascending: within one thread slot the first strict max wins; across slots the
-             * lower slot wins on ties */
+             * smaller bit-reversed slot wins on ties */
             if (d2 > best || (d2 == best && t < bestt)) {
                 best = d2;
                 besti = k;
@@ -484,7 +494,7 @@ BX_EXPORT int bxo_consensus(const float *ss, const float *tt, const float *R, co
     if (Mc <= 0) { if (best) *best = 0; return 0; }
     float *thr = (float *)malloc(sizeof(float) * (size_t)Mc);
     int32_t *cnt = (int32_t *)malloc(sizeof(int32_t) * (size_t)Mc);
-    const float pi_f = (float)M_PI;
+    const float pi_f = (float)3.14159265358979323846;
     for (int i = 0; i < Mc; ++i) {
         const float x = ss[3 * i], y = ss[3 * i + 1], z = ss[3 * i + 2];
         const float nrm = sqrtf(((x * x) + (y * y)) + (z * z));

@@ -446,8 +446,8 @@ def register_pair(sd, cfg, data, perms, ransac_seed=0, keep=False, timings=None)
         inlier_ind, best, counts = consensus(ss_cat.numpy(), tt_cat.numpy(), R_cat.numpy(), t_cat.numpy(), azi_n,
                                              cfg.match.inlier_th)
         _t("consensus", t0)
-        sc = dict(s_mids=s_m, t_mids=t_m, ind=ind.numpy(), R=R.numpy(), t=tr.numpy(), best=best,
-                  inlier_ind=inlier_ind, snn=snn, tnn=tnn, s=s, t=t)
+        sc = dict(s_mids=s_m, t_mids=t_m, ind=ind.numpy(), R=R.numpy(), t=tr.numpy(), best=best, counts=counts,
+                  inlier_ind=inlier_ind, snn=snn, tnn=tnn, src=s, tgt=t)
         aux["scales"].append(sc)
         if enable_early_exit and i == 0:
             t0 = time.perf_counter()

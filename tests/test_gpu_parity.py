@@ -1,0 +1,413 @@
+"""GPU parity: every CUDA stage against the CPU oracle on identical inputs, through the C-ABI
+(``bufferx_b200.ops`` -> ctypes -> libbufferx_b200.so).  Integer / index results must be bit-exact;
+floating point within the tolerance written next to each assert (descriptors 1e-4 rel, north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import bufferx_b200 as bx
+    bx.ops.load_library()
+    return torch.device("cuda:0")
+
+
+def cu(a, dev, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(dev).contiguous()
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------ a1
+@pytest.mark.parametrize("n,m,kind", [(300, 64, "dup"), (5000, 2000, "plain"), (20000, 2000, "plain"),
+                                      (20000, 300, "dup"), (40000, 200, "plain"), (70000, 128, "plain"),
+                                      (120000, 96, "plain")])
+def test_fps_bit_exact(dev, oracle, n, m, kind):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(n + m)
+    xyz = rng.uniform(-3, 3, size=(n, 3)).astype(np.float32)
+    if kind == "dup":                       # exact ties + candidates the |p|^2 <= 1e-3 rule must skip
+        xyz[n // 2:] = xyz[: n - n // 2]
+        xyz[5] = [0.01, 0.02, 0.01]
+        xyz[n - 1] = [0.0, 0.0, 0.0]
+    idx, kp = ops.fps(cu(xyz, dev), [0, n], m)
+    exp = oracle.fps(xyz, m)
+    got = idx[0].cpu().numpy()
+    assert (got == exp).all(), f"first mismatch at {np.flatnonzero(got != exp)[:5]}"
+    assert (kp[0].cpu().numpy() == xyz[exp]).all()
+
+
+def test_fps_two_clouds_one_launch(dev, oracle):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(7000, 3)).astype(np.float32)
+    b = rng.normal(size=(3000, 3)).astype(np.float32) * 2
+    idx, _ = ops.fps(cu(np.concatenate([a, b]), dev), [0, 7000, 10000], 500)
+    assert (idx[0].cpu().numpy() == oracle.fps(a, 500)).all() and (idx[1].cpu().numpy() == oracle.fps(b, 500)).all()
+
+
+# ------------------------------------------------------------------------------------------------ a2
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_radius_estimate_matches_oracle(dev, oracle, seed):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(seed)
+    n = [6000, 20000, 9000][seed]
+    pts = (rng.uniform(-3, 3, size=(n, 3)) * [1, 1, 0.4]).astype(np.float32)
+    kp = pts[oracle.fps(pts, 500)]
+    r, m, hist = ops.radius_estimate(cu(kp, dev), cu(pts, dev), [5, 2, 0.5])
+    cum = oracle.radius_hist(kp, pts)
+    assert (hist[:8193].cpu().numpy().astype(np.int64) == cum).all()      # cumulative histogram is bit-exact
+    exp = oracle.radius_estimation(pts[:1], kp[:1], pts, kp, [5, 2, 0.5], cum=cum)
+    assert np.allclose(r.cpu().numpy(), np.array(exp, dtype=np.float32), atol=0)
+
+
+# ------------------------------------------------------------------------------------------------ a3
+@pytest.mark.parametrize("radius,P", [(0.35, 64), (1.2, 512), (0.02, 32), (50.0, 128)])
+def test_select_patches_bit_exact(dev, oracle, radius, P):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(int(radius * 100) + P)
+    n, K = 9000, 300
+    pts = (rng.uniform(-3, 3, size=(n, 3)) * [1, 1, 0.3]).astype(np.float32)
+    perm = rng.permutation(n).astype(np.int32)
+    kp = pts[oracle.fps(pts, K)]
+    pts4 = ops.permute_cloud(cu(pts, dev), cu(perm, dev))
+    assert (pts4[:, :3].cpu().numpy() == pts[perm]).all()
+    pat, idx = ops.select_patches(pts4, cu(kp, dev), radius, P, want_idx=True)
+    eidx, epat = oracle.select_patches(pts, perm, kp, radius, P)
+    assert (idx.cpu().numpy() == eidx).all()
+    assert (pat.cpu().numpy() == epat).all()
+    # device-side radius gives the same result
+    pat2, _ = ops.select_patches(pts4, cu(kp, dev), torch.tensor([radius], dtype=torch.float32, device=dev), P)
+    assert (pat2.cpu().numpy() == epat).all()
+
+
+def test_ball_query_bit_exact(dev, oracle):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(9)
+    xyz = rng.uniform(-1, 1, size=(777, 3)).astype(np.float32)
+    q = np.concatenate([xyz[:40], [[9, 9, 9]]]).astype(np.float32)
+    idx = ops.ball_query(cu(xyz, dev), cu(q, dev), 0.3, 10)
+    assert (idx.cpu().numpy() == oracle.ball_query(xyz, q, 0.3, 10)[0]).all()
+
+
+# ------------------------------------------------------------------------------------------- a4+a5
+@pytest.mark.parametrize("aligned", [False, True])
+def test_lrf_bit_exact(dev, oracle, c1, aligned):
+    from bufferx_b200 import ops
+    patches = c1["res"][5]["scales"][0]["src"]["patches"]
+    des_r = c1["res"][5]["des_r"][0]
+    delta, Rt, ra = ops.lrf(cu(patches, dev), des_r, aligned)
+    ed, eR, era = oracle.lrf(patches, des_r, aligned)
+    assert (Rt.cpu().numpy() == eR).all(), f"R max diff {np.abs(Rt.cpu().numpy() - eR).max()}"
+    assert (ra.cpu().numpy() == era).all()
+    assert (delta.cpu().numpy() == ed).all()
+    if not aligned:       # sanity: R is a rotation taking the z-axis onto +z
+        R = Rt.cpu().numpy().astype(np.float64)
+        assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- a6+a7
+def test_spt_pnt(dev, oracle, c1):
+    import bufferx_b200 as bx
+    from bufferx_b200 import ops
+    aux = c1["res"][5]
+    delta = aux["scales"][0]["src"]["delta"]
+    model = c1["model"].to(dev)
+    prep = model.Desc.prepared(dev)
+    assert (prep["voxels"].cpu().numpy() == oracle.voxel_table()).all()
+    assert (prep["rot"].cpu().numpy() == oracle.derot_table()).all()
+    feat, vidx, inv = ops.spt_pnt(cu(delta, dev), prep["voxels"], prep["rot"], 0.8 / 3, 10, prep["w_pnt"], prep["b_pnt"], 20, debug=True)
+    einv, evidx = oracle.spt(delta)
+    assert (vidx.cpu().numpy() == evidx).all()                       # integer selection: bit-exact
+    assert (inv.cpu().numpy() == einv).all()                         # de-rotated samples: bit-exact
+    with torch.no_grad():
+        efeat = oracle.pnt_max(torch.from_numpy(einv), c1["sd"]).numpy()
+    assert np.abs(feat.cpu().numpy() - efeat).max() < 2e-6 * max(1.0, np.abs(efeat).max())   # folded BN: fp32 rounding only
+    model.cpu()
+
+
+# ------------------------------------------------------------------------------------------- a8+a9
+def test_cylindrical_net_and_pooling(dev, oracle, c1):
+    from bufferx_b200 import ops
+    aux = c1["res"][5]
+    s = aux["scales"][0]["src"]
+    model = c1["model"].to(dev)
+    K = s["feat"].shape[0]
+    x, _ = model.Desc.conv_net(cu(s["feat"].numpy(), dev).view(K, 16, 3, 7, 20))
+    ex = s["x"].numpy()
+    assert relerr(x.cpu().numpy(), ex) < 1e-4                        # 8 stacked fp32 convs vs torch CPU
+    prep = model.Desc.prepared(dev)
+    desc, equi = ops.pool_desc(cu(ex, dev), prep["w1"], prep["b1"], prep["w2"], prep["b2"])
+    assert np.abs(desc.cpu().numpy() - s["desc"].numpy()).max() < 1e-5
+    assert np.abs(equi.cpu().numpy() - s["equi"].numpy()).max() < 1e-5
+    model.cpu()
+
+
+# ---------------------------------------------------------------------------------------------- a10
+@pytest.mark.parametrize("Ka,Kb", [(256, 256), (1500, 1500), (70, 901)])
+def test_mutual_nn_bit_exact(dev, oracle, Ka, Kb):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(Ka + Kb)
+    a = rng.normal(size=(Ka, 32)).astype(np.float32)
+    b = rng.normal(size=(Kb, 32)).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    b[Kb // 2] = b[3]                                                # exact tie
+    a[5] = b[7]
+    s, t, dM, snn, tnn = ops.mutual_nn(cu(a, dev), cu(b, dev), want_nn=True)
+    es, et, esnn, etnn = oracle.mutual_nn(a, b)
+    M = int(dM.item())
+    assert (snn.cpu().numpy()[:Ka] == esnn).all() and (tnn.cpu().numpy()[:Kb] == etnn).all()
+    assert M == len(es) and (s[:M].cpu().numpy() == es).all() and (t[:M].cpu().numpy() == et).all()
+
+
+# ------------------------------------------------------------------------------------------ a11-a12
+def test_cost_volume_and_hypotheses(dev, oracle, c1):
+    from bufferx_b200 import ops
+    aux = c1["res"][5]
+    sc = aux["scales"][0]
+    model = c1["model"].to(dev)
+    K = sc["src"]["desc"].shape[0]
+    es, et = cu(sc["src"]["equi"].numpy(), dev), cu(sc["tgt"]["equi"].numpy(), dev)
+    sm, tm = cu(sc["s_mids"], dev, torch.int32), cu(sc["t_mids"], dev, torch.int32)
+    M = len(sc["s_mids"])
+    smp = torch.zeros(K, dtype=torch.int32, device=dev); smp[:M] = sm
+    tmp = torch.zeros(K, dtype=torch.int32, device=dev); tmp[:M] = tm
+    dM = torch.tensor([M], dtype=torch.int32, device=dev)
+    logits = model.Pose.logits(es, et, smp, tmp, dM, K)
+    cfg = c1["cfg"]
+    src_k = c1["data"]["src_fds_pcd"][aux["s_fps"][:K]]
+    tgt_k = c1["data"]["tgt_fds_pcd"][aux["t_fps"][:K]]
+    offs = torch.zeros(2, dtype=torch.int32, device=dev)
+    ind = torch.zeros(K, dtype=torch.float32, device=dev)
+    Ra, ta = torch.zeros((K, 3, 3), device=dev), torch.zeros((K, 3), device=dev)
+    ssa, tta = torch.zeros((K, 3), device=dev), torch.zeros((K, 3), device=dev)
+    ops.hypotheses(logits, 20, cu(src_k, dev), cu(tgt_k, dev), cu(sc["src"]["R"].numpy(), dev), cu(sc["tgt"]["R"].numpy(), dev),
+                   smp, tmp, dM, K, offs[0:1], offs[1:2], ind, Ra, ta, ssa, tta)
+    assert int(offs[1].item()) == M
+    assert np.abs(ind[:M].cpu().numpy() - sc["ind"]).max() < 2e-3     # soft arg-max bin (0..19) after 10 fp32 convs
+    # hypotheses from the ORACLE's bins must agree tightly: recompute with oracle ind through torch
+    R, t = oracle.hypotheses(ind[:M].cpu(), torch.from_numpy(src_k)[sc["s_mids"].astype(np.int64)],
+                             torch.from_numpy(tgt_k)[sc["t_mids"].astype(np.int64)], sc["src"]["R"][sc["s_mids"].astype(np.int64)],
+                             sc["tgt"]["R"][sc["t_mids"].astype(np.int64)], 20)
+    assert np.abs(Ra[:M].cpu().numpy() - R.numpy()).max() < 5e-6 and np.abs(ta[:M].cpu().numpy() - t.numpy()).max() < 5e-5
+    assert (ssa[:M].cpu().numpy() == src_k[sc["s_mids"]]).all() and (tta[:M].cpu().numpy() == tgt_k[sc["t_mids"]]).all()
+    model.cpu()
+
+
+# ---------------------------------------------------------------------------------------------- a13
+def _corr_problem(rng, n, inlier_frac, noise=0.01):
+    ss = rng.uniform(-3, 3, (n, 3))
+    A = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    A *= np.sign(np.linalg.det(A))
+    tv = rng.uniform(-1, 1, 3)
+    tt = ss @ A.T + tv + rng.normal(scale=noise, size=(n, 3))
+    out = rng.random(n) > inlier_frac
+    tt[out] = rng.uniform(-3, 3, (out.sum(), 3))
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = A, tv
+    return ss.astype(np.float32), tt.astype(np.float32), T, ~out
+
+
+@pytest.mark.parametrize("Mc", [1, 37, 1200, 4500])
+def test_consensus_bit_exact(dev, oracle, Mc):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(Mc)
+    ss, tt, T, inl = _corr_problem(rng, Mc, 0.4, 0.02)
+    R = np.tile(np.eye(3, dtype=np.float32), (Mc, 1, 1))
+    t = rng.normal(size=(Mc, 3)).astype(np.float32)
+    for j in range(0, Mc, 3):           # a third of the hypotheses are the true pose + small perturbation
+        R[j] = T[:3, :3].astype(np.float32)
+        t[j] = (T[:3, 3] + rng.normal(scale=0.02, size=3)).astype(np.float32)
+    cap = Mc + 11
+    pad = lambda a: np.concatenate([a, np.zeros((cap - Mc,) + a.shape[1:], a.dtype)])
+    ind, dI, dbest, counts = ops.consensus(cu(pad(ss), dev), cu(pad(tt), dev), cu(pad(R), dev), cu(pad(t), dev),
+                                           torch.tensor([Mc], dtype=torch.int32, device=dev), cap, 20, 1 / 3)
+    eind, ebest, ecounts = oracle.consensus(ss, tt, R, t, 20, 1 / 3)
+    assert (counts[:Mc].cpu().numpy() == ecounts).all()
+    assert int(dbest.item()) == ebest and int(dI.item()) == len(eind)
+    assert (ind[:len(eind)].cpu().numpy() == eind).all()
+
+
+# ---------------------------------------------------------------------------------------------- a14
+@pytest.mark.parametrize("n,frac,conf,iters", [(400, 0.5, 0.999, 50000), (300, 0.15, 1.0, 20000), (60, 0.3, 0.999, 50000),
+                                               (1000, 0.05, 0.999, 50000), (2, 1.0, 0.999, 100), (0, 1.0, 0.999, 100)])
+def test_ransac_equals_oracle(dev, oracle, n, frac, conf, iters):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(n + iters)
+    total = max(n, 3) + 40
+    ss, tt, T, _ = _corr_problem(rng, total, frac)
+    ind = np.sort(rng.choice(total, n, replace=False)).astype(np.int32) if n else np.zeros(0, np.int32)
+    pad = np.zeros(max(n, 1) + 5, np.int32)
+    pad[:n] = ind
+    res = ops.ransac(cu(ss, dev), cu(tt, dev), cu(pad, dev), torch.tensor([n], dtype=torch.int32, device=dev), len(pad),
+                     0.10, 0.8, conf, iters, seed=1234)
+    Tg, ninl, bitr, nit = ops.decode_ransac_result(res.cpu())
+    e = oracle.ransac(ss, tt, ind, 0.10, 0.8, conf, iters, 1234)
+    assert ninl == e["num_inliers"] and bitr == e["best_itr"] and nit == e["iters"], (ninl, bitr, nit, e["num_inliers"], e["best_itr"], e["iters"])
+    assert np.abs(Tg - e["T"]).max() < 1e-12
+
+
+def test_ransac_statistical_success(dev):
+    """Open3D-equivalent acceptance on many seeds: the recovered pose is inside the RRE/RTE thresholds."""
+    from bufferx_b200 import ops
+    from bufferx_b200.se3 import compute_rre, compute_rte
+    rng = np.random.default_rng(5)
+    ss, tt, T, inl = _corr_problem(rng, 500, 0.3)
+    d_ss, d_tt = cu(ss, dev), cu(tt, dev)
+    ind = torch.arange(500, dtype=torch.int32, device=dev)
+    dI = torch.tensor([500], dtype=torch.int32, device=dev)
+    ok = 0
+    for seed in range(20):
+        Tg, ninl, _, _ = ops.decode_ransac_result(ops.ransac(d_ss, d_tt, ind, dI, 500, 0.10, 0.8, 0.999, 50000, seed).cpu())
+        ok += compute_rre(Tg, T) < 15.0 and compute_rte(Tg, T) < 0.3 and ninl > 0.7 * inl.sum()
+    assert ok == 20
+
+
+# ---------------------------------------------------------------------------------------------- a15
+def test_refine_close_to_oracle(dev, oracle):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(8)
+    ss, tt, T, _ = _corr_problem(rng, 900, 0.6)
+    T0 = T.copy()
+    T0[:3, 3] += 0.03
+    To, rounds = ops.refine(cu(ss, dev), cu(tt, dev), torch.tensor([900], dtype=torch.int32, device=dev), 900,
+                            cu(T0.reshape(16), dev, torch.float64), 0.10)
+    eT, erounds = oracle.refine(ss, tt, T0.astype(np.float32), 0.10)
+    assert np.abs(To.cpu().numpy().reshape(4, 4) - eT).max() < 1e-5      # fp32 pose, fp64 fit: summation order only
+    assert int(rounds.item()) == erounds
+
+
+# ------------------------------------------------------------------------------------------- whole pair
+def _compare_pair(model, sd, cfg, data, perms, oracle, name):
+    from bufferx_b200.se3 import compute_rre, compute_rte
+    with torch.no_grad():
+        pose, times, ninl, nmut, nind, su = model(data, perms=perms, ransac_seed=0, debug=True)
+    dbg = model.last_debug
+    o_pose, o_ninl, o_nmut, o_nind, o_su, aux = oracle.register_pair(sd, cfg, data, perms, 0, keep=True)
+    K = cfg.patch.num_fps
+    assert (dbg["fps_idx"][0].cpu().numpy()[:len(aux["s_fps"])] == aux["s_fps"]).all()
+    assert (dbg["fps_idx"][1].cpu().numpy()[:len(aux["t_fps"])] == aux["t_fps"]).all()
+    assert np.allclose(dbg["des_r"].cpu().numpy(), np.array(aux["des_r"], dtype=np.float32), atol=0)
+    rep = {}
+    for i, (sc, osc) in enumerate(zip(dbg["scales"], aux["scales"])):
+        for side, key in (("s", "src"), ("t", "tgt")):
+            assert (sc[side]["idx"].cpu().numpy() == osc[key]["idx"]).all(), f"{name} scale {i} {key}: neighbour lists differ"
+            assert (sc[side]["vidx"].cpu().numpy() == osc[key]["vidx"]).all(), f"{name} scale {i} {key}: voxel selections differ"
+            assert (sc[side]["R"].cpu().numpy() == osc[key]["R"].numpy()).all()
+            d, od = sc[side]["desc"].cpu().numpy(), osc[key]["desc"].numpy()
+            den = np.abs(od).max(1)
+            rel = np.abs(d - od).max(1) / np.where(den > 0, den, 1)
+            assert rel.max() < 1e-4, f"{name} scale {i} {key}: descriptor rel err {rel.max()}"
+        M, oM = int(sc["dM"].item()), len(osc["s_mids"])
+        rep[f"M{i}"] = (M, oM)
+        # arg-min flips between near-tied descriptors are possible at 1e-7 differences; allow a handful
+        gs = set(zip(sc["s_mids"][:M].cpu().numpy().tolist(), sc["t_mids"][:M].cpu().numpy().tolist()))
+        es = set(zip(osc["s_mids"].tolist(), osc["t_mids"].tolist()))
+        assert len(gs ^ es) <= max(2, oM // 200), f"{name} scale {i}: match sets differ by {len(gs ^ es)}"
+    assert su == o_su and abs(nmut - o_nmut) <= max(2, o_nmut // 200)
+    if rep and all(a == b for a, b in rep.values()):
+        # identical match lists -> identical consensus set and RANSAC outcome
+        assert nind == o_nind and ninl == o_ninl
+        assert compute_rre(pose, o_pose) < 0.1 and compute_rte(pose, o_pose) < 0.005
+    return pose, o_pose, rep
+
+
+def test_pair_c1_against_oracle_and_golden(dev, oracle, c1):
+    model = c1["model"].to(dev)
+    pose, o_pose, rep = _compare_pair(model, c1["sd"], c1["cfg"], c1["data"], c1["perms"], oracle, "C1")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_seed0.npz"))
+    dbg = model.last_debug
+    assert (dbg["fps_idx"][0].cpu().numpy() == g["s_fps"]).all()
+    assert np.allclose(dbg["scales"][0]["s"]["desc"].cpu().numpy(), g["s0_src_desc"], rtol=0, atol=2e-5)
+    model.cpu()
+
+
+def test_pair_c1_three_scales_outdoor_flags(dev, oracle):
+    """3 scales, aligned-to-z (outdoor flags), no refinement, confidence 1.0 on the small cloud."""
+    import bufferx_b200 as bx
+    from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
+    cfg = workload_cfg("C3")
+    cfg.patch.num_fps, cfg.patch.num_points_radius_estimate, cfg.match.iter_n = 200, 400, 4000
+    model = init_synthetic_weights(bx.BufferX(cfg), seed=7)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    data = make_pair("C1", 5)
+    data["is_aligned_to_global_z"] = True
+    perms = oracle.draw_perms(cfg, 5000, 5000, 3)
+    _compare_pair(model.to(dev), sd, cfg, data, perms, oracle, "C1x3")
+
+
+def test_forward_draws_host_permutations_like_the_reference(dev, oracle, c1):
+    """Without explicit perms forward() must consume NumPy's global RNG exactly like the reference
+    (one np.random.choice(N, N, replace=False) per Desc call, src then tgt, per scale)."""
+    model = c1["model"].to(dev)
+    np.random.seed(0)
+    with torch.no_grad():
+        model(c1["data"], ransac_seed=0, debug=True)
+    a = model.last_debug["scales"][0]["s"]["idx"].cpu().numpy()
+    assert (a == c1["res"][5]["scales"][0]["src"]["idx"]).all()
+    model.cpu()
+
+
+# ------------------------------------------------------------------------------- full-size properties
+def test_c2_full_size_pair(dev, oracle):
+    """BASELINE config C2 (2x20000 points, 1500 key-points, 512 pts/patch, 3 scales, 50000 iters):
+    whole pair against the oracle + size-independent properties."""
+    import bufferx_b200 as bx
+    from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
+    cfg = workload_cfg("C2")
+    model = init_synthetic_weights(bx.BufferX(cfg))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    data = make_pair("C2", 0)
+    perms = oracle.draw_perms(cfg, 20000, 20000, 0)
+    model = model.to(dev)
+    _compare_pair(model, sd, cfg, data, perms, oracle, "C2")
+    dbg = model.last_debug
+    f = dbg["fps_idx"].cpu().numpy()
+    assert f[0, 0] == 0 and len(set(f[0].tolist())) == f.shape[1]            # FPS: starts at 0, no repeats
+    for sc in dbg["scales"]:
+        p = sc["s"]["raw_patches"].cpu().numpy()
+        k = dbg["kpts"][0, :1500].cpu().numpy()
+        assert (p[:, -1] == k).all()                                         # slot P-1 is the key-point
+        d = np.linalg.norm(p - k[:, None], axis=-1)
+        assert d.max() < float(dbg["des_r"][dbg["scales"].index(sc)].item()) + 1e-6   # every member is inside the ball
+        idx = sc["s"]["idx"].cpu().numpy()
+        inc = np.diff(idx, axis=1)
+        assert ((inc > 0) | (idx[:, 1:] == idx[:, :1])).all()                # indices ascending, then first-hit padding
+        e = sc["s"]["equi"].cpu().numpy()
+        n = np.linalg.norm(e, axis=1)
+        assert np.abs(n[n > 0] - 1).max() < 1e-5                              # equivariant maps are channel-normalised
+
+
+def test_c3_kitti_sized_front_end(dev, oracle):
+    """120000-point clouds: FPS (16-CTA cluster path), radius estimation and neighbour lists vs the oracle."""
+    from bufferx_b200 import ops
+    from bufferx_b200.synth import make_pair
+    data = make_pair("C3", 0)
+    src = data["src_fds_pcd"]
+    idx, kp = ops.fps(cu(src, dev), [0, len(src)], 2048)
+    eidx = oracle.fps(src, 2048)
+    assert (idx[0].cpu().numpy() == eidx).all()
+    kr = src[eidx[:2000]]
+    r, m, _ = ops.radius_estimate(cu(kr, dev), cu(src, dev), [5, 2, 0.5])
+    assert np.allclose(r.cpu().numpy(), np.array(oracle.radius_estimation(src[:1], kr[:1], src, kr, [5, 2, 0.5]), dtype=np.float32), atol=0)
+    perm = np.random.RandomState(1).permutation(len(src)).astype(np.int32)
+    pts4 = ops.permute_cloud(cu(src, dev), cu(perm, dev))
+    q = src[eidx[:256]]
+    pat, pidx = ops.select_patches(pts4, cu(q, dev), float(r[1].item()), 512, want_idx=True)
+    eidx2, epat = oracle.select_patches(src, perm, q, float(r[1].item()), 512)
+    assert (pidx.cpu().numpy() == eidx2).all() and (pat.cpu().numpy() == epat).all()
