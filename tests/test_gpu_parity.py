@@ -333,7 +333,9 @@ def test_pair_c1_against_oracle_and_golden(dev, oracle, c1):
     g = np.load(os.path.join(ROOT, "tests", "golden", "c1_seed0.npz"))
     dbg = model.last_debug
     assert (dbg["fps_idx"][0].cpu().numpy() == g["s_fps"]).all()
-    assert np.allclose(dbg["scales"][0]["s"]["desc"].cpu().numpy(), g["s0_src_desc"], rtol=0, atol=2e-5)
+    d, od = dbg["scales"][0]["s"]["desc"].cpu().numpy(), g["s0_src_desc"]
+    den = np.abs(od).max(1)
+    assert (np.abs(d - od).max(1) / np.where(den > 0, den, 1)).max() < 1e-4      # descriptors: 1e-4 rel (north_star)
     model.cpu()
 
 
@@ -379,12 +381,12 @@ def test_c2_full_size_pair(dev, oracle):
     dbg = model.last_debug
     f = dbg["fps_idx"].cpu().numpy()
     assert f[0, 0] == 0 and len(set(f[0].tolist())) == f.shape[1]            # FPS: starts at 0, no repeats
-    for sc in dbg["scales"]:
+    for si, sc in enumerate(dbg["scales"]):
         p = sc["s"]["raw_patches"].cpu().numpy()
         k = dbg["kpts"][0, :1500].cpu().numpy()
         assert (p[:, -1] == k).all()                                         # slot P-1 is the key-point
         d = np.linalg.norm(p - k[:, None], axis=-1)
-        assert d.max() < float(dbg["des_r"][dbg["scales"].index(sc)].item()) + 1e-6   # every member is inside the ball
+        assert d.max() < float(dbg["des_r"][si].item()) + 1e-6                # every member is inside the ball
         idx = sc["s"]["idx"].cpu().numpy()
         inc = np.diff(idx, axis=1)
         assert ((inc > 0) | (idx[:, 1:] == idx[:, :1])).all()                # indices ascending, then first-hit padding
