@@ -9,7 +9,13 @@ re-laid as [tap][Cin][Cout] with the eval-mode BatchNorm folded in (computed in 
 import torch
 import torch.nn as nn
 
+import os
+
 from bufferx_b200 import ops
+
+# Debug switch only: BX_CONV=ffma routes the conv stacks through the fp32 CUDA-core kernel (bx_conv.cu)
+# instead of the tcgen05 kernel (bx_conv_tc.cu).  Both are sm_100a kernels of this library.
+USE_FFMA = os.environ.get("BX_CONV", "tc").lower() == "ffma"
 
 
 def fold_conv_bn(conv_w, conv_b, bn_mean=None, bn_var=None, bn_w=None, bn_b=None, eps=1e-5):
@@ -75,8 +81,8 @@ class _ConvStack(nn.Module):
                                      None if bn is None or not bn.affine else bn.bias,
                                      eps=1e-5 if bn is None else bn.eps)
                 ks = tuple(conv.kernel_size)
-                out.append(dict(w=Wt, b=b, cin=conv.in_channels, cout=conv.out_channels,
-                                k=ks if len(ks) == 3 else (1,) + ks, relu=relu))
+                out.append(dict(w=Wt, w_tc=ops.conv_tc_weights(Wt) if Wt.is_cuda else None, b=b, cin=conv.in_channels,
+                                cout=conv.out_channels, k=ks if len(ks) == 3 else (1,) + ks, relu=relu))
             self._folded = out
         return self._folded
 
@@ -99,10 +105,11 @@ class Cylindrical_Net(_ConvStack):
         cur = x.contiguous()
         for i, l in enumerate(L):
             out = torch.empty((K, l["cout"], 140), dtype=torch.float32, device=dev)
+            conv, w = (ops.conv_layer, l["w"]) if USE_FFMA else (ops.conv_layer_tc, l["w_tc"])
             if i == 0:
-                ops.conv_layer(ops.GEOM_CYL3D, cur, l["w"], l["b"], out, K, l["cin"], l["cout"], 3, 7, 20, 3, 3, 3, l["relu"])
+                conv(ops.GEOM_CYL3D, cur, w, l["b"], out, K, l["cin"], l["cout"], 3, 7, 20, 3, 3, 3, l["relu"])
             else:
-                ops.conv_layer(ops.GEOM_CYL2D, cur, l["w"], l["b"], out, K, l["cin"], l["cout"], 1, 7, 20, 1, 3, 3, l["relu"])
+                conv(ops.GEOM_CYL2D, cur, w, l["b"], out, K, l["cin"], l["cout"], 1, 7, 20, 1, 3, 3, l["relu"])
             cur = out
         return cur.view(K, L[-1]["cout"], 7, 20), None
 
@@ -128,10 +135,11 @@ class CostNet(_ConvStack):
             kd, kh, kw = l["k"]
             OD, OH, OW = D - kd + 1, H - kh + 1, W - kw + 1
             out = torch.empty((maxM, l["cout"], OD * OH * OW), dtype=torch.float32, device=dev)
+            conv, w = (ops.conv_layer, l["w"]) if USE_FFMA else (ops.conv_layer_tc, l["w_tc"])
             if i == 0:
-                ops.conv_layer(ops.GEOM_COSTVOL, None, l["w"], l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"],
-                               d_n=d_M, equi_s=equi_s, equi_t=equi_t, s_mids=s_mids, t_mids=t_mids)
+                conv(ops.GEOM_COSTVOL, None, w, l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"],
+                     d_n=d_M, equi_s=equi_s, equi_t=equi_t, s_mids=s_mids, t_mids=t_mids)
             else:
-                ops.conv_layer(ops.GEOM_VALID3D, cur, l["w"], l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"], d_n=d_M)
+                conv(ops.GEOM_VALID3D, cur, w, l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"], d_n=d_M)
             cur, D, H, W = out, OD, OH, OW
         return cur.view(maxM, L[-1]["cout"])

@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(_PKG, "libbufferx_b200.so")
 
 SYMBOLS = [
     "bx_last_error", "bx_version", "bx_device_sm_count", "bx_launch_count", "bx_fps", "bx_radius_estimate", "bx_permute_cloud",
-    "bx_select_patches", "bx_ball_query", "bx_lrf", "bx_spt_pnt", "bx_conv_layer", "bx_pool_desc", "bx_mutual_nn",
+    "bx_select_patches", "bx_ball_query", "bx_lrf", "bx_spt_pnt", "bx_conv_layer", "bx_conv_tc_ntile", "bx_conv_layer_tc",
+    "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine",
 ]
 
@@ -59,6 +60,8 @@ def load_library():
     lib.bx_lrf.argtypes = [P, c_int, c_int, c_float, P, c_int, P, P, P, P]
     lib.bx_spt_pnt.argtypes = [P, c_int, c_int, P, c_int, c_int, P, c_float, c_int, P, P, P, P, P, P]
     lib.bx_conv_layer.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
+    lib.bx_conv_layer_tc.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
+    lib.bx_conv_tc_ntile.argtypes = [c_int]
     lib.bx_pool_desc.argtypes = [P, c_int, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_mutual_nn.argtypes = [P, c_int, P, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_hypotheses.argtypes = [P, c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P]
@@ -236,6 +239,48 @@ def conv_layer(geom, x, w, bias, out, n, Cin, Cout, D, H, W, kd, kh, kw, relu, d
     _check(load_library().bx_conv_layer(geom, _dp(x, F32, "x"), _dp(w, F32, "w"), _dp(bias, F32, "bias"), _dp(out, F32, "out"), int(n),
                                         _dp(d_n, I32, "d_n"), Cin, Cout, D, H, W, kd, kh, kw, int(bool(relu)), _dp(equi_s, F32), _dp(equi_t, F32),
                                         _dp(s_mids, I32), _dp(t_mids, I32), _stream()), "bx_conv_layer")
+    if ev:
+        ev[1].record()
+    return out
+
+
+def tf32_split(w: torch.Tensor):
+    """hi = round-to-nearest (ties away) TF32 of w (10-bit mantissa), lo = w - hi (exact in fp32)."""
+    bits = w.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    hi_bits = ((bits + 0x1000) & 0xFFFFE000) & 0xFFFFFFFF
+    hi_bits = torch.where(hi_bits >= 0x80000000, hi_bits - 0x100000000, hi_bits).to(torch.int32)
+    hi = hi_bits.view(torch.float32)
+    return hi, w - hi
+
+
+def conv_tc_weights(Wt: torch.Tensor) -> torch.Tensor:
+    """[T, Cin, Cout] folded fp32 weights -> the tcgen05 operand image of ``bx_conv_layer_tc``:
+    [chunk(Cin/16)][tap][kstep(2)][split(hi,lo)][kunit(2)][n(NT)][4]."""
+    T, Cin, Cout = Wt.shape
+    assert Cin % 16 == 0 and Cout <= 128
+    NT = 128 if Cout > 64 else (64 if Cout > 32 else 32)          # == bx_conv_tc_ntile(Cout)
+    W = torch.zeros((T, Cin, NT), dtype=torch.float32, device=Wt.device)
+    W[:, :, :Cout] = Wt
+    hi, lo = tf32_split(W)
+    both = torch.stack([hi, lo], dim=0)                               # [split, T, Cin, NT]
+    both = both.view(2, T, Cin // 16, 2, 2, 4, NT)                    # [split, T, chunk, kstep, kunit, j, NT]
+    img = both.permute(2, 1, 3, 0, 4, 6, 5).contiguous()              # [chunk, T, kstep, split, kunit, NT, j]
+    return img.view(-1)
+
+
+def conv_layer_tc(geom, x, w_tc, bias, out, n, Cin, Cout, D, H, W, kd, kh, kw, relu, d_n=None, equi_s=None, equi_t=None,
+                  s_mids=None, t_mids=None):
+    ev = None
+    if profiler is not None and d_n is None:
+        OD, OH, OW = (1, 7, 20) if geom in (GEOM_CYL3D, GEOM_CYL2D) else (D - kd + 1, H - kh + 1, W - kw + 1)
+        ev = profiler.span("conv_desc", 2.0 * n * OD * OH * OW * Cout * Cin * kd * kh * kw)
+        ev[0].record()
+    elif profiler is not None:
+        ev = profiler.span("conv_cost", 0.0)
+        ev[0].record()
+    _check(load_library().bx_conv_layer_tc(geom, _dp(x, F32, "x"), _dp(w_tc, F32, "w_tc"), _dp(bias, F32, "bias"), _dp(out, F32, "out"), int(n),
+                                           _dp(d_n, I32, "d_n"), Cin, Cout, D, H, W, kd, kh, kw, int(bool(relu)), _dp(equi_s, F32), _dp(equi_t, F32),
+                                           _dp(s_mids, I32), _dp(t_mids, I32), _stream()), "bx_conv_layer_tc")
     if ev:
         ev[1].record()
     return out

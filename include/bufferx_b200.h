@@ -111,6 +111,16 @@ int bx_conv_layer(int geom, const float *in, const float *w, const float *bias, 
                   const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
                   void *stream);
 
+/* Tensor-core variant (tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulators in TMEM; same geometry
+ * arguments).  w_tc is the host-prepared operand image: for every stage it = chunk*T + tap (chunk = 16
+ * input channels) the block [kstep(2)][split(2: hi,lo)][kunit(2)][n(NT)][4 floats], NT = bx_conv_tc_ntile(Cout),
+ * rows n >= Cout zero, hi = round-to-nearest tf32 of the folded weight, lo = w - hi.  Cin % 16 == 0, Cout <= 128. */
+int bx_conv_tc_ntile(int Cout);
+int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const float *bias, float *out, int n,
+                     const int32_t *d_n, int Cin, int Cout, int D, int H, int W, int kd, int kh, int kw, int relu,
+                     const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
+                     void *stream);
+
 /* ---- a9: attention pooling + normalisation --------------------------------------------------
  * Replaces pool_layer / avg-pool / F.normalize (models/patch_embedder.py:32-39, 80-83).
  * x: [K,32,S]; w1 [32,16] (in-major), b1 [16], w2 [16], b2 [1] (BatchNorm folded);

@@ -413,3 +413,72 @@ def test_c3_kitti_sized_front_end(dev, oracle):
     pat, pidx = ops.select_patches(pts4, cu(q, dev), float(r[1].item()), 512, want_idx=True)
     eidx2, epat = oracle.select_patches(src, perm, q, float(r[1].item()), 512)
     assert (pidx.cpu().numpy() == eidx2).all() and (pat.cpu().numpy() == epat).all()
+
+
+# ------------------------------------------------------------------------- conv kernels, layer by layer
+def _torch_layer(geom, x, W, b, relu, kd, kh, kw):
+    """torch-CPU statement of one conv layer (oracle-side arithmetic: F.conv3d / F.conv2d + explicit padding)."""
+    import torch.nn.functional as F
+    from oracle import oracle as O
+    if geom == "cyl3d":
+        y = F.conv3d(O._pad_cyl(x), W, b).squeeze(2)
+    elif geom == "cyl2d":
+        y = F.conv2d(O._pad_cyl(x), W, b)
+    else:
+        y = F.conv3d(x, W, b)
+    return F.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("impl", ["tc", "ffma"])
+@pytest.mark.parametrize("geom,Cin,Cout,dims,k,n", [
+    ("cyl3d", 16, 64, (3, 7, 20), (3, 3, 3), 37), ("cyl2d", 64, 128, (1, 7, 20), (1, 3, 3), 41),
+    ("cyl2d", 128, 128, (1, 7, 20), (1, 3, 3), 19), ("cyl2d", 64, 32, (1, 7, 20), (1, 3, 3), 300),
+    ("cyl2d", 32, 32, (1, 7, 20), (1, 3, 3), 5), ("valid3d", 32, 64, (18, 3, 18), (3, 3, 3), 9),
+    ("valid3d", 64, 128, (14, 1, 14), (3, 1, 3), 13), ("valid3d", 32, 20, (2, 1, 2), (2, 1, 2), 77)])
+def test_conv_layer_kernels(dev, geom, Cin, Cout, dims, k, n, impl):
+    from bufferx_b200 import ops
+    from bufferx_b200.models.patchnet import fold_conv_bn
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout + n)
+    D, H, W_ = dims
+    kd, kh, kw = k
+    x = torch.randn((n, Cin, D, H, W_), generator=g)
+    Wc = torch.randn((Cout, Cin, kd, kh, kw), generator=g) / (Cin * kd * kh * kw) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    relu = Cout != 20
+    if geom == "cyl3d":
+        ref = _torch_layer(geom, x, Wc, b, relu, kd, kh, kw)
+    elif geom == "cyl2d":
+        ref = _torch_layer(geom, x.squeeze(2), Wc.squeeze(2), b, relu, kd, kh, kw)
+    else:
+        ref = _torch_layer(geom, x, Wc, b, relu, kd, kh, kw)
+    Wt, bf = fold_conv_bn(Wc, b)
+    G = {"cyl3d": ops.GEOM_CYL3D, "cyl2d": ops.GEOM_CYL2D, "valid3d": ops.GEOM_VALID3D}[geom]
+    OD, OH, OW = (1, 7, 20) if geom != "valid3d" else (D - kd + 1, H - kh + 1, W_ - kw + 1)
+    out = torch.full((n, Cout, OD * OH * OW), float("nan"), device=dev)
+    xin = x.to(dev).reshape(n, Cin, -1).contiguous()
+    if impl == "tc":
+        ops.conv_layer_tc(G, xin, ops.conv_tc_weights(Wt.to(dev)), bf.to(dev), out, n, Cin, Cout, D, H, W_, kd, kh, kw, relu)
+    else:
+        ops.conv_layer(G, xin, Wt.to(dev), bf.to(dev), out, n, Cin, Cout, D, H, W_, kd, kh, kw, relu)
+    got = out.cpu().numpy().reshape(ref.shape)
+    err = np.abs(got - ref.numpy()).max() / np.abs(ref.numpy()).max()
+    assert err < 2e-5, f"{impl} {geom} Cin={Cin} Cout={Cout}: rel err {err}"     # fp32-grade (3xTF32 / FFMA) vs torch fp32
+
+
+def test_cost_volume_first_layer_tc_vs_ffma(dev, oracle, c1):
+    """COSTVOL geometry (on-the-fly cost volume + match gather): tensor-core kernel against the CUDA-core kernel."""
+    from bufferx_b200 import ops
+    sc = c1["res"][5]["scales"][0]
+    model = c1["model"].to(dev)
+    L = model.Pose.conv.folded()[0]
+    es, et = cu(sc["src"]["equi"].numpy(), dev), cu(sc["tgt"]["equi"].numpy(), dev)
+    M = len(sc["s_mids"])
+    sm, tm = cu(sc["s_mids"], dev, torch.int32), cu(sc["t_mids"], dev, torch.int32)
+    dM = torch.tensor([M - 3], dtype=torch.int32, device=dev)
+    a = torch.zeros((M, 32, 972), device=dev)
+    b = torch.zeros((M, 32, 972), device=dev)
+    ops.conv_layer(ops.GEOM_COSTVOL, None, L["w"], L["b"], a, M, 32, 32, 20, 5, 20, 3, 3, 3, True, d_n=dM, equi_s=es, equi_t=et, s_mids=sm, t_mids=tm)
+    ops.conv_layer_tc(ops.GEOM_COSTVOL, None, L["w_tc"], L["b"], b, M, 32, 32, 20, 5, 20, 3, 3, 3, True, d_n=dM, equi_s=es, equi_t=et, s_mids=sm, t_mids=tm)
+    assert (b[M - 3:] == 0).all()                                     # rows beyond the device-side count are untouched
+    assert relerr(b.cpu().numpy(), a.cpu().numpy()) < 2e-5
+    model.cpu()
