@@ -3,19 +3,23 @@
 // Same implicit GEMM as bx_conv.cu (rows = (sample, output position), cols = Cout, K = taps*Cin, padding
 // geometry folded into the loader), but the inner product runs as tcgen05.mma kind::tf32 with fp32
 // accumulators in tensor memory.  fp32-grade accuracy (descriptor parity 1e-4 rel) comes from the
-// 3xTF32 split: x = hi + lo with hi = cvt.rna.tf32(x), lo = x - hi (exact);  a*b ~= ah*bh + ah*bl + al*bh
-// (the dropped al*bl term is ~2^-22 relative).  Weights are split on the host, activations in the loader.
+// 3xTF32 split  x = hi + lo  (hi = x with the 13 low mantissa bits cleared, lo = x - hi, exact):
+//     a*b ~= ah*bh + ah*bl + al*bh          (dropped al*bl ~ 2^-20 relative)
+// The tensor core accumulates with truncation, one truncation per tcgen05.mma; the small cross terms
+// therefore get their OWN accumulator (their truncation error is 2^-11 smaller) and only the ah*bh
+// products go through the main one -- 3x fewer truncations on the value that matters.
 //
-// CTA = 256 threads = 256 GEMM rows = two M=128 MMA tiles sharing one B tile; N = NT (32/64/128) columns
-// -> 2*NT TMEM columns.  A stage is 16 input channels of one tap: two K=8 steps, each with hi and lo
-// operand images written by the loader threads straight into the canonical K-major no-swizzle UMMA
-// layout (core matrix = 8 rows x 16 bytes; thread r writes row r with 16-byte STS -> conflict-free):
-//     A image  [kunit(2)][row(256)][16 B]           LBO = 4096 B, SBO = 128 B
-//     B image  [kunit(2)][n(NT)][16 B]              LBO = NT*16 B, SBO = 128 B   (pre-arranged on the host)
-// Two stages are double-buffered; tcgen05.commit on an mbarrier per stage tells the loaders when the tensor
-// core has finished reading a stage.  The k order is (16-channel chunk outer, tap inner) so that the 9/27
-// taps of a chunk re-read the same activations from L1.  Epilogue: tcgen05.ld 32x32b -> bias (+ReLU) ->
-// coalesced stores of out[n][co][pos].
+// Warp-specialised CTA (544 threads, 1 CTA / SM, 256 GEMM rows = two M=128 tiles sharing each B tile):
+//   warps 0-15  loaders : thread -> (row = t & 255, k-step = t >> 8).  Per stage (16 input channels of one
+//               tap) a thread fetches its 8 activations (L1-resident across the taps of a chunk: the k
+//               order is chunk-outer / tap-inner), splits them and writes hi/lo with 16-byte STS straight
+//               into the canonical K-major no-swizzle UMMA layout (core matrix = 8 rows x 16 B):
+//                   A image [kunit(2)][row(256)][16 B]   LBO = 4096 B, SBO = 128 B
+//                   B image [kunit(2)][n(NT)][16 B]      LBO = NT*16 B, SBO = 128 B  (pre-arranged on the host)
+//               then fence.proxy.async + mbarrier arrive on full[stage].
+//   warp 16     MMA issuer: waits full[stage], issues 12 tcgen05.mma (2 k-steps x 2 tiles x 3 products),
+//               tcgen05.commit -> empty[stage]; 4 stages in flight, no __syncthreads in the main loop.
+//   epilogue    (loader warps) tcgen05.ld of hi+lo accumulators -> bias (+ReLU) -> coalesced stores.
 #include "bx_common.cuh"
 
 namespace {
@@ -31,8 +35,10 @@ struct ConvTcParams {
     const int *s_mids, *t_mids;
 };
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_LOADERS = 512;
+constexpr int TC_THREADS = TC_LOADERS + 32;
 constexpr int TC_BM = 256;
+constexpr int TC_STAGES = 4;
 constexpr int A_STAGE_BYTES = 2 * 2 * 2 * TC_BM * 16;  // [kstep][split][kunit][row][16B] = 32 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,6 +71,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -77,12 +87,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
-}
-
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
 }
 
 #define TMEM_LD32(taddr, v)                                                                                    \
@@ -98,210 +102,220 @@ __device__ __forceinline__ float tf32_rna(float x) {
         : "memory")
 
 template <int GEOM, int NT>
-__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const ConvTcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcParams p) {
     constexpr int B_STAGE_BYTES = 2 * 2 * 2 * NT * 16;  // [kstep][split][kunit][n][16B]
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    constexpr int TMEM_COLS = (2 * NT < 32) ? 32 : 2 * NT;  // 64 / 128 / 256: powers of two
+    constexpr int TMEM_COLS = 4 * NT;  // two tiles x (main + cross-term accumulator): 128 / 256 / 512
+    constexpr int B_VEC = B_STAGE_BYTES / 16;
+    constexpr int B_PER_T = (B_VEC + TC_LOADERS - 1) / TC_LOADERS;  // 2 / 1 / 1
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bars[2];
+    __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 1];  // full[4], empty[4], done
     __shared__ uint32_t tmem_base_s;
 
     const int n_samples = p.d_n ? *p.d_n : p.n;
     const long long Mtotal = (long long)n_samples * p.S_out;
     const long long row0 = (long long)blockIdx.x * TC_BM;
     if (row0 >= Mtotal) return;  // uniform per CTA, before any barrier / TMEM allocation
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int n_iters = (p.Cin / 16) * p.T;  // stage = (16-channel chunk, tap); chunk outer, tap inner
 
-    if (warp == 0) {
+    if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 32) {
-        mbar_init(smem_u32(&bars[0]), 1);
-        mbar_init(smem_u32(&bars[1]), 1);
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), TC_LOADERS / 32);   // full: one arrival per loader warp
+            mbar_init(smem_u32(&bars[TC_STAGES + s]), 1);     // empty: one tcgen05.commit
+        }
+        mbar_init(smem_u32(&bars[2 * TC_STAGES]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(&bars[0]);
 
-    // ---- loader geometry: this thread owns GEMM row (row0 + tid) ---------------------------------------
-    const long long lm = row0 + tid;
-    const bool lvalid = lm < Mtotal;
-    int ln = 0, oz = 0, oy = 0, ox = 0;
-    if (lvalid) {
-        ln = (int)(lm / p.S_out);
-        const int pos = (int)(lm - (long long)ln * p.S_out);
-        if (GEOM == BX_GEOM_CYL3D || GEOM == BX_GEOM_CYL2D) {
-            oy = pos / 20;
-            ox = pos - oy * 20;
-        } else {
-            oz = pos / (p.OH * p.OW);
-            const int rem = pos - oz * (p.OH * p.OW);
-            oy = rem / p.OW;
-            ox = rem - oy * p.OW;
-        }
-    }
-    const float *pa = p.in, *pb = nullptr;
-    if (GEOM == BX_GEOM_COSTVOL) {
+    if (warp < 16) {
+        // =========================== loaders ===========================================================
+        const int row = tid & 255, ks = tid >> 8;
+        const long long lm = row0 + row;
+        const bool lvalid = lm < Mtotal;
+        int ln = 0, oz = 0, oy = 0, ox = 0;
         if (lvalid) {
-            pa = p.equi_s + (size_t)p.s_mids[ln] * 32 * 140;
-            pb = p.equi_t + (size_t)p.t_mids[ln] * 32 * 140;
-        }
-    } else {
-        pa = p.in + (size_t)ln * p.Cin * p.S_in;
-    }
-    const int cstride = (GEOM == BX_GEOM_COSTVOL) ? 140 : p.S_in;
-    const int n_iters = (p.Cin / 16) * p.T;  // stage = (16-channel chunk, tap); chunk outer, tap inner
-
-    float a_reg[16];
-    float4 b_reg[(B_STAGE_BYTES / 16 + TC_THREADS - 1) / TC_THREADS];
-    constexpr int B_VEC = B_STAGE_BYTES / 16;                       // 16-byte vectors per stage
-    constexpr int B_PER_T = (B_VEC + TC_THREADS - 1) / TC_THREADS;  // 4 / 2 / 1
-
-    auto load_stage = [&](int it) {
-        const int chunk = it / p.T, t = it - chunk * p.T;
-        const int dz = t / (p.kh * p.kw);
-        const int r2 = t - dz * (p.kh * p.kw);
-        const int dy = r2 / p.kw;
-        const int dx = r2 - dy * p.kw;
-        int offA = 0, offB = 0;
-        bool ok = lvalid;
-        if (GEOM == BX_GEOM_CYL3D || GEOM == BX_GEOM_CYL2D) {
-            const int yy = oy + dy - 1;
-            int xx = ox + dx - 1;
-            xx = xx < 0 ? xx + 20 : (xx >= 20 ? xx - 20 : xx);
-            ok = lvalid && yy >= 0 && yy < 7;
-            offA = dz * 140 + yy * 20 + xx;
-        } else if (GEOM == BX_GEOM_VALID3D) {
-            offA = ((oz + dz) * p.H + (oy + dy)) * p.W + (ox + dx);
-        } else {
-            const int nn = oz + dz, kk = oy + dy, ll = ox + dx;
-            int sh = ll - nn;
-            sh = sh < 0 ? sh + 20 : sh;
-            offA = (1 + kk) * 20 + sh;
-            offB = (1 + kk) * 20 + ll;
-        }
-        const int ci0 = chunk * 16;
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float v = 0.0f;
-            if (ok) {
-                const size_t o = (size_t)(ci0 + kk) * cstride;
-                if (GEOM == BX_GEOM_COSTVOL) v = pa[o + offA] - pb[o + offB];
-                else v = __ldg(pa + o + offA);
+            ln = (int)(lm / p.S_out);
+            const int pos = (int)(lm - (long long)ln * p.S_out);
+            if (GEOM == BX_GEOM_CYL3D || GEOM == BX_GEOM_CYL2D) {
+                oy = pos / 20;
+                ox = pos - oy * 20;
+            } else {
+                oz = pos / (p.OH * p.OW);
+                const int rem = pos - oz * (p.OH * p.OW);
+                oy = rem / p.OW;
+                ox = rem - oy * p.OW;
             }
-            a_reg[kk] = v;
         }
-        const float4 *wsrc = reinterpret_cast<const float4 *>(p.w) + (size_t)it * B_VEC;
-#pragma unroll
-        for (int j = 0; j < B_PER_T; ++j) {
-            const int v = tid + j * TC_THREADS;
-            if (v < B_VEC) b_reg[j] = __ldg(wsrc + v);
+        const float *pa = p.in, *pb = nullptr;
+        if (GEOM == BX_GEOM_COSTVOL) {
+            if (lvalid) {
+                pa = p.equi_s + (size_t)p.s_mids[ln] * 32 * 140;
+                pb = p.equi_t + (size_t)p.t_mids[ln] * 32 * 140;
+            }
+        } else {
+            pa = p.in + (size_t)ln * p.Cin * p.S_in;
         }
-    };
-    auto store_stage = [&](int s) {
-        unsigned char *As = smem + (size_t)s * STAGE_BYTES;
-        unsigned char *Bs = As + A_STAGE_BYTES;
+        const int cstride = (GEOM == BX_GEOM_CYL2D || GEOM == BX_GEOM_COSTVOL) ? 140 : (GEOM == BX_GEOM_CYL3D ? 420 : p.S_in);
+        // incremental (chunk, tap) counters: no integer division in the loop
+        int chunk = 0, t = 0, dz = 0, dy = 0, dx = 0;
+        float a_reg[8];
+        float4 b_reg[B_PER_T];
+
+        auto load_stage = [&](int it) {
+            int offA = 0, offB = 0;
+            bool ok = lvalid;
+            if (GEOM == BX_GEOM_CYL3D || GEOM == BX_GEOM_CYL2D) {
+                const int yy = oy + dy - 1;
+                int xx = ox + dx - 1;
+                xx = xx < 0 ? xx + 20 : (xx >= 20 ? xx - 20 : xx);
+                ok = lvalid && yy >= 0 && yy < 7;
+                offA = dz * 140 + yy * 20 + xx;
+            } else if (GEOM == BX_GEOM_VALID3D) {
+                offA = ((oz + dz) * p.H + (oy + dy)) * p.W + (ox + dx);
+            } else {  // COSTVOL: value(c, n, k, l) = d1[c][1+k][(l-n) mod 20] - d2[c][1+k][l]
+                const int nn = oz + dz, kk = oy + dy, ll = ox + dx;
+                int sh = ll - nn;
+                sh = sh < 0 ? sh + 20 : sh;
+                offA = (1 + kk) * 20 + sh;
+                offB = (1 + kk) * 20 + ll;
+            }
+            const float *src = pa + (size_t)(chunk * 16 + ks * 8) * cstride + offA;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
+            for (int kk = 0; kk < 8; ++kk) {
+                float v = 0.0f;
+                if (ok) {
+                    if (GEOM == BX_GEOM_COSTVOL) v = src[kk * cstride] - pb[(size_t)(chunk * 16 + ks * 8 + kk) * 140 + offB];
+                    else v = __ldg(src + kk * cstride);
+                }
+                a_reg[kk] = v;
+            }
+            const float4 *wsrc = reinterpret_cast<const float4 *>(p.w) + (size_t)it * B_VEC;
+#pragma unroll
+            for (int j = 0; j < B_PER_T; ++j) {
+                const int v = tid + j * TC_LOADERS;
+                if (v < B_VEC) b_reg[j] = __ldg(wsrc + v);
+            }
+            // advance to the next (chunk, tap)
+            ++t;
+            if (++dx == p.kw) {
+                dx = 0;
+                if (++dy == p.kh) { dy = 0; ++dz; }
+            }
+            if (t == p.T) { t = 0; dz = 0; dy = 0; dx = 0; ++chunk; }
+        };
+        auto store_stage = [&](int s) {
+            unsigned char *As = smem + (size_t)s * STAGE_BYTES;
+            unsigned char *Bs = As + A_STAGE_BYTES;
 #pragma unroll
             for (int ku = 0; ku < 2; ++ku) {
                 float hi[4], lo[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float x = a_reg[ks * 8 + ku * 4 + j];
-                    hi[j] = tf32_rna(x);
+                    const float x = a_reg[ku * 4 + j];
+                    hi[j] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
                     lo[j] = x - hi[j];
                 }
                 // [kstep][split][kunit][row][16B]
-                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 0) * 2 + ku) * TC_BM + tid) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 1) * 2 + ku) * TC_BM + tid) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 0) * 2 + ku) * TC_BM + row) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 1) * 2 + ku) * TC_BM + row) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
-        }
 #pragma unroll
-        for (int j = 0; j < B_PER_T; ++j) {
-            const int v = tid + j * TC_THREADS;
-            if (v < B_VEC) *reinterpret_cast<float4 *>(Bs + (size_t)v * 16) = b_reg[j];
-        }
-    };
-
-    // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NT, M = 128
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar0 = smem_u32(&bars[0]), bar1 = smem_u32(&bars[1]);
-
-    load_stage(0);
-    for (int it = 0; it < n_iters; ++it) {
-        const int s = it & 1;
-        if (it >= 2) mbar_wait(s ? bar1 : bar0, (uint32_t)(((it >> 1) - 1) & 1));  // MMAs of iteration it-2 have read stage s
-        store_stage(s);
-        if (it + 1 < n_iters) load_stage(it + 1);                                 // global loads in flight across the barrier
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // generic-proxy stores -> async proxy (tensor core)
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_base = smem_base + (uint32_t)s * STAGE_BYTES;
-            const uint32_t b_base = a_base + A_STAGE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t bh = make_desc(b_base + (uint32_t)((ks * 2 + 0) * 2) * NT * 16, NT * 16, 128);
-                const uint64_t bl = make_desc(b_base + (uint32_t)((ks * 2 + 1) * 2) * NT * 16, NT * 16, 128);
-#pragma unroll
-                for (int tile = 0; tile < 2; ++tile) {
-                    const uint64_t ah = make_desc(a_base + (uint32_t)((ks * 2 + 0) * 2) * TC_BM * 16 + tile * 2048, TC_BM * 16, 128);
-                    const uint64_t al = make_desc(a_base + (uint32_t)((ks * 2 + 1) * 2) * TC_BM * 16 + tile * 2048, TC_BM * 16, 128);
-                    const uint32_t d = tmem_base + (uint32_t)tile * NT;
-                    const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
-                    mma_tf32(d, al, bh, IDESC, first);   // small terms first, the dominant hi*hi product last
-                    mma_tf32(d, ah, bl, IDESC, 1u);
-                    mma_tf32(d, ah, bh, IDESC, 1u);
-                }
+            for (int j = 0; j < B_PER_T; ++j) {
+                const int v = tid + j * TC_LOADERS;
+                if (v < B_VEC) *reinterpret_cast<float4 *>(Bs + (size_t)v * 16) = b_reg[j];
             }
-            mma_commit(s ? bar1 : bar0);
+        };
+
+        load_stage(0);
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it & (TC_STAGES - 1);
+            const uint32_t use = (uint32_t)(it / TC_STAGES);  // how many times this stage slot has been filled before
+            if (use > 0) mbar_wait(bar_base + 8u * (TC_STAGES + s), (use - 1) & 1);  // tensor core has drained the slot
+            store_stage(s);
+            if (it + 1 < n_iters) load_stage(it + 1);            // next stage's global loads in flight
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * s);
         }
-    }
-    // ---- wait for the last MMAs (the commit of the final iteration covers everything issued before it) ----
-    {
-        const int last = n_iters - 1;
-        mbar_wait((last & 1) ? bar1 : bar0, (uint32_t)((last >> 1) & 1));
+        // ---- epilogue ---------------------------------------------------------------------------------
+        mbar_wait(bar_base + 8u * (2 * TC_STAGES), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    // ---- epilogue: thread = row (warp w reads TMEM lanes 32*(w%4).., accumulator tile w/4) ---------------
-    {
-        const int tile = warp >> 2, q = warp & 3;
-        const long long m = row0 + tid;  // tid == tile*128 + q*32 + lane
-        int n = 0, pos = 0;
-        if (m < Mtotal) {
-            n = (int)(m / p.S_out);
-            pos = (int)(m - (long long)n * p.S_out);
-        }
-        float *o = p.out + (size_t)n * p.Cout * p.S_out + pos;
-#pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * NT + c0);
-            TMEM_LD32(taddr, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        {
+            const int q = warp & 3, tile = (warp >> 2) & 1, half = warp >> 3;
+            const long long m = row0 + tile * 128 + q * 32 + (tid & 31);
+            int n = 0, pos = 0;
             if (m < Mtotal) {
+                n = (int)(m / p.S_out);
+                pos = (int)(m - (long long)n * p.S_out);
+            }
+            float *o = p.out + (size_t)n * p.Cout * p.S_out + pos;
+#pragma unroll 1
+            for (int c0 = half * 32; c0 < NT; c0 += 64) {
+                uint32_t v[32], u[32];
+                const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+                TMEM_LD32(tmem_base + lane_base + (uint32_t)(tile * NT + c0), v);           // main accumulator
+                TMEM_LD32(tmem_base + lane_base + (uint32_t)(2 * NT + tile * NT + c0), u);  // cross terms
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < Mtotal) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int co = c0 + j;
-                    if (co < p.Cout) {
-                        float r = __uint_as_float(v[j]) + __ldg(p.bias + co);
-                        if (p.relu) r = fmaxf(r, 0.0f);
-                        o[(size_t)co * p.S_out] = r;
+                    for (int j = 0; j < 32; ++j) {
+                        const int co = c0 + j;
+                        if (co < p.Cout) {
+                            float r = (__uint_as_float(v[j]) + __uint_as_float(u[j])) + __ldg(p.bias + co);
+                            if (p.relu) r = fmaxf(r, 0.0f);
+                            o[(size_t)co * p.S_out] = r;
+                        }
                     }
                 }
             }
         }
-        (void)lane;
+    } else {
+        // =========================== MMA issuer (warp 16) ==============================================
+        // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NT, M = 128
+        constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        if ((tid & 31) == 0) {
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it & (TC_STAGES - 1);
+                mbar_wait(bar_base + 8u * s, (uint32_t)((it / TC_STAGES) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_base = smem_base + (uint32_t)s * STAGE_BYTES;
+                const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t bh = make_desc(b_base + (uint32_t)((ks * 2 + 0) * 2) * NT * 16, NT * 16, 128);
+                    const uint64_t bl = make_desc(b_base + (uint32_t)((ks * 2 + 1) * 2) * NT * 16, NT * 16, 128);
+#pragma unroll
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const uint64_t ah = make_desc(a_base + (uint32_t)((ks * 2 + 0) * 2) * TC_BM * 16 + tile * 2048, TC_BM * 16, 128);
+                        const uint64_t al = make_desc(a_base + (uint32_t)((ks * 2 + 1) * 2) * TC_BM * 16 + tile * 2048, TC_BM * 16, 128);
+                        const uint32_t d_main = tmem_base + (uint32_t)(tile * NT);
+                        const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT + tile * NT);
+                        const uint32_t acc = (it == 0 && ks == 0) ? 0u : 1u;
+                        mma_tf32(d_cross, al, bh, IDESC, acc);
+                        mma_tf32(d_cross, ah, bl, IDESC, 1u);
+                        mma_tf32(d_main, ah, bh, IDESC, acc);
+                    }
+                }
+                mma_commit(bar_base + 8u * (TC_STAGES + s));   // slot s may be refilled once these MMAs have read it
+            }
+            mma_commit(bar_base + 8u * (2 * TC_STAGES));       // everything issued so far has completed -> epilogue
+        }
+        __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 16) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
@@ -311,7 +325,7 @@ int launch_tc(const ConvTcParams &p, int max_n, cudaStream_t st) {
     const long long maxM = (long long)max_n * p.S_out;
     const unsigned gx = (unsigned)((maxM + TC_BM - 1) / TC_BM);
     if (gx == 0) return BX_OK;
-    constexpr int smem = 2 * (A_STAGE_BYTES + 2 * 2 * 2 * NT * 16);
+    constexpr int smem = TC_STAGES * (A_STAGE_BYTES + 2 * 2 * 2 * NT * 16);
     static bool attr_done = false;
     if (!attr_done) {
         BX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<GEOM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
