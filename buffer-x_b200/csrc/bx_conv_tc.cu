@@ -17,9 +17,15 @@
 //                   A image [kunit(2)][row(256)][16 B]   LBO = 4096 B, SBO = 128 B
 //                   B image [kunit(2)][n(NT)][16 B]      LBO = NT*16 B, SBO = 128 B  (pre-arranged on the host)
 //               then fence.proxy.async + mbarrier arrive on full[stage].
+//               The B image of a stage is one contiguous 128*NT-byte block in global memory; loader thread 0
+//               fetches it with ONE cp.async.bulk (UBLKCP) that signals the same full[stage] mbarrier
+//               through its transaction count -- the weights never touch registers.
 //   warp 16     MMA issuer: waits full[stage], issues 12 tcgen05.mma (2 k-steps x 2 tiles x 3 products),
 //               tcgen05.commit -> empty[stage]; 4 stages in flight, no __syncthreads in the main loop.
-//   epilogue    (loader warps) tcgen05.ld of hi+lo accumulators -> bias (+ReLU) -> coalesced stores.
+//   epilogue    (loader warps) tcgen05.ld of main+cross accumulators -> bias (+ReLU) -> coalesced stores.
+// Long reductions are cut into `nseg` segments: at a segment boundary the loader warps drain the
+// accumulators into the (L2-resident) output tile with a properly rounded fp32 add and the next segment
+// restarts from zero, which bounds the number of truncating accumulations per accumulator.
 #include "bx_common.cuh"
 
 namespace {
@@ -31,6 +37,7 @@ struct ConvTcParams {
     const int *d_n;
     int Cin, Cout, D, H, W, kd, kh, kw, relu;
     int S_in, S_out, OD, OH, OW, T;
+    int seg_len;  // stages per segment (>= n_iters: single segment)
     const float *equi_s, *equi_t;
     const int *s_mids, *t_mids;
 };
@@ -89,27 +96,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
-#define TMEM_LD32(taddr, v)                                                                                    \
-    asm volatile(                                                                                              \
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, " \
-        "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"    \
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),      \
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),             \
-          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),           \
-          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),           \
-          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                                \
-        : "r"(taddr)                                                                                           \
+#define TMEM_LD16(taddr, v)                                                                                   \
+    asm volatile(                                                                                             \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, " \
+        "%14, %15}, [%16];"                                                                                   \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),     \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+        : "r"(taddr)                                                                                          \
         : "memory")
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 template <int GEOM, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcParams p) {
     constexpr int B_STAGE_BYTES = 2 * 2 * 2 * NT * 16;  // [kstep][split][kunit][n][16B]
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     constexpr int TMEM_COLS = 4 * NT;  // two tiles x (main + cross-term accumulator): 128 / 256 / 512
-    constexpr int B_VEC = B_STAGE_BYTES / 16;
-    constexpr int B_PER_T = (B_VEC + TC_LOADERS - 1) / TC_LOADERS;  // 2 / 1 / 1
+    // barriers: full[4] (16 loader-warp arrivals + 1 expect_tx arrival), empty[4], segdone, accfree
+    constexpr int BAR_EMPTY = TC_STAGES, BAR_SEGDONE = 2 * TC_STAGES, BAR_ACCFREE = 2 * TC_STAGES + 1;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 1];  // full[4], empty[4], done
+    __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 2];
     __shared__ uint32_t tmem_base_s;
 
     const int n_samples = p.d_n ? *p.d_n : p.n;
@@ -118,6 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     if (row0 >= Mtotal) return;  // uniform per CTA, before any barrier / TMEM allocation
     const int tid = threadIdx.x, warp = tid >> 5;
     const int n_iters = (p.Cin / 16) * p.T;  // stage = (16-channel chunk, tap); chunk outer, tap inner
+    const int seg_len = p.seg_len;
 
     if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
@@ -125,10 +140,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     }
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(smem_u32(&bars[s]), TC_LOADERS / 32);   // full: one arrival per loader warp
-            mbar_init(smem_u32(&bars[TC_STAGES + s]), 1);     // empty: one tcgen05.commit
+            mbar_init(smem_u32(&bars[s]), TC_LOADERS / 32 + 1);
+            mbar_init(smem_u32(&bars[BAR_EMPTY + s]), 1);
         }
-        mbar_init(smem_u32(&bars[2 * TC_STAGES]), 1);
+        mbar_init(smem_u32(&bars[BAR_SEGDONE]), 1);
+        mbar_init(smem_u32(&bars[BAR_ACCFREE]), TC_LOADERS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -170,9 +186,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         // incremental (chunk, tap) counters: no integer division in the loop
         int chunk = 0, t = 0, dz = 0, dy = 0, dx = 0;
         float a_reg[8];
-        float4 b_reg[B_PER_T];
 
-        auto load_stage = [&](int it) {
+        auto load_stage = [&]() {
             int offA = 0, offB = 0;
             bool ok = lvalid;
             if (GEOM == BX_GEOM_CYL3D || GEOM == BX_GEOM_CYL2D) {
@@ -200,12 +215,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 }
                 a_reg[kk] = v;
             }
-            const float4 *wsrc = reinterpret_cast<const float4 *>(p.w) + (size_t)it * B_VEC;
-#pragma unroll
-            for (int j = 0; j < B_PER_T; ++j) {
-                const int v = tid + j * TC_LOADERS;
-                if (v < B_VEC) b_reg[j] = __ldg(wsrc + v);
-            }
             // advance to the next (chunk, tap)
             ++t;
             if (++dx == p.kw) {
@@ -216,7 +225,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         };
         auto store_stage = [&](int s) {
             unsigned char *As = smem + (size_t)s * STAGE_BYTES;
-            unsigned char *Bs = As + A_STAGE_BYTES;
 #pragma unroll
             for (int ku = 0; ku < 2; ++ku) {
                 float hi[4], lo[4];
@@ -230,63 +238,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 0) * 2 + ku) * TC_BM + row) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 1) * 2 + ku) * TC_BM + row) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
-#pragma unroll
-            for (int j = 0; j < B_PER_T; ++j) {
-                const int v = tid + j * TC_LOADERS;
-                if (v < B_VEC) *reinterpret_cast<float4 *>(Bs + (size_t)v * 16) = b_reg[j];
-            }
         };
-
-        load_stage(0);
-        for (int it = 0; it < n_iters; ++it) {
-            const int s = it & (TC_STAGES - 1);
-            const uint32_t use = (uint32_t)(it / TC_STAGES);  // how many times this stage slot has been filled before
-            if (use > 0) mbar_wait(bar_base + 8u * (TC_STAGES + s), (use - 1) & 1);  // tensor core has drained the slot
-            store_stage(s);
-            if (it + 1 < n_iters) load_stage(it + 1);            // next stage's global loads in flight
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * s);
+        // accumulators -> output tile.  mode 0: out = acc (first drain); 1: out += acc; 2: final (bias, ReLU)
+        const int eq = warp & 3, etile = (warp >> 2) & 1, ehalf = warp >> 3;
+        const long long em = row0 + etile * 128 + eq * 32 + (tid & 31);
+        int en = 0, epos = 0;
+        if (em < Mtotal) {
+            en = (int)(em / p.S_out);
+            epos = (int)(em - (long long)en * p.S_out);
         }
-        // ---- epilogue ---------------------------------------------------------------------------------
-        mbar_wait(bar_base + 8u * (2 * TC_STAGES), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {
-            const int q = warp & 3, tile = (warp >> 2) & 1, half = warp >> 3;
-            const long long m = row0 + tile * 128 + q * 32 + (tid & 31);
-            int n = 0, pos = 0;
-            if (m < Mtotal) {
-                n = (int)(m / p.S_out);
-                pos = (int)(m - (long long)n * p.S_out);
-            }
-            float *o = p.out + (size_t)n * p.Cout * p.S_out + pos;
+        float *eo = p.out + (size_t)en * p.Cout * p.S_out + epos;
+        auto drain = [&](int mode, bool have_prev) {
+            const uint32_t lane_base = (uint32_t)(eq * 32) << 16;
 #pragma unroll 1
-            for (int c0 = half * 32; c0 < NT; c0 += 64) {
-                uint32_t v[32], u[32];
-                const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-                TMEM_LD32(tmem_base + lane_base + (uint32_t)(tile * NT + c0), v);           // main accumulator
-                TMEM_LD32(tmem_base + lane_base + (uint32_t)(2 * NT + tile * NT + c0), u);  // cross terms
+            for (int c0 = ehalf * 16; c0 < NT; c0 += 32) {
+                uint32_t v[16], u[16];
+                TMEM_LD16(tmem_base + lane_base + (uint32_t)(etile * NT + c0), v);           // main accumulator
+                TMEM_LD16(tmem_base + lane_base + (uint32_t)(2 * NT + etile * NT + c0), u);  // cross terms
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (m < Mtotal) {
+                if (em < Mtotal) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         const int co = c0 + j;
                         if (co < p.Cout) {
-                            float r = (__uint_as_float(v[j]) + __uint_as_float(u[j])) + __ldg(p.bias + co);
-                            if (p.relu) r = fmaxf(r, 0.0f);
-                            o[(size_t)co * p.S_out] = r;
+                            float r = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                            float *dst = eo + (size_t)co * p.S_out;
+                            if (have_prev) r += *dst;
+                            if (mode == 2) {
+                                r += __ldg(p.bias + co);
+                                if (p.relu) r = fmaxf(r, 0.0f);
+                            }
+                            *dst = r;
                         }
                     }
                 }
             }
+        };
+
+        load_stage();
+        int seg = 0;
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it & (TC_STAGES - 1);
+            if (it > 0 && it - seg * seg_len == seg_len) {
+                // segment boundary: every MMA of the finished segment has completed -> drain, then free the accumulators
+                mbar_wait(bar_base + 8u * BAR_SEGDONE, (uint32_t)(seg & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                drain(1, seg > 0);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * BAR_ACCFREE);
+                ++seg;
+            }
+            const uint32_t use = (uint32_t)(it / TC_STAGES);  // how many times this stage slot has been filled before
+            if (use > 0) mbar_wait(bar_base + 8u * (BAR_EMPTY + s), (use - 1) & 1);  // tensor core has drained the slot
+            if (tid == 0) {  // weights of this stage: one bulk copy, completion counted on full[s]
+                mbar_arrive_expect_tx(bar_base + 8u * s, (uint32_t)B_STAGE_BYTES);
+                bulk_g2s(smem_base + (uint32_t)s * STAGE_BYTES + A_STAGE_BYTES,
+                         reinterpret_cast<const unsigned char *>(p.w) + (size_t)it * B_STAGE_BYTES, (uint32_t)B_STAGE_BYTES, bar_base + 8u * s);
+            }
+            store_stage(s);
+            if (it + 1 < n_iters) load_stage();                   // next stage's activations in flight
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * s);
         }
+        // ---- final epilogue ------------------------------------------------------------------------------
+        mbar_wait(bar_base + 8u * BAR_SEGDONE, (uint32_t)(seg & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        drain(2, seg > 0);
     } else {
         // =========================== MMA issuer (warp 16) ==============================================
         // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NT, M = 128
         constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         if ((tid & 31) == 0) {
+            int seg = 0;
             for (int it = 0; it < n_iters; ++it) {
                 const int s = it & (TC_STAGES - 1);
+                bool seg_first = (it == 0);
+                if (it > 0 && it - seg * seg_len == seg_len) {
+                    mbar_wait(bar_base + 8u * BAR_ACCFREE, (uint32_t)(seg & 1));  // loaders have drained the accumulators
+                    ++seg;
+                    seg_first = true;
+                }
                 mbar_wait(bar_base + 8u * s, (uint32_t)((it / TC_STAGES) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_base = smem_base + (uint32_t)s * STAGE_BYTES;
@@ -301,15 +334,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                         const uint64_t al = make_desc(a_base + (uint32_t)((ks * 2 + 1) * 2) * TC_BM * 16 + tile * 2048, TC_BM * 16, 128);
                         const uint32_t d_main = tmem_base + (uint32_t)(tile * NT);
                         const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT + tile * NT);
-                        const uint32_t acc = (it == 0 && ks == 0) ? 0u : 1u;
+                        const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
                         mma_tf32(d_cross, al, bh, IDESC, acc);
                         mma_tf32(d_cross, ah, bl, IDESC, 1u);
                         mma_tf32(d_main, ah, bh, IDESC, acc);
                     }
                 }
-                mma_commit(bar_base + 8u * (TC_STAGES + s));   // slot s may be refilled once these MMAs have read it
+                mma_commit(bar_base + 8u * (BAR_EMPTY + s));   // slot s may be refilled once these MMAs have read it
+                if (it == n_iters - 1 || (it + 1) - seg * seg_len == seg_len) mma_commit(bar_base + 8u * BAR_SEGDONE);
             }
-            mma_commit(bar_base + 8u * (2 * TC_STAGES));       // everything issued so far has completed -> epilogue
         }
         __syncwarp();
     }
@@ -359,6 +392,11 @@ BX_API int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const 
     p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
     p.equi_s = equi_s; p.equi_t = equi_t; p.s_mids = s_mids; p.t_mids = t_mids;
     p.T = kd * kh * kw;
+    {   // segments: at most ~24 stages (= 48 truncating accumulations) per accumulator
+        const int n_iters = (Cin / 16) * p.T;
+        const int nseg = (n_iters + 23) / 24;
+        p.seg_len = (n_iters + nseg - 1) / nseg;
+    }
     cudaStream_t st = bx_stream(stream);
     switch (geom) {
         case BX_GEOM_CYL3D:
