@@ -2,30 +2,31 @@
 //
 // Same implicit GEMM as bx_conv.cu (rows = (sample, output position), cols = Cout, K = taps*Cin, padding
 // geometry folded into the loader), but the inner product runs as tcgen05.mma kind::tf32 with fp32
-// accumulators in tensor memory.  fp32-grade accuracy (descriptor parity 1e-4 rel) comes from the
-// 3xTF32 split  x = hi + lo  (hi = x with the 13 low mantissa bits cleared, lo = x - hi, exact):
-//     a*b ~= ah*bh + ah*bl + al*bh          (dropped al*bl ~ 2^-20 relative)
-// The tensor core accumulates with truncation, one truncation per tcgen05.mma; the small cross terms
-// therefore get their OWN accumulator (their truncation error is 2^-11 smaller) and only the ah*bh
-// products go through the main one -- 3x fewer truncations on the value that matters.
+// accumulators in tensor memory.  fp32-grade accuracy (descriptor parity 1e-4 rel) needs two things:
+//   1. the 3xTF32 split  x = hi + lo  (hi = x with the 13 low mantissa bits cleared, lo = x - hi, exact):
+//          a*b ~= ah*bh + ah*bl + al*bh          (dropped al*bl ~ 2^-20 relative)
+//   2. short accumulation chains: the tensor core accumulates with truncation, so the error of a chain grows
+//      linearly with its length (measured on B200, K = 1152: 5x the fp32-FFMA error for one chain, below it
+//      for chains of 12 MMAs; tools/tc_precision.py).  The ah*bh products therefore go to a PING-PONG pair
+//      of TMEM accumulators that is cut every TC_SEG stages (12 MMAs); finished segments are added with
+//      round-to-nearest into fp32 running sums held in the loader threads' registers while the tensor core
+//      already fills the other accumulator.  The cross terms (2^-11 smaller) keep one long chain.
 //
-// Warp-specialised CTA (544 threads, 1 CTA / SM, 256 GEMM rows = two M=128 tiles sharing each B tile):
-//   warps 0-15  loaders : thread -> (row = t & 255, k-step = t >> 8).  Per stage (16 input channels of one
-//               tap) a thread fetches its 8 activations (L1-resident across the taps of a chunk: the k
-//               order is chunk-outer / tap-inner), splits them and writes hi/lo with 16-byte STS straight
+// Warp-specialised CTA (544 threads, 1 CTA / SM, 128 GEMM rows = one M=128 tile, N = NT columns):
+//   warps 0-15  loaders : thread -> (row = t & 127, 16-byte K unit = t >> 7).  Per stage (16 input channels
+//               of one tap; chunk-outer / tap-inner order keeps a chunk's activations in L1 across its taps) a
+//               thread fetches 4 activations, splits them and writes hi/lo with one 16-byte STS each straight
 //               into the canonical K-major no-swizzle UMMA layout (core matrix = 8 rows x 16 B):
-//                   A image [kunit(2)][row(256)][16 B]   LBO = 4096 B, SBO = 128 B
-//                   B image [kunit(2)][n(NT)][16 B]      LBO = NT*16 B, SBO = 128 B  (pre-arranged on the host)
-//               then fence.proxy.async + mbarrier arrive on full[stage].
-//               The B image of a stage is one contiguous 128*NT-byte block in global memory; loader thread 0
-//               fetches it with ONE cp.async.bulk (UBLKCP) that signals the same full[stage] mbarrier
-//               through its transaction count -- the weights never touch registers.
-//   warp 16     MMA issuer: waits full[stage], issues 12 tcgen05.mma (2 k-steps x 2 tiles x 3 products),
-//               tcgen05.commit -> empty[stage]; 4 stages in flight, no __syncthreads in the main loop.
-//   epilogue    (loader warps) tcgen05.ld of main+cross accumulators -> bias (+ReLU) -> coalesced stores.
-// Long reductions are cut into `nseg` segments: at a segment boundary the loader warps drain the
-// accumulators into the (L2-resident) output tile with a properly rounded fp32 add and the next segment
-// restarts from zero, which bounds the number of truncating accumulations per accumulator.
+//                   A image [kstep][split][kunit][row(128)][16 B]   LBO = 2048 B, SBO = 128 B
+//                   B image [kstep][split][kunit][n(NT)][16 B]      LBO = NT*16 B, SBO = 128 B (host-arranged)
+//               then fence.proxy.async + mbarrier arrive on full[stage].  Thread 0 fetches the stage's B image
+//               (one contiguous 128*NT-byte block) with ONE cp.async.bulk whose transaction count lands on the
+//               same full[stage] barrier -- the weights never touch registers.
+//               Every TC_SEG stages each loader warp drains its 32 lanes x NT/4 columns of the finished main
+//               accumulator (tcgen05.ld) into its running sums and releases the accumulator (accfree barrier).
+//   warp 16     MMA issuer: waits full[stage], issues 6 tcgen05.mma (2 k-steps x {al*bh, ah*bl, ah*bh}),
+//               tcgen05.commit -> empty[stage]; 6 stages in flight, no __syncthreads in the main loop.
+//   epilogue    running sums + cross accumulator + bias (+ReLU) -> coalesced stores of out[n][co][pos].
 #include "bx_common.cuh"
 
 namespace {
@@ -37,16 +38,16 @@ struct ConvTcParams {
     const int *d_n;
     int Cin, Cout, D, H, W, kd, kh, kw, relu;
     int S_in, S_out, OD, OH, OW, T;
-    int seg_len;  // stages per segment (>= n_iters: single segment)
+    int seg_len;  // stages per main-accumulator segment
     const float *equi_s, *equi_t;
     const int *s_mids, *t_mids;
 };
 
 constexpr int TC_LOADERS = 512;
 constexpr int TC_THREADS = TC_LOADERS + 32;
-constexpr int TC_BM = 256;
-constexpr int TC_STAGES = 4;
-constexpr int A_STAGE_BYTES = 2 * 2 * 2 * TC_BM * 16;  // [kstep][split][kunit][row][16B] = 32 KB
+constexpr int TC_BM = 128;
+constexpr int TC_STAGES = 6;
+constexpr int A_STAGE_BYTES = 2 * 2 * 2 * TC_BM * 16;  // [kstep][split][kunit][row][16B] = 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -82,6 +83,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -96,34 +107,44 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
-#define TMEM_LD16(taddr, v)                                                                                   \
-    asm volatile(                                                                                             \
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, " \
-        "%14, %15}, [%16];"                                                                                   \
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),     \
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
-        : "r"(taddr)                                                                                          \
-        : "memory")
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+// tcgen05.ld 32 lanes x CW consecutive 32-bit columns (CW = 8, 16 or 32) into v[0..CW)
+template <int CW>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CW]) {
+    if constexpr (CW == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(taddr)
+                     : "memory");
+    } else if constexpr (CW == 16) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr)
+            : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+    }
 }
 
 template <int GEOM, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcParams p) {
     constexpr int B_STAGE_BYTES = 2 * 2 * 2 * NT * 16;  // [kstep][split][kunit][n][16B]
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    constexpr int TMEM_COLS = 4 * NT;  // two tiles x (main + cross-term accumulator): 128 / 256 / 512
-    // barriers: full[4] (16 loader-warp arrivals + 1 expect_tx arrival), empty[4], segdone, accfree
-    constexpr int BAR_EMPTY = TC_STAGES, BAR_SEGDONE = 2 * TC_STAGES, BAR_ACCFREE = 2 * TC_STAGES + 1;
+    constexpr int TMEM_COLS = 4 * NT;   // main[0], main[1], cross (+ NT spare: the allocation is a power of two)
+    constexpr int CW = NT / 4;          // accumulator columns owned by one loader warp
+    // barriers: full[ST] (16 loader-warp arrivals + 1 expect_tx arrival), empty[ST], segdone[2], accfree[2]
+    constexpr int BAR_EMPTY = TC_STAGES, BAR_SEGDONE = 2 * TC_STAGES, BAR_ACCFREE = 2 * TC_STAGES + 2;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 2];
+    __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
 
     const int n_samples = p.d_n ? *p.d_n : p.n;
@@ -132,7 +153,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     if (row0 >= Mtotal) return;  // uniform per CTA, before any barrier / TMEM allocation
     const int tid = threadIdx.x, warp = tid >> 5;
     const int n_iters = (p.Cin / 16) * p.T;  // stage = (16-channel chunk, tap); chunk outer, tap inner
-    const int seg_len = p.seg_len;
+    const int G = p.seg_len;
+    const int nseg = (n_iters + G - 1) / G;
 
     if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
@@ -143,8 +165,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             mbar_init(smem_u32(&bars[s]), TC_LOADERS / 32 + 1);
             mbar_init(smem_u32(&bars[BAR_EMPTY + s]), 1);
         }
-        mbar_init(smem_u32(&bars[BAR_SEGDONE]), 1);
-        mbar_init(smem_u32(&bars[BAR_ACCFREE]), TC_LOADERS / 32);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bars[BAR_SEGDONE + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_ACCFREE + s]), TC_LOADERS / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -156,7 +180,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
 
     if (warp < 16) {
         // =========================== loaders ===========================================================
-        const int row = tid & 255, ks = tid >> 8;
+        const int row = tid & 127, part = tid >> 7;      // part: which 16-byte K unit (4 channels) of the stage
+        const int ks = part >> 1, ku = part & 1;
         const long long lm = row0 + row;
         const bool lvalid = lm < Mtotal;
         int ln = 0, oz = 0, oy = 0, ox = 0;
@@ -183,9 +208,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             pa = p.in + (size_t)ln * p.Cin * p.S_in;
         }
         const int cstride = (GEOM == BX_GEOM_CYL2D || GEOM == BX_GEOM_COSTVOL) ? 140 : (GEOM == BX_GEOM_CYL3D ? 420 : p.S_in);
-        // incremental (chunk, tap) counters: no integer division in the loop
-        int chunk = 0, t = 0, dz = 0, dy = 0, dx = 0;
-        float a_reg[8];
+        int chunk = 0, t = 0, dz = 0, dy = 0, dx = 0;   // incremental (chunk, tap) counters: no division in the loop
+        float a_reg[4];
 
         auto load_stage = [&]() {
             int offA = 0, offB = 0;
@@ -205,17 +229,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 offA = (1 + kk) * 20 + sh;
                 offB = (1 + kk) * 20 + ll;
             }
-            const float *src = pa + (size_t)(chunk * 16 + ks * 8) * cstride + offA;
+            const int c0 = chunk * 16 + part * 4;
+            const float *src = pa + (size_t)c0 * cstride + offA;
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
+            for (int kk = 0; kk < 4; ++kk) {
                 float v = 0.0f;
                 if (ok) {
-                    if (GEOM == BX_GEOM_COSTVOL) v = src[kk * cstride] - pb[(size_t)(chunk * 16 + ks * 8 + kk) * 140 + offB];
+                    if (GEOM == BX_GEOM_COSTVOL) v = src[kk * cstride] - pb[(size_t)(c0 + kk) * 140 + offB];
                     else v = __ldg(src + kk * cstride);
                 }
                 a_reg[kk] = v;
             }
-            // advance to the next (chunk, tap)
             ++t;
             if (++dx == p.kw) {
                 dx = 0;
@@ -225,123 +249,120 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         };
         auto store_stage = [&](int s) {
             unsigned char *As = smem + (size_t)s * STAGE_BYTES;
+            float hi[4], lo[4];
 #pragma unroll
-            for (int ku = 0; ku < 2; ++ku) {
-                float hi[4], lo[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float x = a_reg[ku * 4 + j];
-                    hi[j] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-                    lo[j] = x - hi[j];
-                }
-                // [kstep][split][kunit][row][16B]
-                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 0) * 2 + ku) * TC_BM + row) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 1) * 2 + ku) * TC_BM + row) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            for (int j = 0; j < 4; ++j) {
+                hi[j] = __uint_as_float(__float_as_uint(a_reg[j]) & 0xFFFFE000u);
+                lo[j] = a_reg[j] - hi[j];
             }
+            // [kstep][split][kunit][row][16B]
+            *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 0) * 2 + ku) * TC_BM + row) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 1) * 2 + ku) * TC_BM + row) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         };
-        // accumulators -> output tile.  mode 0: out = acc (first drain); 1: out += acc; 2: final (bias, ReLU)
-        const int eq = warp & 3, etile = (warp >> 2) & 1, ehalf = warp >> 3;
-        const long long em = row0 + etile * 128 + eq * 32 + (tid & 31);
-        int en = 0, epos = 0;
-        if (em < Mtotal) {
-            en = (int)(em / p.S_out);
-            epos = (int)(em - (long long)en * p.S_out);
-        }
-        float *eo = p.out + (size_t)en * p.Cout * p.S_out + epos;
-        auto drain = [&](int mode, bool have_prev) {
-            const uint32_t lane_base = (uint32_t)(eq * 32) << 16;
-#pragma unroll 1
-            for (int c0 = ehalf * 16; c0 < NT; c0 += 32) {
-                uint32_t v[16], u[16];
-                TMEM_LD16(tmem_base + lane_base + (uint32_t)(etile * NT + c0), v);           // main accumulator
-                TMEM_LD16(tmem_base + lane_base + (uint32_t)(2 * NT + etile * NT + c0), u);  // cross terms
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (em < Mtotal) {
+
+        // ---- accumulator ownership of this warp: TMEM lanes 32*(warp&3).., columns CW*(warp>>2).. ----------
+        const int eq = warp & 3, ecs = warp >> 2;
+        const uint32_t tm_lane = (uint32_t)(eq * 32) << 16;
+        float run[CW];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int co = c0 + j;
-                        if (co < p.Cout) {
-                            float r = __uint_as_float(v[j]) + __uint_as_float(u[j]);
-                            float *dst = eo + (size_t)co * p.S_out;
-                            if (have_prev) r += *dst;
-                            if (mode == 2) {
-                                r += __ldg(p.bias + co);
-                                if (p.relu) r = fmaxf(r, 0.0f);
-                            }
-                            *dst = r;
-                        }
-                    }
-                }
+        for (int j = 0; j < CW; ++j) run[j] = 0.0f;
+        auto drain = [&](int j, bool release) {       // add finished segment j (main set j&1) into the running sums
+            const int set = j & 1;
+            mbar_wait(bar_base + 8u * (BAR_SEGDONE + set), (uint32_t)((j >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t v[CW];
+            tmem_ld<CW>(tmem_base + tm_lane + (uint32_t)(set * NT + ecs * CW), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < CW; ++c) run[c] += __uint_as_float(v[c]);
+            if (release) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * (BAR_ACCFREE + set));
             }
         };
 
         load_stage();
-        int seg = 0;
+        int next_drain = 0, s = 0;
+        uint32_t use = 0;                                 // how many times slot s has been filled before
         for (int it = 0; it < n_iters; ++it) {
-            const int s = it & (TC_STAGES - 1);
-            if (it > 0 && it - seg * seg_len == seg_len) {
-                // segment boundary: every MMA of the finished segment has completed -> drain, then free the accumulators
-                mbar_wait(bar_base + 8u * BAR_SEGDONE, (uint32_t)(seg & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                drain(1, seg > 0);
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * BAR_ACCFREE);
-                ++seg;
+            if (next_drain < nseg - 1 && it >= (next_drain + 1) * G + (G < TC_STAGES ? G : TC_STAGES)) {
+                drain(next_drain, true);                  // its MMAs are several stages behind us: short wait
+                ++next_drain;
             }
-            const uint32_t use = (uint32_t)(it / TC_STAGES);  // how many times this stage slot has been filled before
-            if (use > 0) mbar_wait(bar_base + 8u * (BAR_EMPTY + s), (use - 1) & 1);  // tensor core has drained the slot
+            if (use > 0) mbar_wait(bar_base + 8u * (BAR_EMPTY + s), (use - 1) & 1);  // tensor core has read the slot
             if (tid == 0) {  // weights of this stage: one bulk copy, completion counted on full[s]
                 mbar_arrive_expect_tx(bar_base + 8u * s, (uint32_t)B_STAGE_BYTES);
                 bulk_g2s(smem_base + (uint32_t)s * STAGE_BYTES + A_STAGE_BYTES,
                          reinterpret_cast<const unsigned char *>(p.w) + (size_t)it * B_STAGE_BYTES, (uint32_t)B_STAGE_BYTES, bar_base + 8u * s);
             }
             store_stage(s);
-            if (it + 1 < n_iters) load_stage();                   // next stage's activations in flight
+            if (it + 1 < n_iters) load_stage();           // next stage's activations in flight
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * s);
+            if (++s == TC_STAGES) { s = 0; ++use; }
         }
-        // ---- final epilogue ------------------------------------------------------------------------------
-        mbar_wait(bar_base + 8u * BAR_SEGDONE, (uint32_t)(seg & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        drain(2, seg > 0);
+        while (next_drain < nseg) {
+            drain(next_drain, false);
+            ++next_drain;
+        }
+        // ---- epilogue: running sums + cross accumulator + bias (+ReLU) ------------------------------------
+        {
+            uint32_t u[CW];
+            tmem_ld<CW>(tmem_base + tm_lane + (uint32_t)(2 * NT + ecs * CW), u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const long long em = row0 + eq * 32 + (tid & 31);
+            if (em < Mtotal) {
+                const int en = (int)(em / p.S_out);
+                const int epos = (int)(em - (long long)en * p.S_out);
+                float *eo = p.out + (size_t)en * p.Cout * p.S_out + epos;
+#pragma unroll
+                for (int c = 0; c < CW; ++c) {
+                    const int co = ecs * CW + c;
+                    if (co < p.Cout) {
+                        float r = (run[c] + __uint_as_float(u[c])) + __ldg(p.bias + co);
+                        if (p.relu) r = fmaxf(r, 0.0f);
+                        eo[(size_t)co * p.S_out] = r;
+                    }
+                }
+            }
+        }
     } else {
         // =========================== MMA issuer (warp 16) ==============================================
         // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NT, M = 128
         constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         if ((tid & 31) == 0) {
-            int seg = 0;
+            int s = 0, seg = 0, in_seg = 0;
+            uint32_t use = 0;
+            const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT);
             for (int it = 0; it < n_iters; ++it) {
-                const int s = it & (TC_STAGES - 1);
-                bool seg_first = (it == 0);
-                if (it > 0 && it - seg * seg_len == seg_len) {
-                    mbar_wait(bar_base + 8u * BAR_ACCFREE, (uint32_t)(seg & 1));  // loaders have drained the accumulators
-                    ++seg;
-                    seg_first = true;
+                if (in_seg == 0 && seg >= 2) {
+                    // segment `seg` reuses main set seg&1: segment seg-2 must have been drained
+                    mbar_wait(bar_base + 8u * (BAR_ACCFREE + (seg & 1)), (uint32_t)(((seg - 2) >> 1) & 1));
                 }
-                mbar_wait(bar_base + 8u * s, (uint32_t)((it / TC_STAGES) & 1));
+                mbar_wait(bar_base + 8u * s, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_base = smem_base + (uint32_t)s * STAGE_BYTES;
                 const uint32_t b_base = a_base + A_STAGE_BYTES;
+                const uint32_t d_main = tmem_base + (uint32_t)((seg & 1) * NT);
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
                     const uint64_t bh = make_desc(b_base + (uint32_t)((ks * 2 + 0) * 2) * NT * 16, NT * 16, 128);
                     const uint64_t bl = make_desc(b_base + (uint32_t)((ks * 2 + 1) * 2) * NT * 16, NT * 16, 128);
-#pragma unroll
-                    for (int tile = 0; tile < 2; ++tile) {
-                        const uint64_t ah = make_desc(a_base + (uint32_t)((ks * 2 + 0) * 2) * TC_BM * 16 + tile * 2048, TC_BM * 16, 128);
-                        const uint64_t al = make_desc(a_base + (uint32_t)((ks * 2 + 1) * 2) * TC_BM * 16 + tile * 2048, TC_BM * 16, 128);
-                        const uint32_t d_main = tmem_base + (uint32_t)(tile * NT);
-                        const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT + tile * NT);
-                        const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
-                        mma_tf32(d_cross, al, bh, IDESC, acc);
-                        mma_tf32(d_cross, ah, bl, IDESC, 1u);
-                        mma_tf32(d_main, ah, bh, IDESC, acc);
-                    }
+                    const uint64_t ah = make_desc(a_base + (uint32_t)((ks * 2 + 0) * 2) * TC_BM * 16, TC_BM * 16, 128);
+                    const uint64_t al = make_desc(a_base + (uint32_t)((ks * 2 + 1) * 2) * TC_BM * 16, TC_BM * 16, 128);
+                    mma_tf32(d_cross, al, bh, IDESC, (it == 0 && ks == 0) ? 0u : 1u);
+                    mma_tf32(d_cross, ah, bl, IDESC, 1u);
+                    mma_tf32(d_main, ah, bh, IDESC, (in_seg == 0 && ks == 0) ? 0u : 1u);
                 }
                 mma_commit(bar_base + 8u * (BAR_EMPTY + s));   // slot s may be refilled once these MMAs have read it
-                if (it == n_iters - 1 || (it + 1) - seg * seg_len == seg_len) mma_commit(bar_base + 8u * BAR_SEGDONE);
+                if (++s == TC_STAGES) { s = 0; ++use; }
+                if (++in_seg == G || it == n_iters - 1) {
+                    mma_commit(bar_base + 8u * (BAR_SEGDONE + (seg & 1)));
+                    in_seg = 0;
+                    ++seg;
+                }
             }
         }
         __syncwarp();
@@ -380,6 +401,15 @@ int dispatch_nt(const ConvTcParams &p, int max_n, cudaStream_t st) {
 
 BX_API int bx_conv_tc_ntile(int Cout) { return Cout > 64 ? 128 : (Cout > 32 ? 64 : 32); }
 
+// Tuning knob (experiments / tests): maximum number of 16-channel stages accumulated in tensor memory
+// before the accumulators are drained with a rounded fp32 add.  <= 0 restores the default.
+static int g_tc_max_stages = 6;
+BX_API int bx_conv_tc_set_segment_stages(int stages) {
+    const int old = g_tc_max_stages;
+    g_tc_max_stages = stages > 0 ? stages : 6;
+    return old;
+}
+
 BX_API int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const float *bias, float *out, int n,
                             const int32_t *d_n, int Cin, int Cout, int D, int H, int W, int kd, int kh, int kw, int relu,
                             const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
@@ -392,11 +422,7 @@ BX_API int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const 
     p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
     p.equi_s = equi_s; p.equi_t = equi_t; p.s_mids = s_mids; p.t_mids = t_mids;
     p.T = kd * kh * kw;
-    {   // segments: at most ~24 stages (= 48 truncating accumulations) per accumulator
-        const int n_iters = (Cin / 16) * p.T;
-        const int nseg = (n_iters + 23) / 24;
-        p.seg_len = (n_iters + nseg - 1) / nseg;
-    }
+    p.seg_len = g_tc_max_stages;   // main-accumulator segment: 6 stages = 12 truncating accumulations
     cudaStream_t st = bx_stream(stream);
     switch (geom) {
         case BX_GEOM_CYL3D:
