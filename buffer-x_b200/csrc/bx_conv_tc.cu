@@ -13,10 +13,12 @@
 //      already fills the other accumulator.  The cross terms (2^-11 smaller) keep one long chain.
 //
 // Warp-specialised CTA (544 threads, 1 CTA / SM, 128 GEMM rows = one M=128 tile, N = NT columns):
-//   warps 0-15  loaders : thread -> (row = t & 127, 16-byte K unit = t >> 7).  Per stage (16 input channels
-//               of one tap; chunk-outer / tap-inner order keeps a chunk's activations in L1 across its taps) a
-//               thread fetches 4 activations, splits them and writes hi/lo with one 16-byte STS each straight
-//               into the canonical K-major no-swizzle UMMA layout (core matrix = 8 rows x 16 B):
+//   warps 0-15  loaders : four groups of four warps; group g owns the stages it = g, g+4, g+8, ... so a warp
+//               touches a barrier once per FOUR stages (mbarrier / proxy-fence latencies stay off the critical
+//               path).  thread -> row = t & 127.  Per owned stage (16 input channels of one tap; chunk-outer /
+//               tap-inner order keeps a chunk's activations in L1 across its taps) a thread fetches its row's 16
+//               activations, splits them and writes hi/lo with 16-byte STS straight into the canonical K-major
+//               no-swizzle UMMA layout (core matrix = 8 rows x 16 B):
 //                   A image [kstep][split][kunit][row(128)][16 B]   LBO = 2048 B, SBO = 128 B
 //                   B image [kstep][split][kunit][n(NT)][16 B]      LBO = NT*16 B, SBO = 128 B (host-arranged)
 //               then fence.proxy.async + mbarrier arrive on full[stage].  Thread 0 fetches the stage's B image
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     }
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(smem_u32(&bars[s]), TC_LOADERS / 32 + 1);
+            mbar_init(smem_u32(&bars[s]), 4 + 1);            // full: the 4 warps of the owning group + the expect_tx arrival
             mbar_init(smem_u32(&bars[BAR_EMPTY + s]), 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -180,8 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
 
     if (warp < 16) {
         // =========================== loaders ===========================================================
-        const int row = tid & 127, part = tid >> 7;      // part: which 16-byte K unit (4 channels) of the stage
-        const int ks = part >> 1, ku = part & 1;
+        const int row = tid & 127, grp = tid >> 7;       // grp: which stages (it % 4 == grp) this thread fills
         const long long lm = row0 + row;
         const bool lvalid = lm < Mtotal;
         int ln = 0, oz = 0, oy = 0, ox = 0;
@@ -209,9 +210,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         }
         const int cstride = (GEOM == BX_GEOM_CYL2D || GEOM == BX_GEOM_COSTVOL) ? 140 : (GEOM == BX_GEOM_CYL3D ? 420 : p.S_in);
         int chunk = 0, t = 0, dz = 0, dy = 0, dx = 0;   // incremental (chunk, tap) counters: no division in the loop
-        float a_reg[4];
+        auto advance = [&]() {
+            ++t;
+            if (++dx == p.kw) {
+                dx = 0;
+                if (++dy == p.kh) { dy = 0; ++dz; }
+            }
+            if (t == p.T) { t = 0; dz = 0; dy = 0; dx = 0; ++chunk; }
+        };
+        float a_reg[16];
 
-        auto load_stage = [&]() {
+        auto load_stage = [&]() {                       // the stage the counters point at
             int offA = 0, offB = 0;
             bool ok = lvalid;
             if (GEOM == BX_GEOM_CYL3D || GEOM == BX_GEOM_CYL2D) {
@@ -229,10 +238,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 offA = (1 + kk) * 20 + sh;
                 offB = (1 + kk) * 20 + ll;
             }
-            const int c0 = chunk * 16 + part * 4;
+            const int c0 = chunk * 16;
             const float *src = pa + (size_t)c0 * cstride + offA;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < 16; ++kk) {
                 float v = 0.0f;
                 if (ok) {
                     if (GEOM == BX_GEOM_COSTVOL) v = src[kk * cstride] - pb[(size_t)(c0 + kk) * 140 + offB];
@@ -240,24 +249,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 }
                 a_reg[kk] = v;
             }
-            ++t;
-            if (++dx == p.kw) {
-                dx = 0;
-                if (++dy == p.kh) { dy = 0; ++dz; }
-            }
-            if (t == p.T) { t = 0; dz = 0; dy = 0; dx = 0; ++chunk; }
         };
         auto store_stage = [&](int s) {
             unsigned char *As = smem + (size_t)s * STAGE_BYTES;
-            float hi[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                hi[j] = __uint_as_float(__float_as_uint(a_reg[j]) & 0xFFFFE000u);
-                lo[j] = a_reg[j] - hi[j];
+            for (int u = 0; u < 4; ++u) {               // u = kstep*2 + kunit
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float x = a_reg[u * 4 + j];
+                    hi[j] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                    lo[j] = x - hi[j];
+                }
+                const int ks = u >> 1, ku = u & 1;      // [kstep][split][kunit][row][16B]
+                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 0) * 2 + ku) * TC_BM + row) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 1) * 2 + ku) * TC_BM + row) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
-            // [kstep][split][kunit][row][16B]
-            *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 0) * 2 + ku) * TC_BM + row) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 1) * 2 + ku) * TC_BM + row) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         };
 
         // ---- accumulator ownership of this warp: TMEM lanes 32*(warp&3).., columns CW*(warp>>2).. ----------
@@ -282,29 +289,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             }
         };
 
-        load_stage();
-        int next_drain = 0, s = 0;
-        uint32_t use = 0;                                 // how many times slot s has been filled before
-        for (int it = 0; it < n_iters; ++it) {
+        for (int k = 0; k < grp; ++k) advance();         // counters -> this group's first stage
+        if (grp < n_iters) load_stage();
+        int next_drain = 0;
+        for (int it = grp; it < n_iters; it += 4) {
             if (next_drain < nseg - 1 && it >= (next_drain + 1) * G + (G < TC_STAGES ? G : TC_STAGES)) {
                 drain(next_drain, true);                  // its MMAs are several stages behind us: short wait
                 ++next_drain;
             }
+            const int s = it % TC_STAGES;
+            const uint32_t use = (uint32_t)(it / TC_STAGES);   // how many times slot s has been filled before
             if (use > 0) mbar_wait(bar_base + 8u * (BAR_EMPTY + s), (use - 1) & 1);  // tensor core has read the slot
-            if (tid == 0) {  // weights of this stage: one bulk copy, completion counted on full[s]
+            if ((tid & 127) == 0) {  // weights of this stage: one bulk copy, completion counted on full[s]
                 mbar_arrive_expect_tx(bar_base + 8u * s, (uint32_t)B_STAGE_BYTES);
                 bulk_g2s(smem_base + (uint32_t)s * STAGE_BYTES + A_STAGE_BYTES,
                          reinterpret_cast<const unsigned char *>(p.w) + (size_t)it * B_STAGE_BYTES, (uint32_t)B_STAGE_BYTES, bar_base + 8u * s);
             }
             store_stage(s);
-            if (it + 1 < n_iters) load_stage();           // next stage's activations in flight
+            if (it + 4 < n_iters) {                       // this group's next stage: activations in flight
+                advance(); advance(); advance(); advance();
+                load_stage();
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * s);
-            if (++s == TC_STAGES) { s = 0; ++use; }
         }
-        while (next_drain < nseg) {
-            drain(next_drain, false);
+        while (next_drain < nseg) {                      // a set must still be released if a later segment reuses it
+            drain(next_drain, next_drain + 2 < nseg);
             ++next_drain;
         }
         // ---- epilogue: running sums + cross accumulator + bias (+ReLU) ------------------------------------
