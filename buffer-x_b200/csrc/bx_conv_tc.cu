@@ -53,28 +53,47 @@ constexpr int A_STAGE_BYTES = 2 * 2 * 2 * TC_BM * 16;  // [kstep][split][kunit][
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version for sm_100
-    return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// Issue helpers for the MMA warp.  The whole warp runs the issue loop in uniform control flow; `leader`
+// is 1 in exactly one lane (elect.sync) and predicates the tcgen05 instructions themselves, so the compiler
+// does not have to wrap every asm statement in a divergence loop.  The 64-bit shared-memory descriptor is
+// passed as its two 32-bit halves: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14.
+__device__ __forceinline__ uint32_t elect_leader() {
+    uint32_t pred = 0;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred;
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "mov.b64 da, {%2, %4};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%1], da, db, %5, p;\n\t"
+        "}\n" ::"r"(leader),
+        "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
-__device__ __forceinline__ void mma_commit(uint32_t bar_saddr) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr) : "memory");
+__device__ __forceinline__ void mma_commit(uint32_t leader, uint32_t bar_saddr) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t"
+        "}\n" ::"r"(leader),
+        "r"(bar_saddr)
+        : "memory");
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -343,37 +362,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         // =========================== MMA issuer (warp 16) ==============================================
         // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NT, M = 128
         constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        if ((tid & 31) == 0) {
-            int s = 0, seg = 0, in_seg = 0;
-            uint32_t use = 0;
-            const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT);
-            for (int it = 0; it < n_iters; ++it) {
-                if (in_seg == 0 && seg >= 2) {
-                    // segment `seg` reuses main set seg&1: segment seg-2 must have been drained
-                    mbar_wait(bar_base + 8u * (BAR_ACCFREE + (seg & 1)), (uint32_t)(((seg - 2) >> 1) & 1));
-                }
-                mbar_wait(bar_base + 8u * s, use & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_base = smem_base + (uint32_t)s * STAGE_BYTES;
-                const uint32_t b_base = a_base + A_STAGE_BYTES;
-                const uint32_t d_main = tmem_base + (uint32_t)((seg & 1) * NT);
+        constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+        constexpr uint32_t A_LBO = ((uint32_t)(TC_BM * 16) >> 4) << 16;         // K-unit stride of the A image
+        constexpr uint32_t B_LBO = ((uint32_t)(NT * 16) >> 4) << 16;
+        constexpr uint32_t A_IMG = (2u * TC_BM * 16) >> 4;                      // one (kstep, split) image of A, in 16-byte units
+        constexpr uint32_t B_IMG = (2u * NT * 16) >> 4;
+        const uint32_t leader = elect_leader();
+        const uint32_t a0 = (smem_base >> 4) | A_LBO;                            // stage 0, kstep 0, hi
+        const uint32_t b0 = ((smem_base + A_STAGE_BYTES) >> 4) | B_LBO;
+        const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT);
+        int s = 0, seg = 0, in_seg = 0;
+        uint32_t use = 0;
+        for (int it = 0; it < n_iters; ++it) {
+            if (in_seg == 0 && seg >= 2) {
+                // segment `seg` reuses main set seg&1: segment seg-2 must have been drained
+                mbar_wait(bar_base + 8u * (BAR_ACCFREE + (seg & 1)), (uint32_t)(((seg - 2) >> 1) & 1));
+            }
+            mbar_wait(bar_base + 8u * s, use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t so = (uint32_t)s * (uint32_t)(STAGE_BYTES >> 4);
+            const uint32_t d_main = tmem_base + (uint32_t)((seg & 1) * NT);
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const uint64_t bh = make_desc(b_base + (uint32_t)((ks * 2 + 0) * 2) * NT * 16, NT * 16, 128);
-                    const uint64_t bl = make_desc(b_base + (uint32_t)((ks * 2 + 1) * 2) * NT * 16, NT * 16, 128);
-                    const uint64_t ah = make_desc(a_base + (uint32_t)((ks * 2 + 0) * 2) * TC_BM * 16, TC_BM * 16, 128);
-                    const uint64_t al = make_desc(a_base + (uint32_t)((ks * 2 + 1) * 2) * TC_BM * 16, TC_BM * 16, 128);
-                    mma_tf32(d_cross, al, bh, IDESC, (it == 0 && ks == 0) ? 0u : 1u);
-                    mma_tf32(d_cross, ah, bl, IDESC, 1u);
-                    mma_tf32(d_main, ah, bh, IDESC, (in_seg == 0 && ks == 0) ? 0u : 1u);
-                }
-                mma_commit(bar_base + 8u * (BAR_EMPTY + s));   // slot s may be refilled once these MMAs have read it
-                if (++s == TC_STAGES) { s = 0; ++use; }
-                if (++in_seg == G || it == n_iters - 1) {
-                    mma_commit(bar_base + 8u * (BAR_SEGDONE + (seg & 1)));
-                    in_seg = 0;
-                    ++seg;
-                }
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t ah = a0 + so + (uint32_t)(ks * 2 + 0) * A_IMG, al = a0 + so + (uint32_t)(ks * 2 + 1) * A_IMG;
+                const uint32_t bh = b0 + so + (uint32_t)(ks * 2 + 0) * B_IMG, bl = b0 + so + (uint32_t)(ks * 2 + 1) * B_IMG;
+                mma_tf32(leader, d_cross, al, bh, DESC_HI, IDESC, (it == 0 && ks == 0) ? 0u : 1u);
+                mma_tf32(leader, d_cross, ah, bl, DESC_HI, IDESC, 1u);
+                mma_tf32(leader, d_main, ah, bh, DESC_HI, IDESC, (in_seg == 0 && ks == 0) ? 0u : 1u);
+            }
+            mma_commit(leader, bar_base + 8u * (BAR_EMPTY + s));   // slot s may be refilled once these MMAs have read it
+            if (++s == TC_STAGES) { s = 0; ++use; }
+            if (++in_seg == G || it == n_iters - 1) {
+                mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + (seg & 1)));
+                in_seg = 0;
+                ++seg;
             }
         }
         __syncwarp();
