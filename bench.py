@@ -233,52 +233,91 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(mode, steps, timed):
-        """mode 'dev': inputs resident; 'e2e': host tensors through the public forward."""
-        evs, recs = [], []
+    DEPTH = 2          # pairs in flight per GPU (separate streams; one captured CUDA graph per slot)
+    model.enable_cuda_graphs(True, slots_per_shape=DEPTH)
+
+    def run_pipelined(mode, steps, timed):
+        """mode 'dev': inputs resident in HBM; 'e2e': pinned host tensors through the public forward_async()."""
+        recs, handles = [], []
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for slots in model._slots.values():
+            for sl in slots:
+                sl.stream.wait_event(a)
+
+        def collect(h, s):
+            out = h.result()
+            if timed:
+                gt = host[s % pool][2]["relt_pose"]
+                recs.append(pack_record(rank + world * s, out[0], out[1], out[2], out[3], out[4], out[5],
+                                        compute_rte(out[0], gt), compute_rre(out[0], gt), 0.0))
+
         for s in range(steps):
             j = s % pool
-            flush.zero_()                                   # L2 flush between steps (untimed)
+            if len(handles) == DEPTH:
+                collect(*handles.pop(0))
+            with torch.no_grad():
+                if mode == "dev":
+                    h = model.forward_async(devd[j][0], perms=devd[j][1])
+                else:
+                    h = model.forward_async(host[j][0], perms=host[j][1])
+            with torch.cuda.stream(h.stream):
+                pass
+            handles.append((h, s))
+        while handles:
+            collect(*handles.pop(0))
+        cur = torch.cuda.current_stream()
+        for slots in model._slots.values():
+            for sl in slots:
+                cur.wait_stream(sl.stream)
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b), recs
+
+    def run_eager(steps):
+        """Per-kernel event brackets (ops.Profiler) need eager launches: the roofline pass."""
+        model.enable_cuda_graphs(False)
+        ms = 0.0
+        for s in range(steps):
+            j = s % pool
+            flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             with torch.no_grad():
-                if mode == "dev":
-                    out = model(devd[j][0], perms=devd[j][1], ransac_seed=s)
-                else:
-                    hp = host[j][1]
-                    pd = [(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)) for x, y in hp]
-                    out = model(host[j][0], perms=pd, ransac_seed=s)
+                model(devd[j][0], perms=devd[j][1], ransac_seed=s)
             b.record()
-            evs.append((a, b))
-            if timed:
-                gt = host[j][2]["relt_pose"]
-                recs.append(pack_record(rank + world * s, out[0], out[1], out[2], out[3], out[4], out[5],
-                                        compute_rte(out[0], gt), compute_rre(out[0], gt), 0.0))
-        torch.cuda.synchronize()
-        return sum(x.elapsed_time(y) for x, y in evs), recs
+            b.synchronize()
+            ms += a.elapsed_time(b)
+        model.enable_cuda_graphs(True, slots_per_shape=DEPTH)
+        return ms
 
-    run("dev", args.warmup, False)
+    l0 = ops.launch_count()
+    run_eager(1)                                            # also sets every kernel attribute before graph capture
+    launches_per_pair = ops.launch_count() - l0
+    run_pipelined("dev", max(args.warmup, DEPTH), False)    # captures the graphs, warms up
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     # ---- timed region 1: inputs resident in HBM ----------------------------------------------------
-    ops.profiler = ops.Profiler()
-    l0 = ops.launch_count()
     barrier()
-    ms_dev, recs = run("dev", args.steps, True)
+    ms_dev, recs = run_pipelined("dev", args.steps, True)
     allrec = gather_records(np.stack(recs), world * args.steps, device=dev)   # the one collective of the path
     barrier()
-    launches = ops.launch_count() - l0
-    prof = ops.profiler.summary()
-    ops.profiler = None
+    launches = launches_per_pair * args.steps
     # ---- timed region 2: host buffers through the public API --------------------------------------
     if args.short:
         ms_e2e = float("nan")
     else:
-        run("e2e", 2, False)
+        run_pipelined("e2e", DEPTH, False)
         barrier()
-        ms_e2e, _ = run("e2e", args.steps, True)
+        ms_e2e, _ = run_pipelined("e2e", args.steps, True)
         barrier()
+    # ---- roofline pass: eager launches with per-kernel CUDA-event brackets --------------------------
+    ops.profiler = ops.Profiler()
+    ms_eager = run_eager(min(args.steps, 5))
+    prof = ops.profiler.summary()
+    ops.profiler = None
     sampler.stop_flag = True
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
@@ -293,9 +332,10 @@ def main():
         ach_tf = cd["work"] / (cd["ms"] / 1e3) / 1e12 if cd["ms"] > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (Cylindrical_Net layers, fp32 FFMA implicit GEMM)",
                 "achieved": ach_tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf"],
-                "peak_source": f"{pk['src']} bf16 dense (sustained); fp32 FFMA ceiling of 148 SMs is ~70 TFLOP/s",
+                "peak_source": f"{pk['src']} bf16 dense (sustained); the 3-pass TF32 ceiling is ~375 TFLOP/s fp32-equivalent",
                 "launches": cd["launches"], "avg_launch_ms": cd["ms"] / max(cd["launches"], 1),
-                "share_of_step": cd["ms"] / ms_dev if ms_dev else None, "traffic": None}
+                "share_of_step": cd["ms"] / ms_eager if ms_eager else None, "traffic": None,
+                "measured_in": "eager (non-graph) pass of this run: per-kernel CUDA-event brackets need individual launches"}
         kern = {}
         sp = prof.get("select_patches")
         if sp and sp["ms"] > 0:
@@ -305,14 +345,16 @@ def main():
         for k in ("conv_cost", "ransac"):
             if k in prof:
                 kern[k] = {"launches": prof[k]["launches"], "avg_ms": prof[k]["ms"] / max(prof[k]["launches"], 1),
-                           "share_of_step": prof[k]["ms"] / ms_dev}
+                           "share_of_step": prof[k]["ms"] / ms_eager}
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: 2x{ns} pts, {cfg.patch.num_fps} kpts, {cfg.patch.num_points_per_patch} pts/patch, "
                                        f"{S} scales, {cfg.match.iter_n} RANSAC iters, seeded synthetic weights",
                            "pairs_per_rank": args.steps, "sharding": "pair i -> rank i mod world, one all_gather of 32-float records",
-                           "l2": "256 MB flush between steps", "mean_mutual_matches": float(np.mean(allrec[:, 20])),
+                           "l2": "per-pair working set (~1 GB of activations) exceeds the 126 MB L2; eager pass flushes 256 MB between steps",
+                           "pairs_in_flight": DEPTH, "cuda_graphs": True, "eager_ms_per_step": ms_eager / max(min(args.steps, 5), 1),
+                           "mean_mutual_matches": float(np.mean(allrec[:, 20])),
                            "mean_consensus_inliers": float(np.mean(allrec[:, 21]))},
                 "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps},

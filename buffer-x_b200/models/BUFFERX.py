@@ -10,6 +10,12 @@ scales_used)``.  Differences that do not change results:
   * the radius histogram is built once and serves every scale's bisection, on the device;
   * data-dependent sizes stay in device counters, so the whole pair is enqueued without a host round
     trip; the host reads one small result block at the end (early-exit mode adds one read after scale 0).
+
+Throughput API on top of the reference surface (CUDA streams + graphs instead of a tracing compiler):
+  * ``enable_cuda_graphs(True)``: the enqueue of a pair is captured once per (Ns, Nt, aligned) shape and
+    replayed -- one graph launch instead of ~150 kernel launches;
+  * ``forward_async(data_source) -> handle`` / ``handle.result()``: several pairs in flight on separate
+    streams (FPS is a latency-bound 16-SM kernel; a second pair's convolutions fill the other SMs).
 """
 import numpy as np
 import torch
@@ -73,6 +79,92 @@ class _Timer:
             self.total += self.a.elapsed_time(self.b) / 1000.0
 
 
+class _PairSlot:
+    """Static buffers + (optionally) a captured CUDA graph for one (Ns, Nt, aligned) shape on its own stream."""
+
+    def __init__(self, model, Ns, Nt, aligned, use_graph):
+        cfg = model.config
+        self.model, self.Ns, self.Nt, self.aligned = model, Ns, Nt, aligned
+        dev = next(model.parameters()).device
+        self.dev = dev
+        S = cfg.patch.num_scales
+        self.stream = torch.cuda.Stream(device=dev)
+        self.src = torch.empty((Ns, 3), dtype=torch.float32, device=dev)
+        self.tgt = torch.empty((Nt, 3), dtype=torch.float32, device=dev)
+        self.perm_s = torch.empty((S, Ns), dtype=torch.int32, device=dev)
+        self.perm_t = torch.empty((S, Nt), dtype=torch.int32, device=dev)
+        self.h_perm_s = torch.empty((S, Ns), dtype=torch.int32).pin_memory()
+        self.h_perm_t = torch.empty((S, Nt), dtype=torch.int32).pin_memory()
+        self.h_src = torch.empty((Ns, 3), dtype=torch.float32).pin_memory()
+        self.h_tgt = torch.empty((Nt, 3), dtype=torch.float32).pin_memory()
+        self.h_tail = None
+        self.done = torch.cuda.Event()
+        self.graph = None
+        self.tail = None
+        self.busy = False
+        if use_graph:
+            with torch.cuda.stream(self.stream):
+                self.src.zero_(); self.tgt.zero_()
+                base = torch.arange(max(Ns, Nt), dtype=torch.int32, device=dev)
+                self.perm_s.copy_(base[:Ns].expand(S, Ns)); self.perm_t.copy_(base[:Nt].expand(S, Nt))
+                self.src[:, 0] = torch.linspace(1, 2, Ns, device=dev)      # any valid cloud: warm-up sets kernel attributes
+                self.tgt[:, 0] = torch.linspace(1, 2, Nt, device=dev)
+                self._enqueue()                                            # eager warm-up on this stream
+            self.stream.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.tail = self._enqueue()
+        # pinned landing buffer for the result block
+        n_tail = 18 + S + 1 + 1 + 16
+        self.h_tail = torch.empty(n_tail, dtype=torch.float64).pin_memory()
+
+    def _enqueue(self):
+        perms = [(self.perm_s[i], self.perm_t[i]) for i in range(self.perm_s.shape[0])]
+        return self.model._enqueue(self.src, self.tgt, self.aligned, perms, None, False)[0]
+
+    def launch(self, data_source, perms):
+        """H2D of the inputs (pinned staging when they arrive as host arrays), the pair, D2H of the result."""
+        with torch.cuda.stream(self.stream):
+            for dst, hbuf, x in ((self.src, self.h_src, data_source["src_fds_pcd"]), (self.tgt, self.h_tgt, data_source["tgt_fds_pcd"])):
+                x = torch.as_tensor(x)
+                if x.is_cuda:
+                    dst.copy_(x.reshape(-1, 3), non_blocking=True)
+                else:
+                    if x.is_pinned():
+                        dst.copy_(x.reshape(-1, 3), non_blocking=True)
+                    else:
+                        hbuf.copy_(x.reshape(-1, 3))
+                        dst.copy_(hbuf, non_blocking=True)
+            S = self.perm_s.shape[0]
+            for i in range(S):
+                if perms is None:   # the reference's host draws, in its order (src then tgt, per scale)
+                    self.h_perm_s[i].copy_(torch.from_numpy(np.random.choice(self.Ns, self.Ns, replace=False).astype(np.int32)))
+                    self.h_perm_t[i].copy_(torch.from_numpy(np.random.choice(self.Nt, self.Nt, replace=False).astype(np.int32)))
+                else:
+                    ps, pt = perms[i]
+                    if isinstance(ps, torch.Tensor) and ps.is_cuda:
+                        self.perm_s[i].copy_(ps, non_blocking=True); self.perm_t[i].copy_(pt, non_blocking=True)
+                        continue
+                    self.h_perm_s[i].copy_(torch.as_tensor(ps, dtype=torch.int32)); self.h_perm_t[i].copy_(torch.as_tensor(pt, dtype=torch.int32))
+            if perms is None or not (isinstance(perms[0][0], torch.Tensor) and perms[0][0].is_cuda):
+                self.perm_s.copy_(self.h_perm_s, non_blocking=True)
+                self.perm_t.copy_(self.h_perm_t, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+                tail = self.tail
+            else:
+                tail = self._enqueue()
+            self.h_tail.copy_(tail, non_blocking=True)
+            self.done.record(self.stream)
+        self.busy = True
+        return self
+
+    def result(self):
+        self.done.synchronize()
+        self.busy = False
+        return self.model._decode(self.h_tail.clone(), [0.0, 0.0, 0.0])
+
+
 class BufferX(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -83,7 +175,10 @@ class BufferX(nn.Module):
         self.equi_match = EquiMatch(config)
         if config.stage == "test":
             self.pose_estimator = PoseEstimator(config)
-        self._host = None
+        self._use_graphs = False
+        self._slots = {}
+        self._slots_per_shape = 2
+        self._rr = {}
 
     def get_parameter(self):
         return list(self.parameters())
@@ -106,29 +201,54 @@ class BufferX(nn.Module):
         return T.view(1, 4, 4)
 
     # ------------------------------------------------------------------------------------------------
-    def forward(self, data_source, perms=None, ransac_seed=None, debug=False):
+    def enable_cuda_graphs(self, flag=True, slots_per_shape=2):
+        """Capture the per-pair enqueue once per (Ns, Nt, aligned) shape and replay it (no effect on results)."""
+        self._use_graphs = bool(flag)
+        self._slots_per_shape = int(slots_per_shape)
+        self._slots.clear()
+        self._rr.clear()
+        return self
+
+    def _graphable(self):
         cfg = self.config
-        if cfg.stage != "test":
-            raise NotImplementedError("bufferx_b200 implements the inference hot path (cfg.stage == 'test')")
-        dev = next(self.parameters()).device
-        if dev.type != "cuda":
-            raise ops.BufferXError("BufferX.forward needs the model on a CUDA device: there is no CPU path")
+        return not cfg.match.get("enable_early_exit", True) and not cfg.test.get("enable_timing", False)
 
-        def _cloud(x):
-            x = torch.as_tensor(x)
-            return x.to(dev, dtype=torch.float32, non_blocking=True).reshape(-1, 3).contiguous()
+    def _slot(self, Ns, Nt, aligned):
+        key = (Ns, Nt, bool(aligned))
+        lst = self._slots.setdefault(key, [])
+        i = self._rr.get(key, 0)
+        if len(lst) < self._slots_per_shape:
+            lst.append(_PairSlot(self, Ns, Nt, aligned, self._use_graphs))
+            slot = lst[-1]
+        else:
+            slot = lst[i % len(lst)]
+            if slot.busy:
+                raise ops.BufferXError("forward_async: collect the oldest handle's result() before launching more pairs")
+        self._rr[key] = i + 1
+        return slot
 
-        src, tgt = _cloud(data_source["src_fds_pcd"]), _cloud(data_source["tgt_fds_pcd"])
-        aligned = bool(data_source["is_aligned_to_global_z"])
+    def forward_async(self, data_source, perms=None):
+        """Enqueue one pair on a slot stream; returns a handle whose ``result()`` is the forward tuple."""
+        if not self._graphable():
+            raise ops.BufferXError("forward_async needs early exit and timing disabled (they require host round trips)")
+        Ns = int(np.prod(data_source["src_fds_pcd"].shape[:-1]))
+        Nt = int(np.prod(data_source["tgt_fds_pcd"].shape[:-1]))
+        return self._slot(Ns, Nt, bool(data_source["is_aligned_to_global_z"])).launch(data_source, perms)
+
+    # ------------------------------------------------------------------------------------------------
+    def _enqueue(self, src, tgt, aligned, perms, ransac_seed, debug, timers=None):
+        """Everything of one pair on the current stream, no host synchronisation unless early exit is on.
+        Returns (tail block on the device, debug dict)."""
+        cfg = self.config
+        dev = src.device
         Ns, Nt = src.shape[0], tgt.shape[0]
         Kr, K = cfg.patch.num_points_radius_estimate, cfg.patch.num_fps
         S = cfg.patch.num_scales
         thresholds = cfg.patch.search_radius_thresholds
         assert S == len(thresholds), f"num_scales {S} != num_thresholds {len(thresholds)}"
         enable_early_exit = cfg.match.get("enable_early_exit", True)
-        enable_timing = cfg.test.get("enable_timing", False)
-        desc_t, pose_t, opt_t = _Timer(enable_timing), _Timer(enable_timing), _Timer(enable_timing)
         azi_n = cfg.patch.azi_n
+        desc_t, pose_t, opt_t = timers if timers is not None else (_Timer(False), _Timer(False), _Timer(False))
 
         desc_t.tic()
         # ---- key-points: one FPS per cloud, both clouds in one launch --------------------------------
@@ -151,10 +271,9 @@ class BufferX(nn.Module):
         ss_acc = torch.empty((maxMc, 3), dtype=torch.float32, device=dev)
         tt_acc = torch.empty((maxMc, 3), dtype=torch.float32, device=dev)
         offs = torch.zeros(S + 1, dtype=torch.int32, device=dev)
-        ind_dbg = [] if debug else None
         dbg = dict(scales=[]) if debug else None
 
-        init_pose, num_inliers, num_inlier_ind, scales_used = None, 0, 0, 0
+        scales_used = 0
         should_exit = False
         res_block = None
         inl = dI = None
@@ -185,35 +304,67 @@ class BufferX(nn.Module):
             if enable_early_exit and i == 0:
                 opt_t.tic()
                 res_block = self.pose_estimator.enqueue(ss_acc, tt_acc, inl, dI, (i + 1) * K, ransac_seed)
-                init_pose, num_inliers, _, _ = ops.decode_ransac_result(res_block.cpu())   # one host read
+                _, num_inliers, _, _ = ops.decode_ransac_result(res_block.cpu())   # one host read
                 opt_t.toc()
                 should_exit = self.pose_estimator.compute_confidence_score(num_inliers)
                 if should_exit:
                     break
 
         opt_t.tic()
-        ran_final = (not enable_early_exit) or (enable_early_exit and not should_exit)
-        if ran_final:
+        if (not enable_early_exit) or (enable_early_exit and not should_exit):
             res_block = self.pose_estimator.enqueue(ss_acc, tt_acc, inl, dI, scales_used * K, ransac_seed)
         d_Mc = offs[scales_used:scales_used + 1]
-        refined = None
         if cfg.test.pose_refine is True:
             refined, _ = ops.refine(ss_acc, tt_acc, d_Mc, scales_used * K, res_block[:16], cfg.match.dist_th)
-        # ---- one small device->host read for everything the caller needs -----------------------------
-        tail = torch.cat([res_block, offs.double(), dI.double(),
-                          refined.double() if refined is not None else torch.zeros(16, dtype=torch.float64, device=dev)]).cpu()
-        opt_t.toc()
+            refined = refined.double()
+        else:
+            refined = torch.zeros(16, dtype=torch.float64, device=dev)
+        # ---- one small block holds everything the caller needs ---------------------------------------
+        su = torch.full((1,), float(scales_used), dtype=torch.float64, device=dev)
+        tail = torch.cat([res_block, offs.double(), dI.double(), su, refined])
+        if debug:
+            dbg.update(fps_idx=fidx, kpts=fk, des_r=r_dev, des_m=m_dev, ss=ss_acc, tt=tt_acc, R=R_acc, t=t_acc)
+        return tail, dbg
+
+    def _decode(self, tail, times):
+        cfg = self.config
+        S = cfg.patch.num_scales
         init_pose, num_inliers, best_itr, iters = ops.decode_ransac_result(tail[:18])
         offs_h = tail[18:18 + S + 1].numpy().astype(np.int64)
         num_inlier_ind = int(tail[18 + S + 1].item())
+        scales_used = int(tail[18 + S + 2].item())
         num_mutual_inliers = int(offs_h[scales_used])
         if cfg.test.pose_refine is True:
-            pose = tail[18 + S + 2:].numpy().astype(np.float32).reshape(4, 4)
+            pose = tail[18 + S + 3:].numpy().astype(np.float32).reshape(4, 4)
         else:
             pose = init_pose
-        times = [desc_t.total, pose_t.total, opt_t.total]
-        if debug:
-            dbg.update(fps_idx=fidx, kpts=fk, des_r=r_dev, des_m=m_dev, offs=offs_h, init_pose=init_pose, best_itr=best_itr,
-                       iters=iters, ss=ss_acc, tt=tt_acc, R=R_acc, t=t_acc)
-            self.last_debug = dbg
+        self._last_ransac = dict(init_pose=init_pose, best_itr=best_itr, iters=iters, offs=offs_h)
         return pose, times, num_inliers, num_mutual_inliers, num_inlier_ind, scales_used
+
+    def forward(self, data_source, perms=None, ransac_seed=None, debug=False):
+        cfg = self.config
+        if cfg.stage != "test":
+            raise NotImplementedError("bufferx_b200 implements the inference hot path (cfg.stage == 'test')")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise ops.BufferXError("BufferX.forward needs the model on a CUDA device: there is no CPU path")
+        if self._use_graphs and not debug and ransac_seed is None and self._graphable():
+            return self.forward_async(data_source, perms).result()
+
+        def _cloud(x):
+            x = torch.as_tensor(x)
+            return x.to(dev, dtype=torch.float32, non_blocking=True).reshape(-1, 3).contiguous()
+
+        src, tgt = _cloud(data_source["src_fds_pcd"]), _cloud(data_source["tgt_fds_pcd"])
+        aligned = bool(data_source["is_aligned_to_global_z"])
+        enable_timing = cfg.test.get("enable_timing", False)
+        timers = (_Timer(enable_timing), _Timer(enable_timing), _Timer(enable_timing))
+        tail, dbg = self._enqueue(src, tgt, aligned, perms, ransac_seed, debug, timers)
+        timers[2].tic()
+        tail_h = tail.cpu()                 # the one device->host read of the pair
+        timers[2].toc()
+        out = self._decode(tail_h, [timers[0].total, timers[1].total, timers[2].total])
+        if debug:
+            dbg.update(self._last_ransac)
+            self.last_debug = dbg
+        return out

@@ -19,7 +19,7 @@ class PoseEstimator:
         self.cfg = cfg
         self.pose_estimator = cfg.match.pose_estimator
         self.seed = int(cfg.match.get("ransac_seed", 0))
-        self._ws = None
+        self._ws = {}           # one RANSAC workspace per CUDA stream (pairs may be in flight on several streams)
         self._warned = False
 
     # ---- sync-free device path used by BufferX.forward ------------------------------------------------
@@ -32,10 +32,11 @@ class PoseEstimator:
         elif self.pose_estimator not in ("ransac", "kiss_matcher"):
             raise ValueError(f"Unknown pose estimator: {self.pose_estimator}")
         m = self.cfg.match
-        if self._ws is None or self._ws.device != ss.device:
-            self._ws = ops.ransac_workspace(m.iter_n, ss.device)
+        key = (str(ss.device), torch.cuda.current_stream().cuda_stream)
+        if key not in self._ws:
+            self._ws[key] = ops.ransac_workspace(m.iter_n, ss.device)
         return ops.ransac(ss, tt, inlier_ind, d_I, maxI, m.dist_th, m.similar_th, m.confidence, m.iter_n,
-                          self.seed if seed is None else seed, workspace=self._ws)
+                          self.seed if seed is None else seed, workspace=self._ws[key])
 
     # ---- reference-compatible entry point -------------------------------------------------------------
     def estimate_pose(self, src_kpts, tgt_kpts, inlier_ind, seed=None):

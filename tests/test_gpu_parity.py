@@ -482,3 +482,30 @@ def test_cost_volume_first_layer_tc_vs_ffma(dev, oracle, c1):
     assert (b[M - 3:] == 0).all()                                     # rows beyond the device-side count are untouched
     assert relerr(b.cpu().numpy(), a.cpu().numpy()) < 2e-5
     model.cpu()
+
+
+# ------------------------------------------------------------------------------ graphs / async pairs
+def test_cuda_graph_replay_and_async_pairs_match_eager(dev, oracle, c1):
+    """Captured-graph replays on two slot streams (pairs in flight) return exactly the eager results."""
+    import bufferx_b200 as bx
+    from bufferx_b200.synth import make_pair
+    model = c1["model"].to(dev)
+    cfg = c1["cfg"]
+    pairs = [make_pair("C1", s) for s in range(4)]
+    perms = [oracle.draw_perms(cfg, 5000, 5000, 10 + s) for s in range(4)]
+    model.enable_cuda_graphs(False)
+    with torch.no_grad():
+        eager = [model(p, perms=q) for p, q in zip(pairs, perms)]
+        model.enable_cuda_graphs(True, slots_per_shape=2)
+        outs, handles = [], []
+        for p, q in zip(pairs, perms):
+            if len(handles) == 2:
+                outs.append(handles.pop(0).result())
+            handles.append(model.forward_async(p, perms=q))
+        outs += [h.result() for h in handles]
+        again = model(pairs[0], perms=perms[0])              # forward() itself replays the graph when enabled
+    model.enable_cuda_graphs(False)
+    for e, o in zip(eager, outs):
+        assert np.array_equal(np.asarray(e[0]), np.asarray(o[0])) and e[2:] == o[2:]
+    assert np.array_equal(np.asarray(eager[0][0]), np.asarray(again[0])) and eager[0][2:] == again[2:]
+    model.cpu()
