@@ -115,7 +115,7 @@ class _PairSlot:
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self.tail = self._enqueue()
         # pinned landing buffer for the result block
-        n_tail = 18 + S + 1 + 1 + 16
+        n_tail = 18 + (S + 1) + 1 + 1 + 16   # RANSAC block, scale offsets, consensus count, scales used, refined pose
         self.h_tail = torch.empty(n_tail, dtype=torch.float64).pin_memory()
 
     def _enqueue(self):
