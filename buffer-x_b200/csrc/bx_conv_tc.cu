@@ -48,8 +48,8 @@ struct ConvTcParams {
 constexpr int TC_LOADERS = 512;
 constexpr int TC_THREADS = TC_LOADERS + 32;
 constexpr int TC_BM = 128;
-constexpr int TC_STAGES = 6;
-constexpr int A_STAGE_BYTES = 2 * 2 * 2 * TC_BM * 16;  // [kstep][split][kunit][row][16B] = 16 KB
+constexpr int TC_STAGES = 4;
+constexpr int A_STAGE_COLS = 32;  // TMEM columns of one A stage: [kstep(2)][split(hi,lo)][8 tf32 values]
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,6 +83,29 @@ __device__ __forceinline__ void mma_tf32(uint32_t leader, uint32_t tmem_d, uint3
         "}\n" ::"r"(leader),
         "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// A operand from tensor memory (128 lanes x 8 tf32 columns), B operand from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t leader, uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], db, %5, p;\n\t"
+        "}\n" ::"r"(leader),
+        "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
 }
 
 __device__ __forceinline__ void mma_commit(uint32_t leader, uint32_t bar_saddr) {
@@ -159,8 +182,10 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CW]) {
 template <int GEOM, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcParams p) {
     constexpr int B_STAGE_BYTES = 2 * 2 * 2 * NT * 16;  // [kstep][split][kunit][n][16B]
-    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    constexpr int TMEM_COLS = 4 * NT;   // main[0], main[1], cross (+ NT spare: the allocation is a power of two)
+    constexpr int STAGE_BYTES = B_STAGE_BYTES;      // shared memory holds only the weights; A lives in tensor memory
+    constexpr int A_RING = 3 * NT;                  // TMEM columns: main[0], main[1], cross, then the A ring
+    constexpr int TMEM_NEED = A_RING + TC_STAGES * A_STAGE_COLS;
+    constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
     constexpr int CW = NT / 4;          // accumulator columns owned by one loader warp
     // barriers: full[ST] (16 loader-warp arrivals + 1 expect_tx arrival), empty[ST], segdone[2], accfree[2]
     constexpr int BAR_EMPTY = TC_STAGES, BAR_SEGDONE = 2 * TC_STAGES, BAR_ACCFREE = 2 * TC_STAGES + 2;
@@ -269,21 +294,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 a_reg[kk] = v;
             }
         };
-        auto store_stage = [&](int s) {
-            unsigned char *As = smem + (size_t)s * STAGE_BYTES;
+        const uint32_t a_lane = (uint32_t)((warp & 3) * 32) << 16;   // this warp's TMEM lanes = its 32 GEMM rows
+        auto store_stage = [&](int s) {                  // registers -> tensor memory: [kstep][hi,lo][8]
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {               // u = kstep*2 + kunit
-                float hi[4], lo[4];
+            for (int ks = 0; ks < 2; ++ks) {
+                float hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float x = a_reg[u * 4 + j];
+                for (int j = 0; j < 8; ++j) {
+                    const float x = a_reg[ks * 8 + j];
                     hi[j] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
                     lo[j] = x - hi[j];
                 }
-                const int ks = u >> 1, ku = u & 1;      // [kstep][split][kunit][row][16B]
-                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 0) * 2 + ku) * TC_BM + row) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4 *>(As + ((size_t)((ks * 2 + 1) * 2 + ku) * TC_BM + row) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                const uint32_t col = (uint32_t)(A_RING + s * A_STAGE_COLS + ks * 16);
+                tmem_st8(tmem_base + a_lane + col, hi);
+                tmem_st8(tmem_base + a_lane + col + 8, lo);
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         };
 
         // ---- accumulator ownership of this warp: TMEM lanes 32*(warp&3).., columns CW*(warp>>2).. ----------
@@ -321,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             if (use > 0) mbar_wait(bar_base + 8u * (BAR_EMPTY + s), (use - 1) & 1);  // tensor core has read the slot
             if ((tid & 127) == 0) {  // weights of this stage: one bulk copy, completion counted on full[s]
                 mbar_arrive_expect_tx(bar_base + 8u * s, (uint32_t)B_STAGE_BYTES);
-                bulk_g2s(smem_base + (uint32_t)s * STAGE_BYTES + A_STAGE_BYTES,
+                bulk_g2s(smem_base + (uint32_t)s * STAGE_BYTES,
                          reinterpret_cast<const unsigned char *>(p.w) + (size_t)it * B_STAGE_BYTES, (uint32_t)B_STAGE_BYTES, bar_base + 8u * s);
             }
             store_stage(s);
@@ -329,7 +355,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 advance(); advance(); advance(); advance();
                 load_stage();
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // tcgen05.st ordered before the arrive
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * s);
         }
@@ -363,13 +389,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NT, M = 128
         constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
-        constexpr uint32_t A_LBO = ((uint32_t)(TC_BM * 16) >> 4) << 16;         // K-unit stride of the A image
         constexpr uint32_t B_LBO = ((uint32_t)(NT * 16) >> 4) << 16;
-        constexpr uint32_t A_IMG = (2u * TC_BM * 16) >> 4;                      // one (kstep, split) image of A, in 16-byte units
-        constexpr uint32_t B_IMG = (2u * NT * 16) >> 4;
+        constexpr uint32_t B_IMG = (2u * NT * 16) >> 4;                         // one (kstep, split) image of B, in 16-byte units
         const uint32_t leader = elect_leader();
-        const uint32_t a0 = (smem_base >> 4) | A_LBO;                            // stage 0, kstep 0, hi
-        const uint32_t b0 = ((smem_base + A_STAGE_BYTES) >> 4) | B_LBO;
+        const uint32_t b0 = (smem_base >> 4) | B_LBO;                            // stage 0, kstep 0, hi
         const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT);
         int s = 0, seg = 0, in_seg = 0;
         uint32_t use = 0;
@@ -384,11 +407,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             const uint32_t d_main = tmem_base + (uint32_t)((seg & 1) * NT);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t ah = a0 + so + (uint32_t)(ks * 2 + 0) * A_IMG, al = a0 + so + (uint32_t)(ks * 2 + 1) * A_IMG;
+                const uint32_t ah = tmem_base + (uint32_t)(A_RING + s * A_STAGE_COLS + ks * 16), al = ah + 8;
                 const uint32_t bh = b0 + so + (uint32_t)(ks * 2 + 0) * B_IMG, bl = b0 + so + (uint32_t)(ks * 2 + 1) * B_IMG;
-                mma_tf32(leader, d_cross, al, bh, DESC_HI, IDESC, (it == 0 && ks == 0) ? 0u : 1u);
-                mma_tf32(leader, d_cross, ah, bl, DESC_HI, IDESC, 1u);
-                mma_tf32(leader, d_main, ah, bh, DESC_HI, IDESC, (in_seg == 0 && ks == 0) ? 0u : 1u);
+                mma_tf32_ts(leader, d_cross, al, bh, DESC_HI, IDESC, (it == 0 && ks == 0) ? 0u : 1u);
+                mma_tf32_ts(leader, d_cross, ah, bl, DESC_HI, IDESC, 1u);
+                mma_tf32_ts(leader, d_main, ah, bh, DESC_HI, IDESC, (in_seg == 0 && ks == 0) ? 0u : 1u);
             }
             mma_commit(leader, bar_base + 8u * (BAR_EMPTY + s));   // slot s may be refilled once these MMAs have read it
             if (++s == TC_STAGES) { s = 0; ++use; }
@@ -412,7 +435,7 @@ int launch_tc(const ConvTcParams &p, int max_n, cudaStream_t st) {
     const long long maxM = (long long)max_n * p.S_out;
     const unsigned gx = (unsigned)((maxM + TC_BM - 1) / TC_BM);
     if (gx == 0) return BX_OK;
-    constexpr int smem = TC_STAGES * (A_STAGE_BYTES + 2 * 2 * 2 * NT * 16);
+    constexpr int smem = TC_STAGES * (2 * 2 * 2 * NT * 16);
     static bool attr_done = false;
     if (!attr_done) {
         BX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<GEOM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
