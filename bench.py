@@ -78,7 +78,11 @@ def cpu_sample(workload, cfg, sd, data, perms, frac=0.08):
     key-points, scaled back linearly.  Returns (seconds per pair estimate, cores, description, stage dict)."""
     from oracle import oracle as O
     O.build()
-    torch.set_num_threads(os.cpu_count() or 1)
+    # all the host threads the port can USE: beyond ~16 threads the small per-patch convolutions of the
+    # torch-CPU stacks and the OpenMP loops over a few hundred key-points only lose time to oversubscription
+    nthr = max(1, min(os.cpu_count() or 1, 16))
+    torch.set_num_threads(nthr)
+    O.lib().bxo_set_num_threads(nthr)
     src, tgt = data["src_fds_pcd"], data["tgt_fds_pcd"]
     Kr, K, S = cfg.patch.num_points_radius_estimate, cfg.patch.num_fps, cfg.patch.num_scales
     st = {}

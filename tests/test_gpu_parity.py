@@ -509,3 +509,32 @@ def test_cuda_graph_replay_and_async_pairs_match_eager(dev, oracle, c1):
         assert np.array_equal(np.asarray(e[0]), np.asarray(o[0])) and e[2:] == o[2:]
     assert np.array_equal(np.asarray(eager[0][0]), np.asarray(again[0])) and eager[0][2:] == again[2:]
     model.cpu()
+
+
+# ------------------------------------------------------------------------------ other BASELINE configs
+def test_c3_kitti_sized_pair(dev, oracle):
+    """BASELINE config C3 (2x120000 points, 2048 key-points, aligned-to-z, confidence 1.0, no refinement);
+    RANSAC iterations reduced for the CPU oracle's sake -- the GPU side runs the same count."""
+    import bufferx_b200 as bx
+    from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
+    cfg = workload_cfg("C3")
+    cfg.match.iter_n = 5000
+    model = init_synthetic_weights(bx.BufferX(cfg))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    data = make_pair("C3", 1)
+    perms = oracle.draw_perms(cfg, 120000, 120000, 1)
+    _compare_pair(model.to(dev), sd, cfg, data, perms, oracle, "C3")
+
+
+def test_c5_heterogeneous_pair(dev, oracle):
+    """BASELINE config C5 (60000-point vs 30000-point clouds of one scene, outdoor flags)."""
+    import bufferx_b200 as bx
+    from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
+    cfg = workload_cfg("C5")
+    cfg.match.iter_n = 5000
+    cfg.patch.num_fps = 600
+    model = init_synthetic_weights(bx.BufferX(cfg))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    data = make_pair("C5", 0)
+    perms = oracle.draw_perms(cfg, 60000, 30000, 2)
+    _compare_pair(model.to(dev), sd, cfg, data, perms, oracle, "C5")
