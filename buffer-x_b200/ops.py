@@ -21,7 +21,8 @@ SYMBOLS = [
     "bx_last_error", "bx_version", "bx_device_sm_count", "bx_launch_count", "bx_fps", "bx_radius_estimate", "bx_permute_cloud",
     "bx_select_patches", "bx_ball_query", "bx_lrf", "bx_spt_pnt", "bx_conv_layer", "bx_conv_tc_ntile", "bx_conv_layer_tc",
     "bx_pool_desc", "bx_mutual_nn",
-    "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine",
+    "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
+    "bx_radius_neighbors", "bx_grid_subsample",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL = 0, 1, 2, 3
@@ -68,6 +69,8 @@ def load_library():
     lib.bx_consensus.argtypes = [P, P, P, P, P, c_int, c_int, c_float, P, P, P, P, P]
     lib.bx_ransac.argtypes = [P, P, P, P, c_int, c_double, c_double, c_double, c_int, c_uint64, P, P, P]
     lib.bx_refine.argtypes = [P, P, P, c_int, P, c_float, P, P, P]
+    lib.bx_radius_neighbors.argtypes = [P, c_int, P, c_int, P, c_int, P, c_int, c_float, P, c_int, P, P]
+    lib.bx_grid_subsample.argtypes = [P, c_int, c_float, P, P, c_int, P, P, P, P, P, P]
     _lib = lib
     return lib
 
@@ -369,3 +372,44 @@ def refine(ss, tt, d_n, maxn, T_in, dist_th, T_out=None, d_rounds=None):
     _check(load_library().bx_refine(_dp(ss, F32), _dp(tt, F32), _dp(d_n, I32), int(maxn), _dp(T_in, torch.float64, "T_in"), float(dist_th), _dp(T_out),
                                     _dp(d_rounds), _stream()), "bx_refine")
     return T_out, d_rounds
+
+
+def radius_neighbors(queries, supports, q_batches, s_batches, radius: float):
+    """All supports within `radius` of every query, distance-sorted, padded with len(supports) -- the reference's
+    ``radius_neighbors.batch_query`` (cpp_wrappers/cpp_neighbors).  Two launches: count, then gather+sort."""
+    lib = load_library()
+    qb = np.ascontiguousarray(q_batches, dtype=np.int32)
+    sb = np.ascontiguousarray(s_batches, dtype=np.int32)
+    nq, ns = queries.shape[0], supports.shape[0]
+    dmax = torch.zeros(1, dtype=I32, device=queries.device)
+    args = (_dp(queries, F32, "queries"), nq, _dp(supports, F32, "supports"), ns, qb.ctypes.data_as(c_void_p), len(qb),
+            sb.ctypes.data_as(c_void_p), len(sb), float(radius))
+    _check(lib.bx_radius_neighbors(*args, None, 0, _dp(dmax), _stream()), "bx_radius_neighbors")
+    mc = int(dmax.item())
+    if mc > 4096:
+        raise BufferXError(f"bx_radius_neighbors: {mc} neighbours in one ball exceed the 4096-entry in-CTA sort")
+    out = torch.empty((nq, max(mc, 1)), dtype=I32, device=queries.device)
+    if mc > 0:
+        _check(lib.bx_radius_neighbors(*args, _dp(out), mc, _dp(dmax), _stream()), "bx_radius_neighbors")
+    return out[:, :mc]
+
+
+def grid_subsample(points, dl: float):
+    """Voxel barycentres (reference ``grid_subsampling.subsample``): returns (keys u64-as-int64 [m], xyz [m,3], counts [m])."""
+    lib = load_library()
+    n = points.shape[0]
+    dev = points.device
+    cap = 1
+    while cap < 2 * n:
+        cap <<= 1
+    tkeys = torch.empty(cap, dtype=torch.int64, device=dev)
+    tacc = torch.empty((cap, 4), dtype=F32, device=dev)
+    mm = torch.empty(6, dtype=F32, device=dev)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    xyz = torch.empty((n, 3), dtype=F32, device=dev)
+    cnt = torch.empty(n, dtype=I32, device=dev)
+    dm = torch.zeros(1, dtype=I32, device=dev)
+    _check(lib.bx_grid_subsample(_dp(points, F32, "points"), n, float(dl), _dp(tkeys), _dp(tacc), cap, _dp(mm), _dp(keys), _dp(xyz), _dp(cnt),
+                                 _dp(dm), _stream()), "bx_grid_subsample")
+    m = int(dm.item())
+    return keys[:m], xyz[:m], cnt[:m]

@@ -116,6 +116,9 @@ int bx_conv_layer(int geom, const float *in, const float *w, const float *bias, 
  * input channels) the block [kstep(2)][split(2: hi,lo)][kunit(2)][n(NT)][4 floats], NT = bx_conv_tc_ntile(Cout),
  * rows n >= Cout zero, hi = round-to-nearest tf32 of the folded weight, lo = w - hi.  Cin % 16 == 0, Cout <= 128. */
 int bx_conv_tc_ntile(int Cout);
+/* Tuning knob: stages (16 channels x 1 tap) accumulated per TMEM segment before the fp32 drain (default 6);
+ * returns the previous value.  Used by tools/tc_precision.py. */
+int bx_conv_tc_set_segment_stages(int stages);
 int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const float *bias, float *out, int n,
                      const int32_t *d_n, int Cin, int Cout, int D, int H, int W, int kd, int kh, int kw, int relu,
                      const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
@@ -167,6 +170,26 @@ int bx_ransac(const float *ss, const float *tt, const int32_t *inlier_ind, const
  * T_in: 16 doubles (the RANSAC result) cast to fp32 like the reference; T_out: 16 fp32. */
 int bx_refine(const float *ss, const float *tt, const int32_t *d_n, int maxn, const double *T_in, float dist_th,
               float *T_out, int32_t *d_rounds, void *stream);
+
+/* ---- a17: batched fixed-radius neighbours (distance-sorted, padded) ---------------------------
+ * Replaces radius_neighbors.batch_query (cpp_wrappers/cpp_neighbors/wrapper.cpp:58-239 ->
+ * neighbors/neighbors.cpp:334-480 batch_nanoflanntbb_neighbors).  h_q_batches / h_s_batches: HOST arrays
+ * (1..8 query batches, 1..2 support clouds; query batch b searches support cloud b % 2 like the reference).
+ * out == NULL: counting pass (only *d_max_count is written).  Otherwise out is [nq, cap] int32 (cap <= 4096),
+ * rows sorted by distance and padded with ns; *d_max_count = largest true neighbour count. */
+int bx_radius_neighbors(const float *queries, int nq, const float *supports, int ns, const int32_t *h_q_batches, int nqb,
+                        const int32_t *h_s_batches, int nsb, float radius, int32_t *out, int cap, int32_t *d_max_count,
+                        void *stream);
+
+/* ---- a18: voxel-grid barycentre sub-sampling ------------------------------------------------
+ * Replaces grid_subsampling.subsample (cpp_wrappers/cpp_subsampling/wrapper.cpp:631-859 ->
+ * grid_subsampling/grid_subsampling.cpp:5-106, points only).  table_keys [table_cap] u64 and table_acc
+ * [table_cap,4] f32 are workspaces (table_cap = power of two >= 2n), minmax6 a 6-float workspace.
+ * keys_out [n] (reference cell id iX + NX*iY + NX*NY*iZ), xyz_out [n,3], cnt_out [n] (may be NULL), *d_m = cells.
+ * Cells are emitted in hash-table order (the reference emits in unordered_map order). */
+int bx_grid_subsample(const float *pts, int n, float dl, unsigned long long *table_keys, float *table_acc, int table_cap,
+                      float *minmax6, unsigned long long *keys_out, float *xyz_out, int32_t *cnt_out, int32_t *d_m,
+                      void *stream);
 
 #ifdef __cplusplus
 }

@@ -835,3 +835,121 @@ BX_EXPORT void bxo_set_num_threads(int n) {
     (void)n;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * a17. Batched fixed-radius neighbours, distance-sorted, padded (baseline semantics of the reference's
+ * dead CPU module): /root/reference/cpp_wrappers/cpp_neighbors/neighbors/neighbors.cpp:334-480
+ * (batch_nanoflanntbb_neighbors, the variant wired at wrapper.cpp:199).
+ *   r2 = radius*radius in fp32; query batch b searches support cloud (b % 2) -- only s_batches[0] and
+ *   s_batches[1] get a kd-tree (:377-393, :425, :457); distances in fp64 from the fp32 coordinates,
+ *   d = ((dx*dx)+(dy*dy))+(dz*dz), kept iff d < r2 (strict, kiss_matcher/kdtree/nanoflann.hpp:250), sorted by
+ *   distance (ties: lower index first here; the reference's std::sort leaves them unspecified); the index of a
+ *   cloud-1 support is offset by s_batches[0]; rows are padded to the global maximum count with ns_total.
+ * Returns max_count; *out is malloc'ed [nq*max_count] (free with bxo_free).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { double d; int32_t i; } bxo_nd;
+static int bxo_nd_cmp(const void *a, const void *b) {
+    const bxo_nd *x = (const bxo_nd *)a, *y = (const bxo_nd *)b;
+    if (x->d < y->d) return -1;
+    if (x->d > y->d) return 1;
+    return (x->i > y->i) - (x->i < y->i);
+}
+
+BX_EXPORT int bxo_radius_neighbors(const float *queries, int nq, const float *supports, int ns_total, const int32_t *q_batches,
+                                   int nqb, const int32_t *s_batches, int nsb, float radius, int32_t **out) {
+    const double r2 = (double)(radius * radius);
+    const int s0 = nsb > 0 ? s_batches[0] : 0, s1 = nsb > 1 ? s_batches[1] : 0;
+    int32_t *cnt = (int32_t *)calloc((size_t)(nq > 0 ? nq : 1), sizeof(int32_t));
+    bxo_nd **rows = (bxo_nd **)calloc((size_t)(nq > 0 ? nq : 1), sizeof(bxo_nd *));
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int i = 0; i < nq; ++i) {
+        int b = 0, acc = 0;
+        for (int k = 0; k < nqb; ++k) {
+            if (i >= acc && i < acc + q_batches[k]) { b = k; break; }
+            acc += q_batches[k];
+        }
+        const int off = (b % 2 == 0) ? 0 : s0, n = (b % 2 == 0) ? s0 : s1;
+        const double qx = queries[3 * i], qy = queries[3 * i + 1], qz = queries[3 * i + 2];
+        bxo_nd *row = (bxo_nd *)malloc(sizeof(bxo_nd) * (size_t)(n > 0 ? n : 1));
+        int c = 0;
+        for (int j = 0; j < n; ++j) {
+            const float *s = supports + 3 * (size_t)(off + j);
+            const double dx = qx - (double)s[0], dy = qy - (double)s[1], dz = qz - (double)s[2];
+            const double d = ((dx * dx) + (dy * dy)) + (dz * dz);
+            if (d < r2) { row[c].d = d; row[c].i = off + j; ++c; }
+        }
+        qsort(row, (size_t)c, sizeof(bxo_nd), bxo_nd_cmp);
+        rows[i] = row;
+        cnt[i] = c;
+    }
+    int mc = 0;
+    for (int i = 0; i < nq; ++i) mc = cnt[i] > mc ? cnt[i] : mc;
+    int32_t *o = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nq * mc > 0 ? nq * mc : 1));
+    for (int i = 0; i < nq; ++i) {
+        for (int j = 0; j < mc; ++j) o[(size_t)i * mc + j] = j < cnt[i] ? rows[i][j].i : ns_total;
+        free(rows[i]);
+    }
+    free(rows);
+    free(cnt);
+    *out = o;
+    return mc;
+}
+
+BX_EXPORT void bxo_free(void *p) { free(p); }
+
+/* ------------------------------------------------------------------------------------------
+ * a18. Voxel-grid barycentre sub-sampling (baseline semantics):
+ * /root/reference/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106 (points only).
+ *   origin = floor(min * (1/dl)) * dl (fp32, :27); NX, NY = floor((max - origin)/dl) + 1 (:30-31);
+ *   cell = floor((p - origin)/dl) per axis (:53-55), key = iX + NX*iY + NX*NY*iZ (:56); per cell the points are
+ *   summed in INPUT order in fp32 (SampledData::update_points, grid_subsampling.h:93-98) and the barycentre is
+ *   sum * float(1.0/count) (:87).  The reference emits cells in unordered_map iteration order; here ascending key.
+ * keys_out / xyz_out / cnt_out need capacity n.  Returns the number of occupied cells.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint64_t key; int32_t idx; } bxo_ki;
+static int bxo_ki_cmp(const void *a, const void *b) {
+    const bxo_ki *x = (const bxo_ki *)a, *y = (const bxo_ki *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return (x->idx > y->idx) - (x->idx < y->idx);
+}
+
+BX_EXPORT int bxo_grid_subsample(const float *pts, int n, float dl, uint64_t *keys_out, float *xyz_out, int32_t *cnt_out) {
+    if (n <= 0) return 0;
+    float mn[3] = {pts[0], pts[1], pts[2]}, mx[3] = {pts[0], pts[1], pts[2]};
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) {
+            const float v = pts[3 * i + c];
+            if (v < mn[c]) mn[c] = v;
+            if (v > mx[c]) mx[c] = v;
+        }
+    const float inv = 1 / dl;
+    float org[3];
+    for (int c = 0; c < 3; ++c) org[c] = floorf(mn[c] * inv) * dl;
+    const uint64_t NX = (uint64_t)floorf((mx[0] - org[0]) / dl) + 1, NY = (uint64_t)floorf((mx[1] - org[1]) / dl) + 1;
+    bxo_ki *ki = (bxo_ki *)malloc(sizeof(bxo_ki) * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const uint64_t ix = (uint64_t)floorf((pts[3 * i] - org[0]) / dl), iy = (uint64_t)floorf((pts[3 * i + 1] - org[1]) / dl),
+                       iz = (uint64_t)floorf((pts[3 * i + 2] - org[2]) / dl);
+        ki[i].key = ix + NX * iy + NX * NY * iz;
+        ki[i].idx = i;
+    }
+    qsort(ki, (size_t)n, sizeof(bxo_ki), bxo_ki_cmp);
+    int m = 0;
+    for (int i = 0; i < n;) {
+        int j = i;
+        float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+        while (j < n && ki[j].key == ki[i].key) {
+            sx += pts[3 * ki[j].idx]; sy += pts[3 * ki[j].idx + 1]; sz += pts[3 * ki[j].idx + 2];
+            ++j;
+        }
+        const int c = j - i;
+        const float a = (float)(1.0 / (double)c);
+        keys_out[m] = ki[i].key;
+        xyz_out[3 * m] = sx * a; xyz_out[3 * m + 1] = sy * a; xyz_out[3 * m + 2] = sz * a;
+        if (cnt_out) cnt_out[m] = c;
+        ++m;
+        i = j;
+    }
+    free(ki);
+    return m;
+}

@@ -476,3 +476,78 @@ def register_pair(sd, cfg, data, perms, ransac_seed=0, keep=False, timings=None)
         pose = init_pose
     aux.update(ss=ss_cat.numpy(), tt=tt_cat.numpy(), R_cat=R_cat.numpy(), t_cat=t_cat.numpy())
     return pose, num_inliers, num_mutual, len(inlier_ind), scales_used, aux
+
+
+# --------------------------------------------------------------------------- #
+# a17 / a18: baseline semantics of the reference's dead CPU modules (cpp_wrappers)
+# --------------------------------------------------------------------------- #
+def radius_neighbors(queries, supports, q_batches, s_batches, radius: float) -> np.ndarray:
+    queries, supports = _f32(queries), _f32(supports)
+    qb = np.ascontiguousarray(q_batches, dtype=np.int32)
+    sb = np.ascontiguousarray(s_batches, dtype=np.int32)
+    L = lib()
+    L.bxo_radius_neighbors.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p]
+    L.bxo_free.argtypes = [c_void_p]
+    out = c_void_p()
+    mc = L.bxo_radius_neighbors(_p(queries), queries.shape[0], _p(supports), supports.shape[0], _p(qb), len(qb), _p(sb), len(sb),
+                                c_float(radius), ctypes.byref(out))
+    nq = queries.shape[0]
+    arr = np.ctypeslib.as_array(ctypes.cast(out, POINTER(c_int32)), shape=(max(nq * mc, 1),))[: nq * mc].reshape(nq, mc).copy()
+    L.bxo_free(out)
+    return arr
+
+
+def grid_subsample(points, dl: float):
+    """-> (keys uint64 [m], barycentres fp32 [m,3], counts int32 [m]) in ascending cell-key order."""
+    points = _f32(points)
+    n = points.shape[0]
+    keys = np.zeros(max(n, 1), dtype=np.uint64)
+    xyz = np.zeros((max(n, 1), 3), dtype=np.float32)
+    cnt = np.zeros(max(n, 1), dtype=np.int32)
+    L = lib()
+    L.bxo_grid_subsample.argtypes = [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]
+    m = L.bxo_grid_subsample(_p(points), n, c_float(dl), _p(keys), _p(xyz), _p(cnt))
+    return keys[:m].copy(), xyz[:m].copy(), cnt[:m].copy()
+
+
+_REF_SO = os.path.join(_HERE, "_ref", "libbxref.so")
+
+
+def ref_available() -> bool:
+    return os.path.exists(_REF_SO)
+
+
+_ref = None
+
+
+def ref_lib():
+    """The reference's own cpp_wrappers sources compiled unmodified (oracle/ref_build/build_ref.py)."""
+    global _ref
+    if _ref is None:
+        _ref = ctypes.CDLL(_REF_SO)
+        _ref.ref_batch_neighbors.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p]
+        _ref.ref_grid_subsampling.argtypes = [c_void_p, c_int, c_float, c_void_p]
+        _ref.ref_free.argtypes = [c_void_p]
+    return _ref
+
+
+def ref_radius_neighbors(queries, supports, q_batches, s_batches, radius: float) -> np.ndarray:
+    queries, supports = _f32(queries), _f32(supports)
+    qb = np.ascontiguousarray(q_batches, dtype=np.int32)
+    sb = np.ascontiguousarray(s_batches, dtype=np.int32)
+    out = c_void_p()
+    mc = ref_lib().ref_batch_neighbors(_p(queries), queries.shape[0], _p(supports), supports.shape[0], _p(qb), len(qb), _p(sb), len(sb),
+                                       c_float(radius), ctypes.byref(out))
+    nq = queries.shape[0]
+    arr = np.ctypeslib.as_array(ctypes.cast(out, POINTER(c_int32)), shape=(max(nq * mc, 1),))[: nq * mc].reshape(nq, mc).copy()
+    ref_lib().ref_free(out)
+    return arr
+
+
+def ref_grid_subsampling(points, dl: float) -> np.ndarray:
+    points = _f32(points)
+    out = c_void_p()
+    m = ref_lib().ref_grid_subsampling(_p(points), points.shape[0], c_float(dl), ctypes.byref(out))
+    arr = np.ctypeslib.as_array(ctypes.cast(out, POINTER(c_float)), shape=(max(3 * m, 1),))[: 3 * m].reshape(m, 3).copy()
+    ref_lib().ref_free(out)
+    return arr

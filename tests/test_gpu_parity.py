@@ -538,3 +538,28 @@ def test_c5_heterogeneous_pair(dev, oracle):
     data = make_pair("C5", 0)
     perms = oracle.draw_perms(cfg, 60000, 30000, 2)
     _compare_pair(model.to(dev), sd, cfg, data, perms, oracle, "C5")
+
+
+# ----------------------------------------------------------------------------------------- a17 / a18
+@pytest.mark.parametrize("radius,qb,sb", [(0.35, [300, 200], [3500, 2500]), (0.15, [777], [9000]), (0.9, [64, 64], [2000, 1000])])
+def test_radius_neighbors_bit_exact(dev, oracle, radius, qb, sb):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(int(radius * 100))
+    s = rng.uniform(-2, 2, (sum(sb), 3)).astype(np.float32)
+    q = (s[rng.choice(len(s), sum(qb), replace=False)] + rng.normal(scale=0.01, size=(sum(qb), 3))).astype(np.float32)
+    got = ops.radius_neighbors(cu(q, dev), cu(s, dev), qb, sb, radius).cpu().numpy()
+    exp = oracle.radius_neighbors(q, s, qb, sb, radius)
+    assert got.shape == exp.shape and (got == exp).all()
+
+
+def test_grid_subsample_matches_oracle(dev, oracle):
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(4)
+    pts = (rng.uniform(-3, 3, (50000, 3)) * [1, 1, 0.4]).astype(np.float32)
+    for dl in (0.1, 0.35):
+        keys, xyz, cnt = ops.grid_subsample(cu(pts, dev), dl)
+        ek, exyz, ecnt = oracle.grid_subsample(pts, dl)
+        k = keys.cpu().numpy().astype(np.uint64)
+        o = np.argsort(k)
+        assert (k[o] == ek).all() and (cnt.cpu().numpy()[o] == ecnt).all()             # cell ids and counts: bit-exact
+        assert np.abs(xyz.cpu().numpy()[o] - exyz).max() < 2e-6                         # barycentres: fp32 summation order

@@ -355,3 +355,42 @@ def test_synthetic_pairs_are_deterministic():
     a, b = make_pair("C1", 3), make_pair("C1", 3)
     assert (a["src_fds_pcd"] == b["src_fds_pcd"]).all() and a["src_fds_pcd"].dtype == np.float32
     assert a["src_fds_pcd"].shape == (5000, 3) and not (a["src_fds_pcd"] == make_pair("C1", 4)["src_fds_pcd"]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# a17 / a18: restatements against the reference's own C++ (oracle/_ref, built from /root/reference)
+# ------------------------------------------------------------------------------------------------
+def _need_ref(oracle):
+    if not oracle.ref_available():
+        if os.path.isdir("/root/reference"):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_bx_ref_build", os.path.join(ROOT, "oracle", "ref_build", "build_ref.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        else:
+            pytest.skip("oracle/_ref/libbxref.so not built and /root/reference absent")
+
+
+@pytest.mark.parametrize("radius,qb,sb", [(0.35, [300, 200], [3500, 2500]), (0.2, [500], [6000]), (0.6, [100, 150, 250], [3000, 3000])])
+def test_radius_neighbors_restatement_equals_reference_cpp(oracle, radius, qb, sb):
+    _need_ref(oracle)
+    rng = np.random.default_rng(int(radius * 100))
+    s = rng.uniform(-2, 2, (sum(sb), 3)).astype(np.float32)
+    q = (s[rng.choice(len(s), sum(qb), replace=False)] + rng.normal(scale=0.01, size=(sum(qb), 3))).astype(np.float32)
+    a = oracle.radius_neighbors(q, s, qb, sb, radius)
+    b = oracle.ref_radius_neighbors(q, s, qb, sb, radius)
+    assert a.shape == b.shape and (a == b).all()
+    assert (a[:, 0] < len(s)).all()                                      # every query has itself-ish as nearest
+
+
+def test_grid_subsample_restatement_equals_reference_cpp(oracle):
+    _need_ref(oracle)
+    rng = np.random.default_rng(3)
+    pts = (rng.uniform(-3, 3, (20000, 3)) * [1, 1, 0.4]).astype(np.float32)
+    for dl in (0.2, 0.05, 1.7):
+        keys, xyz, cnt = oracle.grid_subsample(pts, dl)
+        ref = oracle.ref_grid_subsampling(pts, dl)
+        srt = lambda x: x[np.lexsort((x[:, 2], x[:, 1], x[:, 0]))]
+        assert len(keys) == len(ref) and np.array_equal(srt(xyz), srt(ref))   # same barycentres, bit for bit
+        assert cnt.sum() == len(pts) and (np.diff(keys.astype(np.int64)) > 0).all()
