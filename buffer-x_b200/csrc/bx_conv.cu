@@ -266,6 +266,88 @@ pool_desc_kernel(const float *__restrict__ x, int K, int C, int S, const float *
     }
 }
 
+// ---- factorised first CostNet layer ---------------------------------------------------------------------
+// The cost volume is V[c][n][k][l] = d1[c][1+k][(l-n) mod 20] - d2[c][1+k][l] (models/BUFFERX.py:51-65) and the first
+// CostNet layer (patchnet.py:196, valid 3x3x3, BN folded, ReLU) is linear in it before the ReLU, so
+//     out0[co][n][k][l] = relu( A[co][k][(l-n) mod 20] - B[co][k][l] )
+//     A[co][k][m] = bias[co] + sum_{c,dk,e} Wa[c][dk][e][co] * d1[c][1+k+dk][(m+e-2) mod 20],  Wa[..e..] = sum_{dl-dn = e-2} w
+//     B[co][k][l] =            sum_{c,dk,dl} Wb[c][dk][dl][co] * d2[c][1+k+dk][l+dl],           Wb       = sum_{dn} w
+// : 60 + 54 output positions per match instead of 972 (27 MMAC -> 1.4 MMAC per match).  The next layer's loader
+// (BX_GEOM_COSTAB) regenerates out0 from A and B, so neither the 256 KB cost volume nor the 124 KB first activation
+// of a match is ever written.  One CTA per match; d1/d2 rows 1..5 staged in shared memory, weights through L1.
+constexpr int AB_T = 256;
+
+__global__ void __launch_bounds__(AB_T)
+costvol_ab_kernel(const float *__restrict__ equi_s, const float *__restrict__ equi_t, const int *__restrict__ s_mids,
+                  const int *__restrict__ t_mids, const int *__restrict__ d_M, const float *__restrict__ wa,
+                  const float *__restrict__ wb, const float *__restrict__ bias, float *__restrict__ A, float *__restrict__ B) {
+    __shared__ float d1[32 * 100], d2[32 * 100];   // [c][row 1..5][20]
+    const int m = blockIdx.x;
+    if (m >= *d_M) return;
+    const int tid = threadIdx.x;
+    const float *e1 = equi_s + (size_t)s_mids[m] * 32 * 140, *e2 = equi_t + (size_t)t_mids[m] * 32 * 140;
+    for (int i = tid; i < 3200; i += AB_T) {
+        const int c = i / 100, r = i - c * 100;
+        d1[i] = __ldg(e1 + c * 140 + 20 + r);
+        d2[i] = __ldg(e2 + c * 140 + 20 + r);
+    }
+    __syncthreads();
+    // items: [cg(4)][pos]: 4 x 60 for A, then 4 x 54 for B; 8 output channels each
+    for (int item = tid; item < 4 * 60 + 4 * 54; item += AB_T) {
+        float acc[8];
+        if (item < 240) {
+            const int cg = item / 60, pos = item - cg * 60, k = pos / 20, mm = pos - k * 20;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + cg * 8 + j);
+            int col[5];
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+                int x = mm + e - 2;
+                col[e] = x < 0 ? x + 20 : (x >= 20 ? x - 20 : x);
+            }
+            for (int c = 0; c < 32; ++c) {
+#pragma unroll
+                for (int dk = 0; dk < 3; ++dk) {
+                    const float *row = d1 + c * 100 + (k + dk) * 20;
+                    const float4 *wp = reinterpret_cast<const float4 *>(wa + ((size_t)(c * 3 + dk) * 5) * 32 + cg * 8);
+#pragma unroll
+                    for (int e = 0; e < 5; ++e) {
+                        const float x = row[col[e]];
+                        const float4 w0 = __ldg(wp + e * 8), w1 = __ldg(wp + e * 8 + 1);
+                        acc[0] += x * w0.x; acc[1] += x * w0.y; acc[2] += x * w0.z; acc[3] += x * w0.w;
+                        acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
+                    }
+                }
+            }
+            float *o = A + ((size_t)m * 32 + cg * 8) * 60 + pos;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j * 60] = acc[j];
+        } else {
+            const int it2 = item - 240;
+            const int cg = it2 / 54, pos = it2 - cg * 54, k = pos / 18, l = pos - k * 18;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+            for (int c = 0; c < 32; ++c) {
+#pragma unroll
+                for (int dk = 0; dk < 3; ++dk) {
+                    const float *row = d2 + c * 100 + (k + dk) * 20 + l;
+                    const float4 *wp = reinterpret_cast<const float4 *>(wb + ((size_t)(c * 3 + dk) * 3) * 32 + cg * 8);
+#pragma unroll
+                    for (int dl = 0; dl < 3; ++dl) {
+                        const float x = row[dl];
+                        const float4 w0 = __ldg(wp + dl * 8), w1 = __ldg(wp + dl * 8 + 1);
+                        acc[0] += x * w0.x; acc[1] += x * w0.y; acc[2] += x * w0.z; acc[3] += x * w0.w;
+                        acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
+                    }
+                }
+            }
+            float *o = B + ((size_t)m * 32 + cg * 8) * 54 + pos;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j * 54] = acc[j];
+        }
+    }
+}
+
 }  // namespace
 
 BX_API int bx_conv_layer(int geom, const float *in, const float *w, const float *bias, float *out, int n,
@@ -312,6 +394,18 @@ BX_API int bx_pool_desc(const float *x, int K, int C, int S, const float *w1, co
     BX_REQUIRE(C == 32 && S >= 1 && S <= POOL_T && K >= 0, "bx_pool_desc: expects C=32, S<=%d", POOL_T);
     if (K == 0) return BX_OK;
     pool_desc_kernel<<<K, POOL_T, 0, bx_stream(stream)>>>(x, K, C, S, w1, b1, w2, b2, desc, equi);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
+BX_API int bx_costvol_ab(const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
+                         const int32_t *d_M, int maxM, const float *wa, const float *wb, const float *bias, float *A,
+                         float *B, void *stream) {
+    BX_REQUIRE(equi_s && equi_t && s_mids && t_mids && d_M && wa && wb && bias && A && B, "bx_costvol_ab: null pointer");
+    BX_REQUIRE(maxM >= 0, "bx_costvol_ab: bad maxM");
+    BX_REQUIRE(((reinterpret_cast<uintptr_t>(wa) | reinterpret_cast<uintptr_t>(wb)) & 15) == 0, "bx_costvol_ab: weights must be 16-byte aligned");
+    if (maxM == 0) return BX_OK;
+    costvol_ab_kernel<<<maxM, AB_T, 0, bx_stream(stream)>>>(equi_s, equi_t, s_mids, t_mids, d_M, wa, wb, bias, A, B);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

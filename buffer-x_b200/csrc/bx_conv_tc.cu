@@ -8,7 +8,7 @@
 //   2. short accumulation chains: the tensor core accumulates with truncation, so the error of a chain grows
 //      linearly with its length (measured on B200, K = 1152: 5x the fp32-FFMA error for one chain, below it
 //      for chains of 12 MMAs; tools/tc_precision.py).  The ah*bh products therefore go to a PING-PONG pair
-//      of TMEM accumulators that is cut every TC_SEG stages (12 MMAs); finished segments are added with
+//      of TMEM accumulators that is cut every seg_len stages (default 6 = 12 MMAs); finished segments are added with
 //      round-to-nearest into fp32 running sums held in the loader threads' registers while the tensor core
 //      already fills the other accumulator.  The cross terms (2^-11 smaller) keep one long chain.
 //
@@ -17,17 +17,18 @@
 //               touches a barrier once per FOUR stages (mbarrier / proxy-fence latencies stay off the critical
 //               path).  thread -> row = t & 127.  Per owned stage (16 input channels of one tap; chunk-outer /
 //               tap-inner order keeps a chunk's activations in L1 across its taps) a thread fetches its row's 16
-//               activations, splits them and writes hi/lo with 16-byte STS straight into the canonical K-major
-//               no-swizzle UMMA layout (core matrix = 8 rows x 16 B):
-//                   A image [kstep][split][kunit][row(128)][16 B]   LBO = 2048 B, SBO = 128 B
-//                   B image [kstep][split][kunit][n(NT)][16 B]      LBO = NT*16 B, SBO = 128 B (host-arranged)
-//               then fence.proxy.async + mbarrier arrive on full[stage].  Thread 0 fetches the stage's B image
-//               (one contiguous 128*NT-byte block) with ONE cp.async.bulk whose transaction count lands on the
-//               same full[stage] barrier -- the weights never touch registers.
-//               Every TC_SEG stages each loader warp drains its 32 lanes x NT/4 columns of the finished main
+//               activations, splits them and writes hi/lo with tcgen05.st (32x32b.x8) into the A ring in TENSOR
+//               MEMORY (32 columns per stage: [kstep][hi,lo][8 values]); the MMAs read A from TMEM (TS form),
+//               which takes the activation operand off the shared-memory read port -- with A in shared memory
+//               the kernel was bound by smem bandwidth (3 MMAs re-read the same 128x8 tile), not by the tensor
+//               pipe.  The B (weight) image of a stage
+//                   [kstep][split][kunit][n(NT)][16 B]      K-major no-swizzle, LBO = NT*16 B, SBO = 128 B
+//               is host-arranged, contiguous, and fetched by ONE cp.async.bulk per stage whose transaction count
+//               lands on the same full[stage] barrier -- the weights never touch registers.
+//               Every seg_len stages each loader warp drains its 32 lanes x NT/4 columns of the finished main
 //               accumulator (tcgen05.ld) into its running sums and releases the accumulator (accfree barrier).
 //   warp 16     MMA issuer: waits full[stage], issues 6 tcgen05.mma (2 k-steps x {al*bh, ah*bl, ah*bh}),
-//               tcgen05.commit -> empty[stage]; 6 stages in flight, no __syncthreads in the main loop.
+//               tcgen05.commit -> empty[stage]; 4 stages in flight, no __syncthreads in the main loop.
 //   epilogue    running sums + cross accumulator + bias (+ReLU) -> coalesced stores of out[n][co][pos].
 #include "bx_common.cuh"
 
@@ -49,6 +50,7 @@ constexpr int TC_LOADERS = 512;
 constexpr int TC_THREADS = TC_LOADERS + 32;
 constexpr int TC_BM = 128;
 constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_TAPS = 128;
 constexpr int A_STAGE_COLS = 32;  // TMEM columns of one A stage: [kstep(2)][split(hi,lo)][8 tf32 values]
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,22 +69,6 @@ __device__ __forceinline__ uint32_t elect_leader() {
         "}\n"
         : "=r"(pred));
     return pred;
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
-                                         uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, q;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "setp.ne.b32 q, %0, 0;\n\t"
-        "mov.b64 da, {%2, %4};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%1], da, db, %5, p;\n\t"
-        "}\n" ::"r"(leader),
-        "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 
 // A operand from tensor memory (128 lanes x 8 tf32 columns), B operand from shared memory
@@ -192,6 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
+    __shared__ int4 tap_tab[TC_MAX_TAPS];
 
     const int n_samples = p.d_n ? *p.d_n : p.n;
     const long long Mtotal = (long long)n_samples * p.S_out;
@@ -205,6 +192,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < p.T) {   // tap geometry table: no counter arithmetic in the loader loop
+        const int dz = tid / (p.kh * p.kw), r = tid - dz * (p.kh * p.kw), dy = r / p.kw, dx = r - dy * p.kw;
+        int base = 0;
+        if (GEOM == BX_GEOM_CYL3D || GEOM == BX_GEOM_CYL2D) base = dz * 140 + (dy - 1) * 20;
+        else if (GEOM == BX_GEOM_VALID3D) base = (dz * p.H + dy) * p.W + dx;
+        tap_tab[tid] = make_int4(dz, dy, dx, base);
     }
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -249,38 +243,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 pa = p.equi_s + (size_t)p.s_mids[ln] * 32 * 140;
                 pb = p.equi_t + (size_t)p.t_mids[ln] * 32 * 140;
             }
+        } else if (GEOM == BX_GEOM_COSTAB) {
+            pa = p.equi_s + (size_t)ln * 32 * 60;     // A [32][3][20]
+            pb = p.equi_t + (size_t)ln * 32 * 54;     // B [32][3][18]
         } else {
             pa = p.in + (size_t)ln * p.Cin * p.S_in;
         }
-        const int cstride = (GEOM == BX_GEOM_CYL2D || GEOM == BX_GEOM_COSTVOL) ? 140 : (GEOM == BX_GEOM_CYL3D ? 420 : p.S_in);
-        int chunk = 0, t = 0, dz = 0, dy = 0, dx = 0;   // incremental (chunk, tap) counters: no division in the loop
-        auto advance = [&]() {
-            ++t;
-            if (++dx == p.kw) {
-                dx = 0;
-                if (++dy == p.kh) { dy = 0; ++dz; }
-            }
-            if (t == p.T) { t = 0; dz = 0; dy = 0; dx = 0; ++chunk; }
+        const int cstride = (GEOM == BX_GEOM_CYL2D || GEOM == BX_GEOM_COSTVOL) ? 140
+                            : (GEOM == BX_GEOM_CYL3D ? 420 : (GEOM == BX_GEOM_COSTAB ? 60 : p.S_in));
+        // (chunk, tap) of the stage this group fills next; the tap geometry comes from the shared table
+        int chunk = grp / p.T, t = grp - chunk * p.T;
+        auto advance4 = [&]() {
+            t += 4;
+            while (t >= p.T) { t -= p.T; ++chunk; }
         };
+        const int oy20 = oy * 20;
+        const int rowbase = (oz * p.H + oy) * p.W + ox;   // VALID3D
         float a_reg[16];
 
         auto load_stage = [&]() {                       // the stage the counters point at
+            const int4 tp = tap_tab[t];                  // (dz, dy, dx, geometry-specific base offset)
             int offA = 0, offB = 0;
             bool ok = lvalid;
             if (GEOM == BX_GEOM_CYL3D || GEOM == BX_GEOM_CYL2D) {
-                const int yy = oy + dy - 1;
-                int xx = ox + dx - 1;
+                const int yy = oy + tp.y - 1;
+                int xx = ox + tp.z - 1;
                 xx = xx < 0 ? xx + 20 : (xx >= 20 ? xx - 20 : xx);
-                ok = lvalid && yy >= 0 && yy < 7;
-                offA = dz * 140 + yy * 20 + xx;
+                ok = lvalid && (unsigned)yy < 7u;
+                offA = tp.w + oy20 + xx;
             } else if (GEOM == BX_GEOM_VALID3D) {
-                offA = ((oz + dz) * p.H + (oy + dy)) * p.W + (ox + dx);
-            } else {  // COSTVOL: value(c, n, k, l) = d1[c][1+k][(l-n) mod 20] - d2[c][1+k][l]
-                const int nn = oz + dz, kk = oy + dy, ll = ox + dx;
+                offA = rowbase + tp.w;
+            } else if (GEOM == BX_GEOM_COSTVOL) {  // value(c, n, k, l) = d1[c][1+k][(l-n) mod 20] - d2[c][1+k][l]
+                const int nn = oz + tp.x, kk = oy + tp.y, ll = ox + tp.z;
                 int sh = ll - nn;
                 sh = sh < 0 ? sh + 20 : sh;
                 offA = (1 + kk) * 20 + sh;
                 offB = (1 + kk) * 20 + ll;
+            } else {  // COSTAB: value(c, n, k, l) = relu(A[c][k][(l-n) mod 20] - B[c][k][l])
+                const int nn = oz + tp.x, kk = oy + tp.y, ll = ox + tp.z;
+                int sh = ll - nn;
+                sh = sh < 0 ? sh + 20 : sh;
+                offA = kk * 20 + sh;
+                offB = kk * 18 + ll;
             }
             const int c0 = chunk * 16;
             const float *src = pa + (size_t)c0 * cstride + offA;
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 float v = 0.0f;
                 if (ok) {
                     if (GEOM == BX_GEOM_COSTVOL) v = src[kk * cstride] - pb[(size_t)(c0 + kk) * 140 + offB];
+                    else if (GEOM == BX_GEOM_COSTAB) v = fmaxf(__ldg(src + kk * cstride) - __ldg(pb + (c0 + kk) * 54 + offB), 0.0f);
                     else v = __ldg(src + kk * cstride);
                 }
                 a_reg[kk] = v;
@@ -334,7 +339,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             }
         };
 
-        for (int k = 0; k < grp; ++k) advance();         // counters -> this group's first stage
         if (grp < n_iters) load_stage();
         int next_drain = 0;
         for (int it = grp; it < n_iters; it += 4) {
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             }
             store_stage(s);
             if (it + 4 < n_iters) {                       // this group's next stage: activations in flight
-                advance(); advance(); advance(); advance();
+                advance4();
                 load_stage();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // tcgen05.st ordered before the arrive
@@ -473,6 +477,7 @@ BX_API int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const 
     BX_REQUIRE(w_tc && bias && out, "bx_conv_layer_tc: null pointer");
     BX_REQUIRE(n >= 0 && Cin >= 16 && Cin % 16 == 0 && Cout >= 1 && Cout <= 128, "bx_conv_layer_tc: bad channels Cin=%d Cout=%d", Cin, Cout);
     BX_REQUIRE((reinterpret_cast<uintptr_t>(w_tc) & 15) == 0, "bx_conv_layer_tc: weights must be 16-byte aligned");
+    BX_REQUIRE(kd >= 1 && kh >= 1 && kw >= 1 && (long long)kd * kh * kw <= TC_MAX_TAPS, "bx_conv_layer_tc: at most %d kernel taps", TC_MAX_TAPS);
     ConvTcParams p = {};
     p.in = in; p.w = w_tc; p.bias = bias; p.out = out; p.n = n; p.d_n = d_n;
     p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
@@ -499,6 +504,11 @@ BX_API int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const 
             BX_REQUIRE(Cin == 32 && D == 20 && H == 5 && W == 20 && kd == 3 && kh == 3 && kw == 3, "bx_conv_layer_tc: COSTVOL expects the [32,20,5,20] volume, k=3x3x3");
             p.OD = 18; p.OH = 3; p.OW = 18; p.S_in = 2000; p.S_out = 972;
             return dispatch_nt<BX_GEOM_COSTVOL>(p, n, st);
+        case BX_GEOM_COSTAB:
+            BX_REQUIRE(equi_s && equi_t, "bx_conv_layer_tc: COSTAB needs the A and B factors");
+            BX_REQUIRE(Cin == 32 && D == 18 && H == 3 && W == 18 && kd == 3 && kh == 3 && kw == 3, "bx_conv_layer_tc: COSTAB expects the [32,18,3,18] activation, k=3x3x3");
+            p.OD = 16; p.OH = 1; p.OW = 16; p.S_in = 972; p.S_out = 256;
+            return dispatch_nt<BX_GEOM_COSTAB>(p, n, st);
         default:
             bx_set_error("bx_conv_layer_tc: unknown geometry %d", geom);
             return BX_ERR_INVALID_ARG;

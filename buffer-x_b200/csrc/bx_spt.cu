@@ -4,114 +4,185 @@
 // sphere_query + var_to_invar (/root/reference/utils/common.py:422-498) and the 1x1 conv + BN + ReLU +
 // max over the 10 samples (patch_embedder.py:26-30, 73-77).  The reference writes [K,420,10] indices,
 // [K,420,10,3] points (75.6 MB at K=1500) and [K,16,420,10] activations (403 MB) to HBM per call; here
-// one CTA owns a patch: its P points sit in shared memory (SoA), each warp walks voxels, finds the first
-// `nv` in-ball points in index order with ballot/popcount, de-rotates them, applies the folded 3->16
-// affine map + ReLU, max-reduces, and the [16,V] tile leaves the SM once, coalesced (26.9 KB/patch).
+// one CTA owns a patch and only the [16,V] feature tile leaves the SM (26.9 KB/patch).
 //
-// Bit contract for the integer selection (oracle bxo_spt): d2 = ((qx-x)^2+(qy-y)^2)+(qz-z)^2 < r*r,
-// first nv hits in index order; slot 0 zeroed when its index is 0 (utils/common.py:447-449), padding
-// slots zeroed.  De-rotation x' = x*c + y*(-s), y' = x*s + y*c, z' = z.  -fmad=false.
+// The selection "first nv points, in index order, inside each voxel ball" is evaluated point-major instead of
+// voxel-major (420 x 512 = 215 K distance tests per patch in the reference's ball query):
+//   1. every non-zero point enumerates only the voxels that CAN contain it -- shells with ||p| - s_r| < rho,
+//      elevation rows with |p_z - c_z| < rho, azimuth bins within asin(rho / R_c) of the point's bin (all bins
+//      where the voxel ring is closer than rho to the axis) -- runs the EXACT test on those (~30-60 instead of
+//      420) and records hits in a per-voxel bitmap over the patch indices (atomicOr in shared memory);
+//   2. the exact-zero points (the key-point copies that pad a patch, up to 80 % of it at the finest scale) are
+//      one ballot mask that is OR-ed into every voxel whose ball contains the origin;
+//   3. a thread per voxel walks its bitmap words in index order and keeps the first nv set bits;
+//   4. a thread per (voxel, channel) de-rotates the selected points, applies the folded 3->16 affine map +
+//      ReLU and max-reduces; the store is coalesced along the voxel axis.
+// The candidate enumeration is conservative (slack 1e-3 on the bands, +1 azimuth bin), membership itself is
+// the bit-exact test of oracle bxo_spt: d2 = ((qx-x)^2+(qy-y)^2)+(qz-z)^2 < r*r; slot 0 zeroed when its index
+// is 0 (utils/common.py:447-449), padding slots zeroed; x' = x*c + y*(-s), y' = x*s + y*c.  -fmad=false.
 #include "bx_common.cuh"
 
 namespace {
 
-constexpr int SPT_WARPS = 8;
+constexpr int SPT_THREADS = 256;
 constexpr int MAX_NV = 16;
+constexpr int MAX_RE = 64;   // rad_n * ele_n rows of the voxel table
 
-__global__ void __launch_bounds__(SPT_WARPS * 32)
+__global__ void __launch_bounds__(SPT_THREADS)
 spt_pnt_kernel(const float *__restrict__ delta, int K, int P, const float *__restrict__ voxels, int V, int azi_n,
                const float *__restrict__ rot, float voxel_r, int nv, const float *__restrict__ w,
                const float *__restrict__ b, float *__restrict__ feat, int *__restrict__ dbg_vidx,
                float *__restrict__ dbg_inv) {
     extern __shared__ float smem[];
-    float *px = smem;            // P
-    float *py = px + P;          // P
-    float *pz = py + P;          // P
-    float *ft = pz + P;          // 16*V
-    float *vx = ft + 16 * V;     // 3*V
-    float *sw = vx + 3 * V;      // 64 (w[16][3], b[16])
-    float *srot = sw + 64;       // 2*azi_n
-    int *sel = reinterpret_cast<int *>(srot + 2 * azi_n);  // SPT_WARPS * MAX_NV
+    const int NW = (P + 31) >> 5;
+    float *px = smem;                                   // P
+    float *py = px + P;                                 // P
+    float *pz = py + P;                                 // P
+    float *vx = pz + P;                                 // 3*V
+    float *sw = vx + 3 * V;                             // 64 (w[16][3], b[16])
+    float *srot = sw + 64;                              // 2*azi_n
+    float *re_s = srot + 2 * azi_n;                     // MAX_RE: |c| of the row
+    float *re_z = re_s + MAX_RE;                        // MAX_RE: c_z of the row
+    int *re_h = reinterpret_cast<int *>(re_z + MAX_RE); // MAX_RE: azimuth half width (>= azi_n/2 means "all")
+    unsigned *bitmap = reinterpret_cast<unsigned *>(re_h + MAX_RE);   // V*NW
+    unsigned *zmask = bitmap + (size_t)V * NW;                         // NW
+    unsigned short *sel = reinterpret_cast<unsigned short *>(zmask + NW);  // V*MAX_NV
+    unsigned char *scnt = reinterpret_cast<unsigned char *>(sel + (size_t)V * MAX_NV);  // V
 
     const int k = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n_re = V / azi_n;
     const float *dl = delta + (size_t)k * P * 3;
-    for (int i = tid; i < 3 * P; i += blockDim.x) {
+    for (int i = tid; i < 3 * P; i += SPT_THREADS) {
         const float v = dl[i];
         const int s = i / 3, c = i - 3 * s;
         (c == 0 ? px : (c == 1 ? py : pz))[s] = v;
     }
-    for (int i = tid; i < 3 * V; i += blockDim.x) vx[i] = voxels[i];
+    for (int i = tid; i < 3 * V; i += SPT_THREADS) vx[i] = voxels[i];
     if (tid < 48) sw[tid] = w[tid];
     if (tid < 16) sw[48 + tid] = b[tid];
-    for (int i = tid; i < 2 * azi_n; i += blockDim.x) srot[i] = rot[i];
+    for (int i = tid; i < 2 * azi_n; i += SPT_THREADS) srot[i] = rot[i];
+    for (int i = tid; i < V * NW; i += SPT_THREADS) bitmap[i] = 0u;
     __syncthreads();
 
     const float r2 = voxel_r * voxel_r;
-    int *my = sel + warp * MAX_NV;
-    const int ch = lane & 15, half = lane >> 4;
-    const float w0 = sw[3 * ch], w1 = sw[3 * ch + 1], w2 = sw[3 * ch + 2], bb = sw[48 + ch];
-    const float empty_val = fmaxf(bb, 0.0f);  // relu(bn(conv(0))) -- what a zeroed slot contributes
-
-    for (int v = warp; v < V; v += SPT_WARPS) {
+    const float slack = voxel_r + 1e-3f;
+    const float step = 6.283185307179586f / (float)azi_n;
+    // ---- per (shell, elevation) row: |c|, c_z, azimuth half width ------------------------------------
+    if (tid < n_re) {
+        const float cx = vx[3 * (tid * azi_n)], cy = vx[3 * (tid * azi_n) + 1], cz = vx[3 * (tid * azi_n) + 2];
+        re_s[tid] = sqrtf(cx * cx + cy * cy + cz * cz);
+        re_z[tid] = cz;
+        const float Rc = sqrtf(cx * cx + cy * cy);
+        int h = azi_n;  // all bins
+        if (Rc > slack) h = (int)ceilf(asinf(fminf(1.0f, slack / Rc)) / step) + 1;
+        re_h[tid] = h;
+    }
+    // ---- zero mask (exact zeros: the key-point copies) -----------------------------------------------
+    for (int base = 0; base < NW * 32; base += SPT_THREADS) {
+        const int i = base + tid;
+        const bool z = (i < P) && (px[i] == 0.0f) && (py[i] == 0.0f) && (pz[i] == 0.0f);
+        const unsigned m = __ballot_sync(BX_FULL, z);
+        if (lane == 0 && (i >> 5) < NW) zmask[i >> 5] = m;
+    }
+    __syncthreads();
+    // ---- 1. voxels whose ball contains the origin take every zero point --------------------------------
+    for (int v = tid; v < V; v += SPT_THREADS) {
         const float qx = vx[3 * v], qy = vx[3 * v + 1], qz = vx[3 * v + 2];
-        int cnt = 0;
-        for (int base = 0; base < P; base += 32) {
-            const int i = base + lane;
-            bool hit = false;
-            if (i < P) hit = bx_d2(qx - px[i], qy - py[i], qz - pz[i]) < r2;
-            const unsigned m = __ballot_sync(BX_FULL, hit);
-            if (m) {
-                const int slot = cnt + __popc(m & ((1u << lane) - 1u));
-                if (hit && slot < nv) my[slot] = i;
-                cnt += __popc(m);
-                if (cnt >= nv) break;
+        if (bx_d2(qx - 0.0f, qy - 0.0f, qz - 0.0f) < r2)
+            for (int wd = 0; wd < NW; ++wd) bitmap[(size_t)v * NW + wd] = zmask[wd];
+    }
+    __syncthreads();
+    // ---- 2. non-zero points: exact test on their candidate voxels --------------------------------------
+    for (int i = tid; i < P; i += SPT_THREADS) {
+        if ((zmask[i >> 5] >> (i & 31)) & 1u) continue;
+        const float x = px[i], y = py[i], z = pz[i];
+        const float rad = sqrtf(x * x + y * y + z * z);
+        float al = atan2f(y, x);
+        if (al < 0.0f) al += 6.283185307179586f;
+        int ap = (int)floorf(al / step);
+        ap = min(max(ap, 0), azi_n - 1);
+        const unsigned bit = 1u << (i & 31);
+        const int wd = i >> 5;
+        for (int re = 0; re < n_re; ++re) {
+            if (fabsf(rad - re_s[re]) >= slack || fabsf(z - re_z[re]) >= slack) continue;
+            const int h = re_h[re];
+            const int lo = (2 * h + 1 >= azi_n) ? 0 : ap - h;
+            const int cnt = (2 * h + 1 >= azi_n) ? azi_n : 2 * h + 1;
+            for (int j = 0; j < cnt; ++j) {
+                int a = lo + j;
+                a = a < 0 ? a + azi_n : (a >= azi_n ? a - azi_n : a);
+                const int v = re * azi_n + a;
+                if (bx_d2(vx[3 * v] - x, vx[3 * v + 1] - y, vx[3 * v + 2] - z) < r2) atomicOr(&bitmap[(size_t)v * NW + wd], bit);
             }
         }
-        if (cnt > nv) cnt = nv;
-        __syncwarp();
-        const int first = cnt > 0 ? my[0] : 0;
+    }
+    __syncthreads();
+    // ---- 3. first nv set bits per voxel, in index order -------------------------------------------------
+    for (int v = tid; v < V; v += SPT_THREADS) {
+        int c = 0;
+        for (int wd = 0; wd < NW && c < nv; ++wd) {
+            unsigned m = bitmap[(size_t)v * NW + wd];
+            while (m && c < nv) {
+                const int bpos = __ffs(m) - 1;
+                m &= m - 1;
+                sel[(size_t)v * MAX_NV + c] = (unsigned short)(wd * 32 + bpos);
+                ++c;
+            }
+        }
+        scnt[v] = (unsigned char)c;
+        if (dbg_vidx || dbg_inv) {
+            const int first = c > 0 ? sel[(size_t)v * MAX_NV] : 0;
+            const int a = v % azi_n;
+            const float cs = srot[2 * a], sn = srot[2 * a + 1];
+            for (int l = 0; l < nv; ++l) {
+                const int i = (l < c) ? sel[(size_t)v * MAX_NV + l] : first;
+                const size_t o = ((size_t)k * V + v) * nv + l;
+                if (dbg_vidx) dbg_vidx[o] = i;
+                if (dbg_inv) {
+                    const bool live = (l < c) && !(l == 0 && first == 0);
+                    float xr = 0.f, yr = 0.f, zr = 0.f;
+                    if (live) {
+                        xr = (px[i] * cs) + (py[i] * (-sn));
+                        yr = (px[i] * sn) + (py[i] * cs);
+                        zr = pz[i];
+                    }
+                    dbg_inv[3 * o] = xr; dbg_inv[3 * o + 1] = yr; dbg_inv[3 * o + 2] = zr;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 4. features: thread per (channel, voxel), voxel fastest -> coalesced stores ----------------------
+    float *out = feat + (size_t)k * 16 * V;
+    for (int t = tid; t < 16 * V; t += SPT_THREADS) {
+        const int ch = t / V, v = t - ch * V;
+        const float w0 = sw[3 * ch], w1 = sw[3 * ch + 1], w2 = sw[3 * ch + 2], bb = sw[48 + ch];
+        const int c = scnt[v];
+        const int first = c > 0 ? sel[(size_t)v * MAX_NV] : 0;
         const int a = v % azi_n;
         const float cs = srot[2 * a], sn = srot[2 * a + 1];
-        // live slots: l < cnt, except slot 0 when its index is 0
-        const int l0 = (first == 0) ? 1 : 0;
-        const bool any_zero = (cnt < nv) || (first == 0);
-        float best = any_zero ? empty_val : -INFINITY;
-        for (int l = l0 + half; l < cnt; l += 2) {
-            // two half-warps interleave the live slots; (l0+half) may skip slot parity, handled by stride 2
-            const int i = my[l];
+        const bool any_zero = (c < nv) || (first == 0);
+        float best = any_zero ? fmaxf(bb, 0.0f) : -INFINITY;   // a zeroed slot contributes relu(bn(conv(0)))
+        for (int l = (first == 0) ? 1 : 0; l < c; ++l) {
+            const int i = sel[(size_t)v * MAX_NV + l];
             const float x = px[i], y = py[i], z = pz[i];
             const float xr = (x * cs) + (y * (-sn));
             const float yr = (x * sn) + (y * cs);
             const float val = (((w0 * xr) + (w1 * yr)) + (w2 * z)) + bb;
             best = fmaxf(best, fmaxf(val, 0.0f));
         }
-        best = fmaxf(best, __shfl_xor_sync(BX_FULL, best, 16));
-        if (lane < 16) ft[ch * V + v] = best;
-        if (dbg_vidx || dbg_inv) {
-            if (lane < nv) {
-                const int l = lane;
-                const int i = (l < cnt) ? my[l] : first;
-                const size_t o = ((size_t)k * V + v) * nv + l;
-                if (dbg_vidx) dbg_vidx[o] = i;
-                if (dbg_inv) {
-                    const bool live = (l < cnt) && !(l == 0 && first == 0);
-                    float xr = 0.f, yr = 0.f, zr = 0.f;
-                    if (live) {
-                        const float x = px[i], y = py[i], z = pz[i];
-                        xr = (x * cs) + (y * (-sn));
-                        yr = (x * sn) + (y * cs);
-                        zr = z;
-                    }
-                    dbg_inv[3 * o] = xr; dbg_inv[3 * o + 1] = yr; dbg_inv[3 * o + 2] = zr;
-                }
-            }
-        }
-        __syncwarp();
+        out[t] = best;
     }
-    __syncthreads();
-    float *out = feat + (size_t)k * 16 * V;
-    for (int i = tid; i < 16 * V; i += blockDim.x) out[i] = ft[i];
+}
+
+size_t spt_smem_bytes(int P, int V, int azi_n) {
+    const int NW = (P + 31) >> 5;
+    size_t bytes = sizeof(float) * (3 * (size_t)P + 3 * (size_t)V + 64 + 2 * (size_t)azi_n + 3 * MAX_RE);
+    bytes += sizeof(unsigned) * ((size_t)V * NW + NW);
+    bytes += sizeof(unsigned short) * (size_t)V * MAX_NV;
+    bytes += (size_t)V + 16;
+    return bytes;
 }
 
 }  // namespace
@@ -120,18 +191,18 @@ BX_API int bx_spt_pnt(const float *delta, int K, int P, const float *voxels, int
                       float voxel_r, int nv, const float *w, const float *b, float *feat, int32_t *dbg_vidx,
                       float *dbg_inv, void *stream) {
     BX_REQUIRE(delta && voxels && rot && w && b && feat, "bx_spt_pnt: null pointer");
-    BX_REQUIRE(K >= 0 && P >= 1 && V >= 1 && azi_n >= 1 && nv >= 1 && nv <= MAX_NV, "bx_spt_pnt: bad sizes");
+    BX_REQUIRE(K >= 0 && P >= 1 && P <= 65535 && V >= 1 && azi_n >= 1 && nv >= 1 && nv <= MAX_NV, "bx_spt_pnt: bad sizes");
+    BX_REQUIRE(V % azi_n == 0 && V / azi_n <= MAX_RE, "bx_spt_pnt: V must be (rad_n*ele_n <= %d) * azi_n", MAX_RE);
     if (K == 0) return BX_OK;
-    const size_t smem = sizeof(float) * (3 * (size_t)P + 16 * (size_t)V + 3 * (size_t)V + 64 + 2 * (size_t)azi_n) +
-                        sizeof(int) * SPT_WARPS * MAX_NV;
+    const size_t smem = spt_smem_bytes(P, V, azi_n);
     BX_REQUIRE(smem <= 200 * 1024, "bx_spt_pnt: P=%d V=%d needs %zu bytes of shared memory", P, V, smem);
     static size_t attr = 0;
     if (smem > attr) {
         BX_CUDA(cudaFuncSetAttribute(spt_pnt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    spt_pnt_kernel<<<K, SPT_WARPS * 32, smem, bx_stream(stream)>>>(delta, K, P, voxels, V, azi_n, rot, voxel_r, nv, w, b,
-                                                                  feat, dbg_vidx, dbg_inv);
+    spt_pnt_kernel<<<K, SPT_THREADS, smem, bx_stream(stream)>>>(delta, K, P, voxels, V, azi_n, rot, voxel_r, nv, w, b,
+                                                             feat, dbg_vidx, dbg_inv);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

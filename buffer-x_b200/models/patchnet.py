@@ -16,6 +16,9 @@ from bufferx_b200 import ops
 # Debug switch only: BX_CONV=ffma routes the conv stacks through the fp32 CUDA-core kernel (bx_conv.cu)
 # instead of the tcgen05 kernel (bx_conv_tc.cu).  Both are sm_100a kernels of this library.
 USE_FFMA = os.environ.get("BX_CONV", "tc").lower() == "ffma"
+# Debug switch only: BX_COSTVOL=direct runs the first CostNet layer as a convolution over the on-the-fly cost volume
+# (GEOM_COSTVOL) instead of its factorised form (bx_costvol_ab + GEOM_COSTAB).
+DIRECT_COSTVOL = os.environ.get("BX_COSTVOL", "factored").lower() == "direct"
 
 
 def fold_conv_bn(conv_w, conv_b, bn_mean=None, bn_var=None, bn_w=None, bn_b=None, eps=1e-5):
@@ -131,12 +134,24 @@ class CostNet(_ConvStack):
         L = self.folded()
         D, H, W = 20, 5, 20
         cur = None
+        factored = (not USE_FFMA) and not DIRECT_COSTVOL
         for i, l in enumerate(L):
             kd, kh, kw = l["k"]
             OD, OH, OW = D - kd + 1, H - kh + 1, W - kw + 1
-            out = torch.empty((maxM, l["cout"], OD * OH * OW), dtype=torch.float32, device=dev)
             conv, w = (ops.conv_layer, l["w"]) if USE_FFMA else (ops.conv_layer_tc, l["w_tc"])
-            if i == 0:
+            if factored and i == 0:
+                # first layer is linear in the cost volume before its ReLU: two small convolutions of the equivariant
+                # maps (bx_costvol_ab); the second layer's loader rebuilds relu(A - B) on the fly (GEOM_COSTAB)
+                if "wa" not in l:
+                    l["wa"], l["wb"] = ops.costvol_factor_weights(l["w"])
+                fa, fb = ops.costvol_ab(equi_s, equi_t, s_mids, t_mids, d_M, maxM, l["wa"], l["wb"], l["b"])
+                D, H, W = OD, OH, OW
+                continue
+            out = torch.empty((maxM, l["cout"], OD * OH * OW), dtype=torch.float32, device=dev)
+            if factored and i == 1:
+                conv(ops.GEOM_COSTAB, None, w, l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"],
+                     d_n=d_M, equi_s=fa, equi_t=fb)
+            elif i == 0:
                 conv(ops.GEOM_COSTVOL, None, w, l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"],
                      d_n=d_M, equi_s=equi_s, equi_t=equi_t, s_mids=s_mids, t_mids=t_mids)
             else:

@@ -22,10 +22,10 @@ SYMBOLS = [
     "bx_select_patches", "bx_ball_query", "bx_lrf", "bx_spt_pnt", "bx_conv_layer", "bx_conv_tc_ntile", "bx_conv_layer_tc",
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
-    "bx_radius_neighbors", "bx_grid_subsample",
+    "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab",
 ]
 
-GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL = 0, 1, 2, 3
+GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
 RADIUS_BINS = 8192
 
 _lib = None
@@ -63,6 +63,7 @@ def load_library():
     lib.bx_conv_layer.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_layer_tc.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_tc_ntile.argtypes = [c_int]
+    lib.bx_costvol_ab.argtypes = [P, P, P, P, P, c_int, P, P, P, P, P, P]
     lib.bx_pool_desc.argtypes = [P, c_int, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_mutual_nn.argtypes = [P, c_int, P, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_hypotheses.argtypes = [P, c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P]
@@ -133,6 +134,22 @@ class Profiler:
 profiler = None  # set to a Profiler() to record spans
 
 
+class _Span:
+    """with _Span("name"): <C-ABI call>  -- no-op unless ops.profiler is set"""
+
+    def __init__(self, name, work=0.0):
+        self.ev = profiler.span(name, work) if profiler else None
+
+    def __enter__(self):
+        if self.ev:
+            self.ev[0].record()
+
+    def __exit__(self, *exc):
+        if self.ev:
+            self.ev[1].record()
+        return False
+
+
 def fps(xyz: torch.Tensor, offsets, npoint: int, want_kpts=True):
     """xyz [sumN,3] f32 cuda; offsets: host sequence of B+1 ints.  Returns idx [B,npoint] i32, kpts [B,npoint,3]."""
     lib = load_library()
@@ -140,7 +157,8 @@ def fps(xyz: torch.Tensor, offsets, npoint: int, want_kpts=True):
     B = len(off) - 1
     idx = torch.empty((B, npoint), dtype=I32, device=xyz.device)
     kp = torch.empty((B, npoint, 3), dtype=F32, device=xyz.device) if want_kpts else None
-    _check(lib.bx_fps(_dp(xyz, F32, "xyz"), off.ctypes.data_as(c_void_p), B, npoint, _dp(idx), _dp(kp), _stream()), "bx_fps")
+    with _Span("fps"):
+        _check(lib.bx_fps(_dp(xyz, F32, "xyz"), off.ctypes.data_as(c_void_p), B, npoint, _dp(idx), _dp(kp), _stream()), "bx_fps")
     return idx, kp
 
 
@@ -212,7 +230,8 @@ def lrf(patches: torch.Tensor, des_r, aligned: bool, delta=None):
     Rt = torch.empty((K, 3, 3), dtype=F32, device=dev)
     ra = torch.empty((K, 3), dtype=F32, device=dev)
     rv, rp = (0.0, _dp(des_r, F32, "des_r")) if isinstance(des_r, torch.Tensor) else (float(des_r), None)
-    _check(load_library().bx_lrf(_dp(patches, F32, "patches"), K, P, rv, rp, int(bool(aligned)), _dp(delta), _dp(Rt), _dp(ra), _stream()), "bx_lrf")
+    with _Span("lrf", 24.0 * K * P):
+        _check(load_library().bx_lrf(_dp(patches, F32, "patches"), K, P, rv, rp, int(bool(aligned)), _dp(delta), _dp(Rt), _dp(ra), _stream()), "bx_lrf")
     return delta, Rt, ra
 
 
@@ -224,8 +243,9 @@ def spt_pnt(delta, voxels, rot, voxel_r: float, nv: int, w, b, azi_n: int, debug
         feat = torch.empty((K, 16, V), dtype=F32, device=dev)
     vidx = torch.empty((K, V, nv), dtype=I32, device=dev) if debug else None
     inv = torch.empty((K, V, nv, 3), dtype=F32, device=dev) if debug else None
-    _check(load_library().bx_spt_pnt(_dp(delta, F32, "delta"), K, P, _dp(voxels, F32), V, azi_n, _dp(rot, F32), float(voxel_r), nv,
-                                     _dp(w, F32), _dp(b, F32), _dp(feat), _dp(vidx), _dp(inv), _stream()), "bx_spt_pnt")
+    with _Span("spt", 12.0 * K * P + 64.0 * K * V):
+        _check(load_library().bx_spt_pnt(_dp(delta, F32, "delta"), K, P, _dp(voxels, F32), V, azi_n, _dp(rot, F32), float(voxel_r), nv,
+                                         _dp(w, F32), _dp(b, F32), _dp(feat), _dp(vidx), _dp(inv), _stream()), "bx_spt_pnt")
     return (feat, vidx, inv) if debug else feat
 
 
@@ -287,6 +307,32 @@ def conv_layer_tc(geom, x, w_tc, bias, out, n, Cin, Cout, D, H, W, kd, kh, kw, r
     if ev:
         ev[1].record()
     return out
+
+
+def costvol_factor_weights(Wt: torch.Tensor):
+    """Folded first CostNet layer [27 taps (dn,dk,dl), 32, 32] -> (wa [32,3,5,32], wb [32,3,3,32]) of bx_costvol_ab:
+    wa[c,dk,e,co] = sum of w over (dn,dl) with dl - dn = e - 2, wb[c,dk,dl,co] = sum over dn (fp64 sums, fp32 storage)."""
+    W = Wt.detach().double().cpu().view(3, 3, 3, Wt.shape[1], Wt.shape[2])     # [dn, dk, dl, c, co]
+    wa = torch.zeros((Wt.shape[1], 3, 5, Wt.shape[2]), dtype=torch.float64)
+    for dn in range(3):
+        for dl in range(3):
+            wa[:, :, dl - dn + 2, :] += W[dn, :, dl].permute(1, 0, 2)
+    wb = W.sum(dim=0).permute(2, 0, 1, 3).contiguous()                              # [c, dk, dl, co]
+    return wa.float().contiguous().to(Wt.device), wb.float().contiguous().to(Wt.device)
+
+
+def costvol_ab(equi_s, equi_t, s_mids, t_mids, d_M, maxM, wa, wb, bias, A=None, B=None):
+    """Factors of the first CostNet activation: out0 = relu(A[co][k][(l-n) mod 20] - B[co][k][l])."""
+    dev = equi_s.device
+    if A is None:
+        A = torch.empty((maxM, 32, 3, 20), dtype=F32, device=dev)
+    if B is None:
+        B = torch.empty((maxM, 32, 3, 18), dtype=F32, device=dev)
+    with _Span("conv_cost"):
+        _check(load_library().bx_costvol_ab(_dp(equi_s, F32, "equi_s"), _dp(equi_t, F32, "equi_t"), _dp(s_mids, I32, "s_mids"),
+                                            _dp(t_mids, I32, "t_mids"), _dp(d_M, I32, "d_M"), int(maxM), _dp(wa, F32, "wa"), _dp(wb, F32, "wb"),
+                                            _dp(bias, F32, "bias"), _dp(A), _dp(B), _stream()), "bx_costvol_ab")
+    return A, B
 
 
 def pool_desc(x, w1, b1, w2, b2, desc=None, equi=None):

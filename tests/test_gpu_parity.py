@@ -490,6 +490,41 @@ def test_cost_volume_first_layer_tc_vs_ffma(dev, oracle, c1):
     model.cpu()
 
 
+def test_cost_volume_factorised_first_layer(dev, oracle, c1):
+    """bx_costvol_ab + GEOM_COSTAB (first CostNet layer as two small convolutions, second layer regenerating
+    relu(A - B) in its loader) against the direct COSTVOL -> VALID3D chain of the CUDA-core kernel."""
+    from bufferx_b200 import ops
+    sc = c1["res"][5]["scales"][0]
+    model = c1["model"].to(dev)
+    L0, L1 = model.Pose.conv.folded()[0], model.Pose.conv.folded()[1]
+    es, et = cu(sc["src"]["equi"].numpy(), dev), cu(sc["tgt"]["equi"].numpy(), dev)
+    M = len(sc["s_mids"])
+    sm, tm = cu(sc["s_mids"], dev, torch.int32), cu(sc["t_mids"], dev, torch.int32)
+    dM = torch.tensor([M - 2], dtype=torch.int32, device=dev)
+    a0 = torch.zeros((M, 32, 972), device=dev)
+    ops.conv_layer(ops.GEOM_COSTVOL, None, L0["w"], L0["b"], a0, M, 32, 32, 20, 5, 20, 3, 3, 3, True, d_n=dM, equi_s=es, equi_t=et, s_mids=sm, t_mids=tm)
+    a1 = torch.zeros((M, 64, 256), device=dev)
+    ops.conv_layer(ops.GEOM_VALID3D, a0, L1["w"], L1["b"], a1, M, 32, 64, 18, 3, 18, 3, 3, 3, True, d_n=dM)
+    wa, wb = ops.costvol_factor_weights(L0["w"])
+    A = torch.zeros((M, 32, 3, 20), device=dev)
+    B = torch.zeros((M, 32, 3, 18), device=dev)
+    ops.costvol_ab(es, et, sm, tm, dM, M, wa, wb, L0["b"], A, B)
+    assert (A[M - 2:] == 0).all() and (B[M - 2:] == 0).all()        # rows beyond the device-side count are untouched
+    # rebuild the first activation from the factors on the host: out0[n,k,l] = relu(A[k,(l-n) mod 20] - B[k,l])
+    n = torch.arange(18, device=dev).view(18, 1, 1)
+    l = torch.arange(18, device=dev).view(1, 1, 18)
+    sh = ((l - n) % 20).expand(18, 3, 18)
+    kk = torch.arange(3, device=dev).view(1, 3, 1).expand(18, 3, 18)
+    re0 = torch.relu(A[:, :, kk, sh] - B[:, :, kk, l.expand(18, 3, 18)]).reshape(M, 32, 972)
+    ref0 = a0.cpu().numpy()[: M - 2]
+    assert np.abs(re0.cpu().numpy()[: M - 2] - ref0).max() < 2e-5 * max(1.0, np.abs(ref0).max())
+    b1 = torch.zeros((M, 64, 256), device=dev)
+    ops.conv_layer_tc(ops.GEOM_COSTAB, None, L1["w_tc"], L1["b"], b1, M, 32, 64, 18, 3, 18, 3, 3, 3, True, d_n=dM, equi_s=A, equi_t=B)
+    assert (b1[M - 2:] == 0).all()
+    assert relerr(b1.cpu().numpy(), a1.cpu().numpy()) < 2e-5
+    model.cpu()
+
+
 # ------------------------------------------------------------------------------ graphs / async pairs
 def test_cuda_graph_replay_and_async_pairs_match_eager(dev, oracle, c1):
     """Captured-graph replays on two slot streams (pairs in flight) return exactly the eager results."""
