@@ -209,7 +209,7 @@ int launch_conv(const ConvParams &p, int max_n, cudaStream_t st) {
 constexpr int POOL_T = 160;
 
 __global__ void __launch_bounds__(POOL_T)
-pool_desc_kernel(const float *__restrict__ x, int K, int C, int S, const float *__restrict__ w1,
+pool_desc_kernel(const float *__restrict__ x, int K, int C, int S, int channels_last, const float *__restrict__ w1,
                  const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
                  float *__restrict__ desc, float *__restrict__ equi) {
     __shared__ float sw1[32 * 16], sb1[16], sw2[16], sb2;
@@ -228,9 +228,19 @@ pool_desc_kernel(const float *__restrict__ x, int K, int C, int S, const float *
 #pragma unroll
         for (int j = 0; j < 16; ++j) h[j] = sb1[j];
         float nrm = 0.0f;
+        if (channels_last) {   // x: [K][32/4][S][4] (tensor-core conv output, channel-blocked)
+            const float4 *x4 = reinterpret_cast<const float4 *>(xp) + tid;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 v = __ldg(x4 + (size_t)q * S);
+                xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) xv[c] = xp[(size_t)c * S + tid];
+        }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-            xv[c] = xp[(size_t)c * S + tid];
             nrm = fmaf(xv[c], xv[c], nrm);
 #pragma unroll
             for (int j = 0; j < 16; ++j) h[j] = fmaf(xv[c], sw1[c * 16 + j], h[j]);
@@ -388,12 +398,13 @@ BX_API int bx_conv_layer(int geom, const float *in, const float *w, const float 
     }
 }
 
-BX_API int bx_pool_desc(const float *x, int K, int C, int S, const float *w1, const float *b1, const float *w2,
-                        const float *b2, float *desc, float *equi, void *stream) {
+BX_API int bx_pool_desc(const float *x, int K, int C, int S, int channels_last, const float *w1, const float *b1,
+                        const float *w2, const float *b2, float *desc, float *equi, void *stream) {
     BX_REQUIRE(x && w1 && b1 && w2 && b2 && desc && equi, "bx_pool_desc: null pointer");
     BX_REQUIRE(C == 32 && S >= 1 && S <= POOL_T && K >= 0, "bx_pool_desc: expects C=32, S<=%d", POOL_T);
     if (K == 0) return BX_OK;
-    pool_desc_kernel<<<K, POOL_T, 0, bx_stream(stream)>>>(x, K, C, S, w1, b1, w2, b2, desc, equi);
+    BX_REQUIRE(!channels_last || (reinterpret_cast<uintptr_t>(x) & 15) == 0, "bx_pool_desc: x must be 16-byte aligned");
+    pool_desc_kernel<<<K, POOL_T, 0, bx_stream(stream)>>>(x, K, C, S, channels_last ? 1 : 0, w1, b1, w2, b2, desc, equi);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

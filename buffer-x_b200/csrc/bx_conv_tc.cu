@@ -46,8 +46,6 @@ struct ConvTcParams {
     const int *s_mids, *t_mids;
 };
 
-constexpr int TC_LOADERS = 512;
-constexpr int TC_THREADS = TC_LOADERS + 32;
 constexpr int TC_BM = 128;
 constexpr int TC_STAGES = 4;
 constexpr int TC_MAX_TAPS = 128;
@@ -165,15 +163,23 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CW]) {
     }
 }
 
-template <int GEOM, int NT>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcParams p) {
+// LG = loader groups of 4 warps (group g fills the stages it = g, g+LG, ...); NSETS = main accumulators (2 = ping-pong,
+// 1 = the tensor core waits for the drain).  Wide layers (NT = 128) run LG = 4, NSETS = 2, one CTA per SM (384 of the 512
+// TMEM columns).  Narrow layers (NT <= 64) are dominated by per-tile latencies (pipeline fill, drains, epilogue), not
+// by tensor time, so they run LG = 2 (288 threads) with at most 256 TMEM columns: TWO CTAs per SM overlap one tile's
+// prologue / drain bubbles / epilogue with the other tile's MMAs.
+template <int GEOM, int NT, int LG, int NSETS>
+__global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel(const ConvTcParams p) {
+    constexpr int TC_LOADERS = LG * 128;
+    constexpr int MMA_WARP = LG * 4;
     constexpr int B_STAGE_BYTES = 2 * 2 * 2 * NT * 16;  // [kstep][split][kunit][n][16B]
     constexpr int STAGE_BYTES = B_STAGE_BYTES;      // shared memory holds only the weights; A lives in tensor memory
-    constexpr int A_RING = 3 * NT;                  // TMEM columns: main[0], main[1], cross, then the A ring
+    constexpr int A_RING = (NSETS + 1) * NT;        // TMEM columns: main[0..NSETS), cross, then the A ring
     constexpr int TMEM_NEED = A_RING + TC_STAGES * A_STAGE_COLS;
     constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
-    constexpr int CW = NT / 4;          // accumulator columns owned by one loader warp
-    // barriers: full[ST] (16 loader-warp arrivals + 1 expect_tx arrival), empty[ST], segdone[2], accfree[2]
+    static_assert(LG == 4 || TMEM_NEED <= 256, "two CTAs per SM need <= 256 TMEM columns each");
+    constexpr int CW = NT / LG;         // accumulator columns owned by one loader warp
+    // barriers: full[ST] (4 loader-warp arrivals + 1 expect_tx arrival), empty[ST], segdone[2], accfree[2]
     constexpr int BAR_EMPTY = TC_STAGES, BAR_SEGDONE = 2 * TC_STAGES, BAR_ACCFREE = 2 * TC_STAGES + 2;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 4];
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     const int G = p.seg_len;
     const int nseg = (n_iters + G - 1) / G;
 
-    if (warp == 16) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -214,13 +220,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_s;
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_base = smem_u32(&bars[0]);
+    uint32_t tmem_base = tmem_base_s;
+    uint32_t smem_base = smem_u32(smem);
+    uint32_t bar_base = smem_u32(&bars[0]);
+    // opaque to the compiler: keep the three bases in registers instead of re-deriving the shared-window address
+    // (S2R SR_CgaCtaId + LEA chains) in front of every barrier operation of the loader loop
+    asm volatile("" : "+r"(tmem_base), "+r"(smem_base), "+r"(bar_base));
 
-    if (warp < 16) {
+    if (warp < MMA_WARP) {
         // =========================== loaders ===========================================================
-        const int row = tid & 127, grp = tid >> 7;       // grp: which stages (it % 4 == grp) this thread fills
+        const int row = tid & 127, grp = tid >> 7;       // grp: which stages (it % LG == grp) this thread fills
         const long long lm = row0 + row;
         const bool lvalid = lm < Mtotal;
         int ln = 0, oz = 0, oy = 0, ox = 0;
@@ -247,14 +256,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             pa = p.equi_s + (size_t)ln * 32 * 60;     // A [32][3][20]
             pb = p.equi_t + (size_t)ln * 32 * 54;     // B [32][3][18]
         } else {
-            pa = p.in + (size_t)ln * p.Cin * p.S_in;
+            pa = p.in + (size_t)ln * p.S_in * p.Cin;      // activations are channel-blocked: [n][Cin/4][position][4]
         }
-        const int cstride = (GEOM == BX_GEOM_CYL2D || GEOM == BX_GEOM_COSTVOL) ? 140
-                            : (GEOM == BX_GEOM_CYL3D ? 420 : (GEOM == BX_GEOM_COSTAB ? 60 : p.S_in));
+        constexpr int cstride = (GEOM == BX_GEOM_COSTVOL) ? 140 : 60;   // channel-first factor maps of the two cost-volume loaders
         // (chunk, tap) of the stage this group fills next; the tap geometry comes from the shared table
         int chunk = grp / p.T, t = grp - chunk * p.T;
-        auto advance4 = [&]() {
-            t += 4;
+        auto advance_lg = [&]() {
+            t += LG;
             while (t >= p.T) { t -= p.T; ++chunk; }
         };
         const int oy20 = oy * 20;
@@ -287,16 +295,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 offB = kk * 18 + ll;
             }
             const int c0 = chunk * 16;
-            const float *src = pa + (size_t)c0 * cstride + offA;
+            if (GEOM == BX_GEOM_COSTVOL || GEOM == BX_GEOM_COSTAB) {
+                const float *src = pa + (size_t)c0 * cstride + offA;
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) {
-                float v = 0.0f;
-                if (ok) {
-                    if (GEOM == BX_GEOM_COSTVOL) v = src[kk * cstride] - pb[(size_t)(c0 + kk) * 140 + offB];
-                    else if (GEOM == BX_GEOM_COSTAB) v = fmaxf(__ldg(src + kk * cstride) - __ldg(pb + (c0 + kk) * 54 + offB), 0.0f);
-                    else v = __ldg(src + kk * cstride);
+                for (int kk = 0; kk < 16; ++kk) {
+                    float v = 0.0f;
+                    if (ok) {
+                        if (GEOM == BX_GEOM_COSTVOL) v = src[kk * cstride] - pb[(size_t)(c0 + kk) * 140 + offB];
+                        else v = fmaxf(__ldg(src + kk * cstride) - __ldg(pb + (c0 + kk) * 54 + offB), 0.0f);
+                    }
+                    a_reg[kk] = v;
                 }
-                a_reg[kk] = v;
+            } else {  // four 16-byte loads, one per group of 4 channels; a warp's 32 rows read 512 contiguous bytes each
+                const float4 *src = reinterpret_cast<const float4 *>(pa) + (size_t)(chunk * 4) * p.S_in + offA;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (ok) v = __ldg(src + (size_t)q * p.S_in);
+                    a_reg[4 * q] = v.x; a_reg[4 * q + 1] = v.y; a_reg[4 * q + 2] = v.z; a_reg[4 * q + 3] = v.w;
+                }
             }
         };
         const uint32_t a_lane = (uint32_t)((warp & 3) * 32) << 16;   // this warp's TMEM lanes = its 32 GEMM rows
@@ -324,8 +341,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
 #pragma unroll
         for (int j = 0; j < CW; ++j) run[j] = 0.0f;
         auto drain = [&](int j, bool release) {       // add finished segment j (main set j&1) into the running sums
-            const int set = j & 1;
-            mbar_wait(bar_base + 8u * (BAR_SEGDONE + set), (uint32_t)((j >> 1) & 1));
+            const int set = j % NSETS;
+            mbar_wait(bar_base + 8u * (BAR_SEGDONE + set), (uint32_t)((j / NSETS) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t v[CW];
             tmem_ld<CW>(tmem_base + tm_lane + (uint32_t)(set * NT + ecs * CW), v);
@@ -341,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
 
         if (grp < n_iters) load_stage();
         int next_drain = 0;
-        for (int it = grp; it < n_iters; it += 4) {
+        for (int it = grp; it < n_iters; it += LG) {
             if (next_drain < nseg - 1 && it >= (next_drain + 1) * G + (G < TC_STAGES ? G : TC_STAGES)) {
                 drain(next_drain, true);                  // its MMAs are several stages behind us: short wait
                 ++next_drain;
@@ -355,8 +372,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
                          reinterpret_cast<const unsigned char *>(p.w) + (size_t)it * B_STAGE_BYTES, (uint32_t)B_STAGE_BYTES, bar_base + 8u * s);
             }
             store_stage(s);
-            if (it + 4 < n_iters) {                       // this group's next stage: activations in flight
-                advance4();
+            if (it + LG < n_iters) {                      // this group's next stage: activations in flight
+                advance_lg();
                 load_stage();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // tcgen05.st ordered before the arrive
@@ -364,32 +381,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * s);
         }
         while (next_drain < nseg) {                      // a set must still be released if a later segment reuses it
-            drain(next_drain, next_drain + 2 < nseg);
+            drain(next_drain, next_drain + NSETS < nseg);
             ++next_drain;
         }
         // ---- epilogue: running sums + cross accumulator + bias (+ReLU) ------------------------------------
         {
             uint32_t u[CW];
-            tmem_ld<CW>(tmem_base + tm_lane + (uint32_t)(2 * NT + ecs * CW), u);
+            tmem_ld<CW>(tmem_base + tm_lane + (uint32_t)(NSETS * NT + ecs * CW), u);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const long long em = row0 + eq * 32 + (tid & 31);
             if (em < Mtotal) {
                 const int en = (int)(em / p.S_out);
                 const int epos = (int)(em - (long long)en * p.S_out);
-                float *eo = p.out + (size_t)en * p.Cout * p.S_out + epos;
+                // channel-blocked output [n][Cout/4][position][4]: one 16-byte store per group of 4 channels, coalesced
+                // across the warp's 32 consecutive rows
+                float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)en * (p.Cout >> 2) + ((ecs * CW) >> 2)) * p.S_out + epos;
 #pragma unroll
-                for (int c = 0; c < CW; ++c) {
+                for (int c = 0; c < CW; c += 4) {
                     const int co = ecs * CW + c;
                     if (co < p.Cout) {
-                        float r = (run[c] + __uint_as_float(u[c])) + __ldg(p.bias + co);
-                        if (p.relu) r = fmaxf(r, 0.0f);
-                        eo[(size_t)co * p.S_out] = r;
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + co));
+                        float4 r;
+                        r.x = (run[c] + __uint_as_float(u[c])) + b4.x;
+                        r.y = (run[c + 1] + __uint_as_float(u[c + 1])) + b4.y;
+                        r.z = (run[c + 2] + __uint_as_float(u[c + 2])) + b4.z;
+                        r.w = (run[c + 3] + __uint_as_float(u[c + 3])) + b4.w;
+                        if (p.relu) { r.x = fmaxf(r.x, 0.0f); r.y = fmaxf(r.y, 0.0f); r.z = fmaxf(r.z, 0.0f); r.w = fmaxf(r.w, 0.0f); }
+                        eo[(size_t)(c >> 2) * p.S_out] = r;
                     }
                 }
             }
         }
     } else {
-        // =========================== MMA issuer (warp 16) ==============================================
+        // =========================== MMA issuer (last warp) ============================================
         // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NT, M = 128
         constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
@@ -397,18 +421,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
         constexpr uint32_t B_IMG = (2u * NT * 16) >> 4;                         // one (kstep, split) image of B, in 16-byte units
         const uint32_t leader = elect_leader();
         const uint32_t b0 = (smem_base >> 4) | B_LBO;                            // stage 0, kstep 0, hi
-        const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT);
+        const uint32_t d_cross = tmem_base + (uint32_t)(NSETS * NT);
         int s = 0, seg = 0, in_seg = 0;
         uint32_t use = 0;
         for (int it = 0; it < n_iters; ++it) {
-            if (in_seg == 0 && seg >= 2) {
-                // segment `seg` reuses main set seg&1: segment seg-2 must have been drained
-                mbar_wait(bar_base + 8u * (BAR_ACCFREE + (seg & 1)), (uint32_t)(((seg - 2) >> 1) & 1));
+            if (in_seg == 0 && seg >= NSETS) {
+                // segment `seg` reuses main set seg % NSETS: segment seg-NSETS must have been drained
+                mbar_wait(bar_base + 8u * (BAR_ACCFREE + (seg % NSETS)), (uint32_t)(((seg - NSETS) / NSETS) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             mbar_wait(bar_base + 8u * s, use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t so = (uint32_t)s * (uint32_t)(STAGE_BYTES >> 4);
-            const uint32_t d_main = tmem_base + (uint32_t)((seg & 1) * NT);
+            const uint32_t d_main = tmem_base + (uint32_t)((seg % NSETS) * NT);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const uint32_t ah = tmem_base + (uint32_t)(A_RING + s * A_STAGE_COLS + ks * 16), al = ah + 8;
@@ -420,7 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
             mma_commit(leader, bar_base + 8u * (BAR_EMPTY + s));   // slot s may be refilled once these MMAs have read it
             if (++s == TC_STAGES) { s = 0; ++use; }
             if (++in_seg == G || it == n_iters - 1) {
-                mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + (seg & 1)));
+                mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + (seg % NSETS)));
                 in_seg = 0;
                 ++seg;
             }
@@ -429,12 +454,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcPara
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 16) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
-template <int GEOM, int NT>
+template <int GEOM, int NT, int LG, int NSETS>
 int launch_tc(const ConvTcParams &p, int max_n, cudaStream_t st) {
     const long long maxM = (long long)max_n * p.S_out;
     const unsigned gx = (unsigned)((maxM + TC_BM - 1) / TC_BM);
@@ -442,19 +467,29 @@ int launch_tc(const ConvTcParams &p, int max_n, cudaStream_t st) {
     constexpr int smem = TC_STAGES * (2 * 2 * 2 * NT * 16);
     static bool attr_done = false;
     if (!attr_done) {
-        BX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<GEOM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<GEOM, NT, LG, NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    conv_tc_kernel<GEOM, NT><<<gx, TC_THREADS, smem, st>>>(p);
+    conv_tc_kernel<GEOM, NT, LG, NSETS><<<gx, LG * 128 + 32, smem, st>>>(p);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }
 
+int g_tc_wide_only = -1;   // -1: read BX_TC_WIDE once (debug / A-B switch: 1 = every layer on the one-CTA-per-SM configuration)
+
 template <int GEOM>
 int dispatch_nt(const ConvTcParams &p, int max_n, cudaStream_t st) {
-    if (p.Cout > 64) return launch_tc<GEOM, 128>(p, max_n, st);
-    if (p.Cout > 32) return launch_tc<GEOM, 64>(p, max_n, st);
-    return launch_tc<GEOM, 32>(p, max_n, st);
+    if (g_tc_wide_only < 0) {
+        const char *e = getenv("BX_TC_WIDE");
+        g_tc_wide_only = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (p.Cout > 64) return launch_tc<GEOM, 128, 4, 2>(p, max_n, st);
+    if (g_tc_wide_only) {
+        if (p.Cout > 32) return launch_tc<GEOM, 64, 4, 2>(p, max_n, st);
+        return launch_tc<GEOM, 32, 4, 2>(p, max_n, st);
+    }
+    if (p.Cout > 32) return launch_tc<GEOM, 64, 2, 1>(p, max_n, st);
+    return launch_tc<GEOM, 32, 2, 2>(p, max_n, st);
 }
 
 }  // namespace
@@ -475,8 +510,10 @@ BX_API int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const 
                             const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
                             void *stream) {
     BX_REQUIRE(w_tc && bias && out, "bx_conv_layer_tc: null pointer");
-    BX_REQUIRE(n >= 0 && Cin >= 16 && Cin % 16 == 0 && Cout >= 1 && Cout <= 128, "bx_conv_layer_tc: bad channels Cin=%d Cout=%d", Cin, Cout);
+    BX_REQUIRE(n >= 0 && Cin >= 16 && Cin % 16 == 0 && Cout >= 4 && Cout % 4 == 0 && Cout <= 128, "bx_conv_layer_tc: bad channels Cin=%d Cout=%d", Cin, Cout);
     BX_REQUIRE((reinterpret_cast<uintptr_t>(w_tc) & 15) == 0, "bx_conv_layer_tc: weights must be 16-byte aligned");
+    BX_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
+               "bx_conv_layer_tc: activations and bias must be 16-byte aligned");
     BX_REQUIRE(kd >= 1 && kh >= 1 && kw >= 1 && (long long)kd * kh * kw <= TC_MAX_TAPS, "bx_conv_layer_tc: at most %d kernel taps", TC_MAX_TAPS);
     ConvTcParams p = {};
     p.in = in; p.w = w_tc; p.bias = bias; p.out = out; p.n = n; p.d_n = d_n;

@@ -4,7 +4,7 @@
 // sphere_query + var_to_invar (/root/reference/utils/common.py:422-498) and the 1x1 conv + BN + ReLU +
 // max over the 10 samples (patch_embedder.py:26-30, 73-77).  The reference writes [K,420,10] indices,
 // [K,420,10,3] points (75.6 MB at K=1500) and [K,16,420,10] activations (403 MB) to HBM per call; here
-// one CTA owns a patch and only the [16,V] feature tile leaves the SM (26.9 KB/patch).
+// one CTA owns a patch and only the [4,V,4] feature tile (channel-blocked) leaves the SM (26.9 KB/patch).
 //
 // The selection "first nv points, in index order, inside each voxel ball" is evaluated point-major instead of
 // voxel-major (420 x 512 = 215 K distance tests per patch in the reference's ball query):
@@ -153,10 +153,11 @@ spt_pnt_kernel(const float *__restrict__ delta, int K, int P, const float *__res
         }
     }
     __syncthreads();
-    // ---- 4. features: thread per (channel, voxel), voxel fastest -> coalesced stores ----------------------
+    // ---- 4. features in the channel-blocked layout [K][16/4][V][4] the tensor-core convolution reads; thread t writes
+    //         element t of the tile (coalesced): t = (cg * V + v) * 4 + c4 ------------------------------------------
     float *out = feat + (size_t)k * 16 * V;
     for (int t = tid; t < 16 * V; t += SPT_THREADS) {
-        const int ch = t / V, v = t - ch * V;
+        const int cg = t / (4 * V), r4 = t - cg * 4 * V, v = r4 >> 2, ch = cg * 4 + (r4 & 3);
         const float w0 = sw[3 * ch], w1 = sw[3 * ch + 1], w2 = sw[3 * ch + 2], bb = sw[48 + ch];
         const int c = scnt[v];
         const int first = c > 0 ? sel[(size_t)v * MAX_NV] : 0;

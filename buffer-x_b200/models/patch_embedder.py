@@ -98,13 +98,18 @@ class MiniSpinNet(nn.Module):
         delta, R, rand_axis = ops.lrf(patches, des_r, bool(is_aligned_to_global_z))
         res = ops.spt_pnt(delta, prep["voxels"], prep["rot"], self.delta / self.rad_n, self.voxel_sample, prep["w_pnt"],
                           prep["b_pnt"], self.azi_n, debug=debug)
-        feat = res[0] if debug else res
+        feat = res[0] if debug else res                                  # [K,4,V,4] channel-blocked
         K = kpts.shape[0]
-        x, _ = self.conv_net(feat.view(K, 16, self.rad_n, self.ele_n, self.azi_n))
-        desc, equi = ops.pool_desc(x, prep["w1"], prep["b1"], prep["w2"], prep["b2"])
+        if pn.USE_FFMA:   # CUDA-core debug path works channel-first
+            x, _ = self.conv_net(ops.from_blocked(feat).view(K, 16, self.rad_n, self.ele_n, self.azi_n))
+            desc, equi = ops.pool_desc(x, prep["w1"], prep["b1"], prep["w2"], prep["b2"])
+        else:
+            x, _ = self.conv_net(feat)                                   # [K,8,140,4] channel-blocked
+            desc, equi = ops.pool_desc(x, prep["w1"], prep["b1"], prep["w2"], prep["b2"], channels_last=True)
         out = {"desc": desc, "equi": equi, "rand_axis": rand_axis, "R": R, "patches": delta, "aug_rotation": None}
         if debug:
-            out.update(idx=idx, raw_patches=patches, vidx=res[1], inv=res[2], feat=feat, x=x)
+            x_cf = x if pn.USE_FFMA else ops.from_blocked(x).view(K, -1, self.ele_n, self.azi_n)
+            out.update(idx=idx, raw_patches=patches, vidx=res[1], inv=res[2], feat=ops.from_blocked(feat), x=x_cf)
         return out
 
     def get_parameter(self):

@@ -101,20 +101,21 @@ class Cylindrical_Net(_ConvStack):
         self.out_dim = dim
 
     def forward(self, x):
-        """x: [K,16,3,7,20] CUDA f32 -> (x_out [K,32,7,20], None)."""
+        """Tensor-core path (default): x [K,4,420,4] channel-blocked -> x_out [K,8,140,4] channel-blocked.
+        CUDA-core debug path (BX_CONV=ffma): x [K,16,3,7,20] -> [K,32,7,20].  Returns (x_out, None)."""
         K = x.shape[0]
         dev = x.device
         L = self.folded()
         cur = x.contiguous()
         for i, l in enumerate(L):
-            out = torch.empty((K, l["cout"], 140), dtype=torch.float32, device=dev)
+            out = torch.empty((K, l["cout"], 140) if USE_FFMA else (K, l["cout"] // 4, 140, 4), dtype=torch.float32, device=dev)
             conv, w = (ops.conv_layer, l["w"]) if USE_FFMA else (ops.conv_layer_tc, l["w_tc"])
             if i == 0:
                 conv(ops.GEOM_CYL3D, cur, w, l["b"], out, K, l["cin"], l["cout"], 3, 7, 20, 3, 3, 3, l["relu"])
             else:
                 conv(ops.GEOM_CYL2D, cur, w, l["b"], out, K, l["cin"], l["cout"], 1, 7, 20, 1, 3, 3, l["relu"])
             cur = out
-        return cur.view(K, L[-1]["cout"], 7, 20), None
+        return (cur.view(K, L[-1]["cout"], 7, 20) if USE_FFMA else cur), None
 
 
 class CostNet(_ConvStack):
@@ -147,7 +148,8 @@ class CostNet(_ConvStack):
                 fa, fb = ops.costvol_ab(equi_s, equi_t, s_mids, t_mids, d_M, maxM, l["wa"], l["wb"], l["b"])
                 D, H, W = OD, OH, OW
                 continue
-            out = torch.empty((maxM, l["cout"], OD * OH * OW), dtype=torch.float32, device=dev)
+            # tensor-core layers exchange channel-blocked activations [maxM, C/4, positions, 4]
+            out = torch.empty((maxM, l["cout"], OD * OH * OW) if USE_FFMA else (maxM, l["cout"] // 4, OD * OH * OW, 4), dtype=torch.float32, device=dev)
             if factored and i == 1:
                 conv(ops.GEOM_COSTAB, None, w, l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"],
                      d_n=d_M, equi_s=fa, equi_t=fb)
@@ -157,4 +159,4 @@ class CostNet(_ConvStack):
             else:
                 conv(ops.GEOM_VALID3D, cur, w, l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"], d_n=d_M)
             cur, D, H, W = out, OD, OH, OW
-        return cur.view(maxM, L[-1]["cout"])
+        return cur.view(maxM, L[-1]["cout"])      # one output position: blocked [maxM, C/4, 1, 4] == [maxM, C]

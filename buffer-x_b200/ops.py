@@ -64,7 +64,7 @@ def load_library():
     lib.bx_conv_layer_tc.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_tc_ntile.argtypes = [c_int]
     lib.bx_costvol_ab.argtypes = [P, P, P, P, P, c_int, P, P, P, P, P, P]
-    lib.bx_pool_desc.argtypes = [P, c_int, c_int, c_int, P, P, P, P, P, P, P]
+    lib.bx_pool_desc.argtypes = [P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_mutual_nn.argtypes = [P, c_int, P, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_hypotheses.argtypes = [P, c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P]
     lib.bx_consensus.argtypes = [P, P, P, P, P, c_int, c_int, c_float, P, P, P, P, P]
@@ -240,7 +240,7 @@ def spt_pnt(delta, voxels, rot, voxel_r: float, nv: int, w, b, azi_n: int, debug
     V = voxels.shape[0]
     dev = delta.device
     if feat is None:
-        feat = torch.empty((K, 16, V), dtype=F32, device=dev)
+        feat = torch.empty((K, 4, V, 4), dtype=F32, device=dev)    # channel-blocked (see to_blocked)
     vidx = torch.empty((K, V, nv), dtype=I32, device=dev) if debug else None
     inv = torch.empty((K, V, nv, 3), dtype=F32, device=dev) if debug else None
     with _Span("spt", 12.0 * K * P + 64.0 * K * V):
@@ -291,8 +291,21 @@ def conv_tc_weights(Wt: torch.Tensor) -> torch.Tensor:
     return img.view(-1)
 
 
+def to_blocked(x: torch.Tensor) -> torch.Tensor:
+    """[n, C, S...] channel-first -> [n, C/4, S, 4] channel-blocked (activation layout of bx_conv_layer_tc)."""
+    n, C = x.shape[0], x.shape[1]
+    return x.reshape(n, C // 4, 4, -1).permute(0, 1, 3, 2).contiguous()
+
+
+def from_blocked(x: torch.Tensor) -> torch.Tensor:
+    """[n, C/4, S, 4] channel-blocked -> [n, C, S] channel-first."""
+    n, G, S, _ = x.shape
+    return x.permute(0, 1, 3, 2).reshape(n, G * 4, S).contiguous()
+
+
 def conv_layer_tc(geom, x, w_tc, bias, out, n, Cin, Cout, D, H, W, kd, kh, kw, relu, d_n=None, equi_s=None, equi_t=None,
                   s_mids=None, t_mids=None):
+    """x / out are channel-blocked: [n, Cin/4, S_in, 4] / [n, Cout/4, S_out, 4]."""
     ev = None
     if profiler is not None and d_n is None:
         OD, OH, OW = (1, 7, 20) if geom in (GEOM_CYL3D, GEOM_CYL2D) else (D - kd + 1, H - kh + 1, W - kw + 1)
@@ -335,16 +348,17 @@ def costvol_ab(equi_s, equi_t, s_mids, t_mids, d_M, maxM, wa, wb, bias, A=None, 
     return A, B
 
 
-def pool_desc(x, w1, b1, w2, b2, desc=None, equi=None):
-    K, C = x.shape[0], x.shape[1]
+def pool_desc(x, w1, b1, w2, b2, desc=None, equi=None, channels_last=False):
+    """x: [K,32,7,20] (channel-first) or channel-blocked [K,8,140,4] with channels_last=True.  equi is always [K,32,7,20]."""
+    K, C = x.shape[0], 32
     S = x.numel() // max(K * C, 1) if K > 0 else 140
     dev = x.device
     if desc is None:
         desc = torch.empty((K, C), dtype=F32, device=dev)
     if equi is None:
-        equi = torch.empty_like(x)
-    _check(load_library().bx_pool_desc(_dp(x, F32, "x"), K, C, S, _dp(w1, F32), _dp(b1, F32), _dp(w2, F32), _dp(b2, F32), _dp(desc), _dp(equi), _stream()),
-           "bx_pool_desc")
+        equi = torch.empty((K, C, 7, 20) if S == 140 else (K, C, S), dtype=F32, device=dev)
+    _check(load_library().bx_pool_desc(_dp(x, F32, "x"), K, C, S, int(bool(channels_last)), _dp(w1, F32), _dp(b1, F32), _dp(w2, F32), _dp(b2, F32),
+                                       _dp(desc), _dp(equi), _stream()), "bx_pool_desc")
     return desc, equi
 
 

@@ -91,7 +91,8 @@ int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r
  * sphere_query, var_to_invar of utils/common.py:422-498) fused with pnt_layer + max-pool
  * (patch_embedder.py:26-30, 73-77); the [K,420,10,3] tensor is never written.
  * voxels: [V,3] (V = rad_n*ele_n*azi_n, azimuth fastest); rot: [azi_n,2] (cos,sin of -a*2pi/azi_n);
- * w: [16,3], b: [16] = 1x1 conv with BatchNorm folded in.  feat: [K,16,V].
+ * w: [16,3], b: [16] = 1x1 conv with BatchNorm folded in.  feat: [K,4,V,4] (channel-blocked, the layout
+ * bx_conv_layer_tc reads: element (c, v) at ((c/4)*V + v)*4 + c%4).
  * dbg_vidx [K,V,nv] / dbg_inv [K,V,nv,3] are optional parity taps (NULL in production). */
 int bx_spt_pnt(const float *delta, int K, int P, const float *voxels, int V, int azi_n, const float *rot,
                float voxel_r, int nv, const float *w, const float *b, float *feat, int32_t *dbg_vidx,
@@ -115,7 +116,9 @@ int bx_conv_layer(int geom, const float *in, const float *w, const float *bias, 
                   void *stream);
 
 /* Tensor-core variant (tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulators in TMEM; same geometry
- * arguments).  w_tc is the host-prepared operand image: for every stage it = chunk*T + tap (chunk = 16
+ * arguments).  Activations are CHANNEL-BLOCKED here: in [n][Cin/4][S_in][4], out [n][Cout/4][S_out][4] (a GEMM row
+ * fetches its 16 input channels with four 16-byte loads that coalesce across the warp's 32 consecutive rows; the
+ * epilogue stores the same way); Cout % 4 == 0; in, out, bias 16-byte aligned.  w_tc is the host-prepared operand image: for every stage it = chunk*T + tap (chunk = 16
  * input channels) the block [kstep(2)][split(2: hi,lo)][kunit(2)][n(NT)][4 floats], NT = bx_conv_tc_ntile(Cout),
  * rows n >= Cout zero, hi = round-to-nearest tf32 of the folded weight, lo = w - hi.  Cin % 16 == 0, Cout <= 128. */
 int bx_conv_tc_ntile(int Cout);
@@ -138,10 +141,10 @@ int bx_costvol_ab(const float *equi_s, const float *equi_t, const int32_t *s_mid
 
 /* ---- a9: attention pooling + normalisation --------------------------------------------------
  * Replaces pool_layer / avg-pool / F.normalize (models/patch_embedder.py:32-39, 80-83).
- * x: [K,32,S]; w1 [32,16] (in-major), b1 [16], w2 [16], b2 [1] (BatchNorm folded);
- * desc: [K,32]; equi: [K,32,S]. */
-int bx_pool_desc(const float *x, int K, int C, int S, const float *w1, const float *b1, const float *w2,
-                 const float *b2, float *desc, float *equi, void *stream);
+ * x: [K,32,S], or channel-blocked [K,8,S,4] when channels_last != 0 (the layout bx_conv_layer_tc writes); w1 [32,16] (in-major),
+ * b1 [16], w2 [16], b2 [1] (BatchNorm folded); desc: [K,32]; equi: [K,32,S] (always channel-first). */
+int bx_pool_desc(const float *x, int K, int C, int S, int channels_last, const float *w1, const float *b1,
+                 const float *w2, const float *b2, float *desc, float *equi, void *stream);
 
 /* ---- a10: mutual nearest-neighbour matching -------------------------------------------------
  * Replaces BufferX.mutual_matching (models/BUFFERX.py:469-496) -> knn_cuda.KNN(k=1) both ways.

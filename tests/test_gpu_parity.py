@@ -136,6 +136,8 @@ def test_spt_pnt(dev, oracle, c1):
     assert (inv.cpu().numpy() == einv).all()                         # de-rotated samples: bit-exact
     with torch.no_grad():
         efeat = oracle.pnt_max(torch.from_numpy(einv), c1["sd"]).numpy()
+    assert feat.shape == (delta.shape[0], 4, 420, 4)                 # channel-blocked, the layout bx_conv_layer_tc reads
+    feat = ops.from_blocked(feat)
     assert np.abs(feat.cpu().numpy() - efeat).max() < 2e-6 * max(1.0, np.abs(efeat).max())   # folded BN: fp32 rounding only
     model.cpu()
 
@@ -147,13 +149,25 @@ def test_cylindrical_net_and_pooling(dev, oracle, c1):
     s = aux["scales"][0]["src"]
     model = c1["model"].to(dev)
     K = s["feat"].shape[0]
-    x, _ = model.Desc.conv_net(cu(s["feat"].numpy(), dev).view(K, 16, 3, 7, 20))
+    from bufferx_b200.models import patchnet as pn
+    f = cu(s["feat"].numpy(), dev)                                   # oracle layout: [K,16,420]
     ex = s["x"].numpy()
-    assert relerr(x.cpu().numpy(), ex) < 1e-4                        # 8 stacked fp32 convs vs torch CPU
     prep = model.Desc.prepared(dev)
+    if pn.USE_FFMA:
+        x, _ = model.Desc.conv_net(f.view(K, 16, 3, 7, 20))
+        xcf = x
+    else:
+        x, _ = model.Desc.conv_net(ops.to_blocked(f))                # channel-blocked in / out: [K,8,140,4]
+        assert x.shape == (K, 8, 140, 4)
+        xcf = ops.from_blocked(x).reshape(K, 32, 7, 20)
+        d2, e2 = ops.pool_desc(ops.to_blocked(cu(ex, dev).reshape(K, 32, 140)), prep["w1"], prep["b1"], prep["w2"], prep["b2"],
+                               channels_last=True)
+    assert relerr(xcf.cpu().numpy(), ex) < 1e-4                      # 8 stacked fp32 convs vs torch CPU
     desc, equi = ops.pool_desc(cu(ex, dev), prep["w1"], prep["b1"], prep["w2"], prep["b2"])
     assert np.abs(desc.cpu().numpy() - s["desc"].numpy()).max() < 1e-5
     assert np.abs(equi.cpu().numpy() - s["equi"].numpy()).max() < 1e-5
+    if not pn.USE_FFMA:                                              # both input layouts of the pooling kernel agree bit for bit
+        assert (d2 == desc).all() and (e2 == equi).all()
     model.cpu()
 
 
@@ -462,8 +476,11 @@ def test_conv_layer_kernels(dev, geom, Cin, Cout, dims, k, n, impl):
     OD, OH, OW = (1, 7, 20) if geom != "valid3d" else (D - kd + 1, H - kh + 1, W_ - kw + 1)
     out = torch.full((n, Cout, OD * OH * OW), float("nan"), device=dev)
     xin = x.to(dev).reshape(n, Cin, -1).contiguous()
-    if impl == "tc":
-        ops.conv_layer_tc(G, xin, ops.conv_tc_weights(Wt.to(dev)), bf.to(dev), out, n, Cin, Cout, D, H, W_, kd, kh, kw, relu)
+    if impl == "tc":                                                  # tensor-core kernel: channel-blocked activations
+        out_cb = torch.full((n, Cout // 4, OD * OH * OW, 4), float("nan"), device=dev)
+        ops.conv_layer_tc(G, ops.to_blocked(xin), ops.conv_tc_weights(Wt.to(dev)), bf.to(dev), out_cb, n, Cin, Cout, D, H, W_,
+                          kd, kh, kw, relu)
+        out = ops.from_blocked(out_cb)
     else:
         ops.conv_layer(G, xin, Wt.to(dev), bf.to(dev), out, n, Cin, Cout, D, H, W_, kd, kh, kw, relu)
     got = out.cpu().numpy().reshape(ref.shape)
@@ -482,11 +499,11 @@ def test_cost_volume_first_layer_tc_vs_ffma(dev, oracle, c1):
     sm, tm = cu(sc["s_mids"], dev, torch.int32), cu(sc["t_mids"], dev, torch.int32)
     dM = torch.tensor([M - 3], dtype=torch.int32, device=dev)
     a = torch.zeros((M, 32, 972), device=dev)
-    b = torch.zeros((M, 32, 972), device=dev)
+    b = torch.zeros((M, 8, 972, 4), device=dev)                       # tensor-core kernel writes channel-blocked
     ops.conv_layer(ops.GEOM_COSTVOL, None, L["w"], L["b"], a, M, 32, 32, 20, 5, 20, 3, 3, 3, True, d_n=dM, equi_s=es, equi_t=et, s_mids=sm, t_mids=tm)
     ops.conv_layer_tc(ops.GEOM_COSTVOL, None, L["w_tc"], L["b"], b, M, 32, 32, 20, 5, 20, 3, 3, 3, True, d_n=dM, equi_s=es, equi_t=et, s_mids=sm, t_mids=tm)
     assert (b[M - 3:] == 0).all()                                     # rows beyond the device-side count are untouched
-    assert relerr(b.cpu().numpy(), a.cpu().numpy()) < 2e-5
+    assert relerr(ops.from_blocked(b).cpu().numpy(), a.cpu().numpy()) < 2e-5
     model.cpu()
 
 
@@ -518,10 +535,10 @@ def test_cost_volume_factorised_first_layer(dev, oracle, c1):
     re0 = torch.relu(A[:, :, kk, sh] - B[:, :, kk, l.expand(18, 3, 18)]).reshape(M, 32, 972)
     ref0 = a0.cpu().numpy()[: M - 2]
     assert np.abs(re0.cpu().numpy()[: M - 2] - ref0).max() < 2e-5 * max(1.0, np.abs(ref0).max())
-    b1 = torch.zeros((M, 64, 256), device=dev)
+    b1 = torch.zeros((M, 16, 256, 4), device=dev)                     # channel-blocked
     ops.conv_layer_tc(ops.GEOM_COSTAB, None, L1["w_tc"], L1["b"], b1, M, 32, 64, 18, 3, 18, 3, 3, 3, True, d_n=dM, equi_s=A, equi_t=B)
     assert (b1[M - 2:] == 0).all()
-    assert relerr(b1.cpu().numpy(), a1.cpu().numpy()) < 2e-5
+    assert relerr(ops.from_blocked(b1).cpu().numpy(), a1.cpu().numpy()) < 2e-5
     model.cpu()
 
 

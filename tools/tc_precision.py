@@ -20,9 +20,12 @@ def run(K, Cout, n, S, seg, relu_like=True, impl="tc"):
     ref = torch.einsum("ok,nks->nos", W.double(), x.double())
     Wt = W.t().contiguous()[None]                      # [T=1, Cin, Cout]
     out = torch.empty((n, Cout, S), device=dev)
-    if impl == "tc":
+    if impl == "tc":                                   # tensor-core kernel: channel-blocked activations
         lib.bx_conv_tc_set_segment_stages(seg)
-        ops.conv_layer_tc(ops.GEOM_VALID3D, x.to(dev), ops.conv_tc_weights(Wt.to(dev)), b.to(dev), out, n, K, Cout, 1, 1, S, 1, 1, 1, False)
+        out_cb = torch.empty((n, Cout // 4, S, 4), device=dev)
+        ops.conv_layer_tc(ops.GEOM_VALID3D, ops.to_blocked(x.to(dev)), ops.conv_tc_weights(Wt.to(dev)), b.to(dev), out_cb, n, K, Cout,
+                          1, 1, S, 1, 1, 1, False)
+        out = ops.from_blocked(out_cb)
     else:
         ops.conv_layer(ops.GEOM_VALID3D, x.to(dev), Wt.to(dev), b.to(dev), out, n, K, Cout, 1, 1, S, 1, 1, 1, False)
     err = (out.cpu().double() - ref)
