@@ -277,13 +277,33 @@ class BufferX(nn.Module):
         should_exit = False
         res_block = None
         inl = dI = None
+        # Without early exit every scale runs anyway: describe all 2*S (cloud, scale) key-point sets in one batched
+        # pass (one SPT / conv-stack / pooling launch sequence instead of 2*S).  The host permutation draws keep the
+        # reference's order (src then tgt, scale by scale).
+        batched = None
+        if not enable_early_exit and not debug:
+            desc_t.tic()
+            jobs = []
+            for i in range(S):
+                for pts_c, k_c, j in ((src, src_kpts, 0), (tgt, tgt_kpts, 1)):
+                    pm = None if perms is None else perms[i][j]
+                    if pm is None:
+                        pm = np.random.choice(pts_c.shape[0], pts_c.shape[0], replace=False)
+                    if not isinstance(pm, torch.Tensor):
+                        pm = torch.from_numpy(np.ascontiguousarray(pm, dtype=np.int32)).to(dev, non_blocking=True)
+                    jobs.append((pts_c, k_c, r_dev[i:i + 1], pm))
+            batched = self.Desc.forward_multi(jobs, aligned)
+            desc_t.toc()
         for i in range(S):
             desc_t.tic()
             des_r = r_dev[i:i + 1]
             ps = None if perms is None else perms[i][0]
             pt = None if perms is None else perms[i][1]
-            sd = self.Desc(src[None], src_kpts[None], des_r, aligned, perm=ps, debug=debug)
-            td = self.Desc(tgt[None], tgt_kpts[None], des_r, aligned, perm=pt, debug=debug)
+            if batched is not None:
+                sd, td = batched[2 * i], batched[2 * i + 1]
+            else:
+                sd = self.Desc(src[None], src_kpts[None], des_r, aligned, perm=ps, debug=debug)
+                td = self.Desc(tgt[None], tgt_kpts[None], des_r, aligned, perm=pt, debug=debug)
             s_mids, t_mids, dM, snn, tnn = ops.mutual_nn(sd["desc"], td["desc"], want_nn=debug)
             desc_t.toc()
 

@@ -112,5 +112,42 @@ class MiniSpinNet(nn.Module):
             out.update(idx=idx, raw_patches=patches, vidx=res[1], inv=res[2], feat=ops.from_blocked(feat), x=x_cf)
         return out
 
+    def forward_multi(self, jobs, is_aligned_to_global_z):
+        """Descriptors of several (cloud, key-points, radius, permutation) jobs in ONE pass through SPT, the
+        convolution stack and the pooling layer (all CTA-per-patch kernels: batching the 2 x num_scales calls of a
+        pair removes five of six launch tails and wave-quantisation losses).  Per-job results are views into the
+        batched buffers; same arithmetic as ``forward`` per patch.  jobs: list of (pts [N,3], kpts [K,3], des_r
+        1-element CUDA tensor, perm int32 [N])."""
+        dev = jobs[0][0].device
+        prep = self.prepared(dev)
+        P = self.patch_sample
+        Ks = [j[1].shape[0] for j in jobs]
+        Kt = sum(Ks)
+        patches = torch.empty((Kt, P, 3), dtype=torch.float32, device=dev)
+        delta = torch.empty_like(patches)
+        Rs, axes = [], []
+        o = 0
+        for (pts, kpts, des_r, perm), K in zip(jobs, Ks):
+            pts4 = ops.permute_cloud(pts.contiguous(), perm)
+            ops.select_patches(pts4, kpts.contiguous(), des_r, P, patches=patches[o:o + K])
+            _, R, ra = ops.lrf(patches[o:o + K], des_r, bool(is_aligned_to_global_z), delta=delta[o:o + K])
+            Rs.append(R)
+            axes.append(ra)
+            o += K
+        feat = ops.spt_pnt(delta, prep["voxels"], prep["rot"], self.delta / self.rad_n, self.voxel_sample, prep["w_pnt"],
+                           prep["b_pnt"], self.azi_n)
+        if pn.USE_FFMA:
+            x, _ = self.conv_net(ops.from_blocked(feat).view(Kt, 16, self.rad_n, self.ele_n, self.azi_n))
+            desc, equi = ops.pool_desc(x, prep["w1"], prep["b1"], prep["w2"], prep["b2"])
+        else:
+            x, _ = self.conv_net(feat)
+            desc, equi = ops.pool_desc(x, prep["w1"], prep["b1"], prep["w2"], prep["b2"], channels_last=True)
+        outs, o = [], 0
+        for K, R, ra in zip(Ks, Rs, axes):
+            outs.append({"desc": desc[o:o + K], "equi": equi[o:o + K], "rand_axis": ra, "R": R, "patches": delta[o:o + K],
+                         "aug_rotation": None})
+            o += K
+        return outs
+
     def get_parameter(self):
         return list(self.parameters())

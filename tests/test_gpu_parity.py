@@ -373,6 +373,35 @@ def test_pair_c1_three_scales_outdoor_flags(dev, oracle):
     _compare_pair(model.to(dev), sd, cfg, data, perms, oracle, "C1x3")
 
 
+def test_batched_descriptor_pass_equals_per_scale_pass(dev, oracle):
+    """Without early exit the production path describes all 2*S (cloud, scale) sets in one batched pass
+    (MiniSpinNet.forward_multi); the debug path runs them one by one.  Same kernels per patch -> identical results."""
+    import bufferx_b200 as bx
+    from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
+    cfg = workload_cfg("C2")
+    cfg.patch.num_fps, cfg.patch.num_points_radius_estimate, cfg.match.iter_n = 300, 400, 5000
+    assert cfg.match.get("enable_early_exit", True) is False
+    model = init_synthetic_weights(bx.BufferX(cfg), seed=11).to(dev)
+    data = make_pair("C1", 2)
+    perms = oracle.draw_perms(cfg, 5000, 5000, 2)
+    with torch.no_grad():
+        a = model(data, perms=perms, ransac_seed=3, debug=False)         # batched
+        b = model(data, perms=perms, ransac_seed=3, debug=True)          # per scale
+        jobs = []
+        dbg = model.last_debug
+        for i in range(cfg.patch.num_scales):
+            for j, key in ((0, "src_fds_pcd"), (1, "tgt_fds_pcd")):
+                jobs.append((cu(data[key], dev), dbg["kpts"][j, :cfg.patch.num_fps].contiguous(), dbg["des_r"][i:i + 1],
+                             cu(perms[i][j], dev, torch.int32)))
+        outs = model.Desc.forward_multi(jobs, bool(data["is_aligned_to_global_z"]))
+    assert np.array_equal(a[0], b[0]) and a[2:] == b[2:]                 # pose, inlier counts, scales used
+    for i, sc in enumerate(dbg["scales"]):
+        for j, side in ((0, "s"), (1, "t")):
+            o = outs[2 * i + j]
+            assert (o["desc"] == sc[side]["desc"]).all() and (o["equi"] == sc[side]["equi"]).all() and (o["R"] == sc[side]["R"]).all()
+    model.cpu()
+
+
 def test_forward_draws_host_permutations_like_the_reference(dev, oracle, c1):
     """Without explicit perms forward() must consume NumPy's global RNG exactly like the reference
     (one np.random.choice(N, N, replace=False) per Desc call, src then tgt, per scale)."""
