@@ -8,15 +8,19 @@
 //
 // The selection "first nv points, in index order, inside each voxel ball" is evaluated point-major instead of
 // voxel-major (420 x 512 = 215 K distance tests per patch in the reference's ball query):
-//   1. every non-zero point enumerates only the voxels that CAN contain it -- shells with ||p| - s_r| < rho,
-//      elevation rows with |p_z - c_z| < rho, azimuth bins within asin(rho / R_c) of the point's bin (all bins
-//      where the voxel ring is closer than rho to the axis) -- runs the EXACT test on those (~30-60 instead of
-//      420) and records hits in a per-voxel bitmap over the patch indices (atomicOr in shared memory);
+//   1. every non-zero point enumerates only the voxels that CAN contain it -- (shell, elevation) rows whose ring is
+//      closer than rho to the point in the (planar radius, z) half plane, azimuth bins within asin(rho / R_c) of the
+//      point's bin (all bins where the ring is closer than rho to the axis) -- runs the EXACT test on those (~50
+//      instead of 420) and records hits in a per-voxel bitmap over the patch indices (atomicOr in shared memory).
+//      The points are first counting-sorted by their nearest ring so that the 32 lanes of a warp need the same few
+//      rows: the row loop is warp-uniform, rows no lane needs are skipped, and the azimuth window of a row has the
+//      same length for every lane (no divergence);
 //   2. the exact-zero points (the key-point copies that pad a patch, up to 80 % of it at the finest scale) are
 //      one ballot mask that is OR-ed into every voxel whose ball contains the origin;
 //   3. a thread per voxel walks its bitmap words in index order and keeps the first nv set bits;
-//   4. a thread per (voxel, channel) de-rotates the selected points, applies the folded 3->16 affine map +
-//      ReLU and max-reduces; the store is coalesced along the voxel axis.
+//   4. a thread per (voxel, group of 4 channels) de-rotates the selected non-zero points once, applies the folded
+//      3->16 affine map + ReLU and max-reduces (exact-zero points contribute relu(b) like a zeroed slot); one
+//      coalesced 16-byte store in the channel-blocked layout.
 // The candidate enumeration is conservative (slack 1e-3 on the bands, +1 azimuth bin), membership itself is
 // the bit-exact test of oracle bxo_spt: d2 = ((qx-x)^2+(qy-y)^2)+(qz-z)^2 < r*r; slot 0 zeroed when its index
 // is 0 (utils/common.py:447-449), padding slots zeroed; x' = x*c + y*(-s), y' = x*s + y*c.  -fmad=false.
@@ -41,13 +45,17 @@ spt_pnt_kernel(const float *__restrict__ delta, int K, int P, const float *__res
     float *vx = pz + P;                                 // 3*V
     float *sw = vx + 3 * V;                             // 64 (w[16][3], b[16])
     float *srot = sw + 64;                              // 2*azi_n
-    float *re_s = srot + 2 * azi_n;                     // MAX_RE: |c| of the row
+    float *re_s = srot + 2 * azi_n;                     // MAX_RE: planar radius of the row's ring
     float *re_z = re_s + MAX_RE;                        // MAX_RE: c_z of the row
     int *re_h = reinterpret_cast<int *>(re_z + MAX_RE); // MAX_RE: azimuth half width (>= azi_n/2 means "all")
     unsigned *bitmap = reinterpret_cast<unsigned *>(re_h + MAX_RE);   // V*NW
     unsigned *zmask = bitmap + (size_t)V * NW;                         // NW
     unsigned short *sel = reinterpret_cast<unsigned short *>(zmask + NW);  // V*MAX_NV
-    unsigned char *scnt = reinterpret_cast<unsigned char *>(sel + (size_t)V * MAX_NV);  // V
+    unsigned short *order = sel + (size_t)V * MAX_NV;                  // P: non-zero point indices, ring-sorted
+    int *cell_cnt = reinterpret_cast<int *>(order + ((P + 1) & ~1));   // MAX_RE + 1
+    unsigned short *snz = reinterpret_cast<unsigned short *>(cell_cnt + MAX_RE + 1);   // V: slots holding a non-zero point
+    unsigned char *pkey = reinterpret_cast<unsigned char *>(snz + V);   // P: ring of a point, 0xFF = zero point
+    unsigned char *scnt = pkey + P;                                     // V
 
     const int k = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -67,13 +75,14 @@ spt_pnt_kernel(const float *__restrict__ delta, int K, int P, const float *__res
 
     const float r2 = voxel_r * voxel_r;
     const float slack = voxel_r + 1e-3f;
+    const float slack2 = slack * slack;
     const float step = 6.283185307179586f / (float)azi_n;
     // ---- per (shell, elevation) row: |c|, c_z, azimuth half width ------------------------------------
     if (tid < n_re) {
         const float cx = vx[3 * (tid * azi_n)], cy = vx[3 * (tid * azi_n) + 1], cz = vx[3 * (tid * azi_n) + 2];
-        re_s[tid] = sqrtf(cx * cx + cy * cy + cz * cz);
-        re_z[tid] = cz;
         const float Rc = sqrtf(cx * cx + cy * cy);
+        re_s[tid] = Rc;                                 // the ring of the row in the (planar radius, z) half plane
+        re_z[tid] = cz;
         int h = azi_n;  // all bins
         if (Rc > slack) h = (int)ceilf(asinf(fminf(1.0f, slack / Rc)) / step) + 1;
         re_h[tid] = h;
@@ -94,26 +103,69 @@ spt_pnt_kernel(const float *__restrict__ delta, int K, int P, const float *__res
     }
     __syncthreads();
     // ---- 2. non-zero points: exact test on their candidate voxels --------------------------------------
+    // 2a. counting sort of the points by their nearest (shell, elevation) ring in the (planar radius, z) half plane:
+    //     the 32 points of a warp then share the few rows that can contain them, and rows no lane needs are skipped
+    //     warp-wide.
+    if (tid < MAX_RE) cell_cnt[tid] = 0;
+    __syncthreads();
     for (int i = tid; i < P; i += SPT_THREADS) {
-        if ((zmask[i >> 5] >> (i & 31)) & 1u) continue;
+        unsigned char key = 0xFF;
+        if (!((zmask[i >> 5] >> (i & 31)) & 1u)) {
+            const float x = px[i], y = py[i], z = pz[i];
+            const float rp = sqrtf(x * x + y * y);
+            float best = 3.0e38f;
+            int kb = 0;
+            for (int re = 0; re < n_re; ++re) {
+                const float dr = rp - re_s[re], dz = z - re_z[re];
+                const float d = dr * dr + dz * dz;
+                if (d < best) { best = d; kb = re; }
+            }
+            key = (unsigned char)kb;
+            atomicAdd(&cell_cnt[kb], 1);
+        }
+        pkey[i] = key;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int re = 0; re < n_re; ++re) { const int c = cell_cnt[re]; cell_cnt[re] = acc; acc += c; }
+        cell_cnt[MAX_RE] = acc;   // number of non-zero points
+    }
+    __syncthreads();
+    for (int i = tid; i < P; i += SPT_THREADS) {
+        const unsigned char key = pkey[i];
+        if (key != 0xFF) order[atomicAdd(&cell_cnt[key], 1)] = (unsigned short)i;
+    }
+    __syncthreads();
+    // 2b. lane = point (ring-sorted); the row loop is warp-uniform and a row's azimuth window has the same length for
+    //     every lane, so there is no divergence inside it.
+    const int n_nz = cell_cnt[MAX_RE];
+    for (int base = (tid & ~31); base < n_nz; base += SPT_THREADS) {
+        const bool valid = base + lane < n_nz;
+        const int i = valid ? order[base + lane] : 0;
         const float x = px[i], y = py[i], z = pz[i];
-        const float rad = sqrtf(x * x + y * y + z * z);
+        const float rp = sqrtf(x * x + y * y);
         float al = atan2f(y, x);
         if (al < 0.0f) al += 6.283185307179586f;
         int ap = (int)floorf(al / step);
         ap = min(max(ap, 0), azi_n - 1);
         const unsigned bit = 1u << (i & 31);
-        const int wd = i >> 5;
+        unsigned *bm = bitmap + (i >> 5);
         for (int re = 0; re < n_re; ++re) {
-            if (fabsf(rad - re_s[re]) >= slack || fabsf(z - re_z[re]) >= slack) continue;
+            // a voxel centre of the row is at least the in-plane distance to the row's ring away from the point
+            const float dr = rp - re_s[re], dz = z - re_z[re];
+            const bool act = valid && (dr * dr + dz * dz) < slack2;
+            if (!__any_sync(BX_FULL, act)) continue;
             const int h = re_h[re];
-            const int lo = (2 * h + 1 >= azi_n) ? 0 : ap - h;
-            const int cnt = (2 * h + 1 >= azi_n) ? azi_n : 2 * h + 1;
+            const bool all = 2 * h + 1 >= azi_n;
+            const int cnt = all ? azi_n : 2 * h + 1;
+            int a = all ? 0 : ap - h;
+            a = a < 0 ? a + azi_n : a;
+            const int vb = re * azi_n;
             for (int j = 0; j < cnt; ++j) {
-                int a = lo + j;
-                a = a < 0 ? a + azi_n : (a >= azi_n ? a - azi_n : a);
-                const int v = re * azi_n + a;
-                if (bx_d2(vx[3 * v] - x, vx[3 * v + 1] - y, vx[3 * v + 2] - z) < r2) atomicOr(&bitmap[(size_t)v * NW + wd], bit);
+                const int v = vb + a;
+                if (act && bx_d2(vx[3 * v] - x, vx[3 * v + 1] - y, vx[3 * v + 2] - z) < r2) atomicOr(bm + (size_t)v * NW, bit);
+                a = (a + 1 == azi_n) ? 0 : a + 1;
             }
         }
     }
@@ -131,6 +183,14 @@ spt_pnt_kernel(const float *__restrict__ delta, int K, int P, const float *__res
             }
         }
         scnt[v] = (unsigned char)c;
+        // slots whose point is an exact zero (key-point copies) contribute relu(b) like a zeroed slot: the feature
+        // pass only visits the others
+        unsigned nzm = 0;
+        for (int l = 0; l < c; ++l) {
+            const int i = sel[(size_t)v * MAX_NV + l];
+            if (!((zmask[i >> 5] >> (i & 31)) & 1u) && !(l == 0 && i == 0)) nzm |= 1u << l;
+        }
+        snz[v] = (unsigned short)nzm;
         if (dbg_vidx || dbg_inv) {
             const int first = c > 0 ? sel[(size_t)v * MAX_NV] : 0;
             const int a = v % azi_n;
@@ -153,27 +213,37 @@ spt_pnt_kernel(const float *__restrict__ delta, int K, int P, const float *__res
         }
     }
     __syncthreads();
-    // ---- 4. features in the channel-blocked layout [K][16/4][V][4] the tensor-core convolution reads; thread t writes
-    //         element t of the tile (coalesced): t = (cg * V + v) * 4 + c4 ------------------------------------------
-    float *out = feat + (size_t)k * 16 * V;
-    for (int t = tid; t < 16 * V; t += SPT_THREADS) {
-        const int cg = t / (4 * V), r4 = t - cg * 4 * V, v = r4 >> 2, ch = cg * 4 + (r4 & 3);
-        const float w0 = sw[3 * ch], w1 = sw[3 * ch + 1], w2 = sw[3 * ch + 2], bb = sw[48 + ch];
+    // ---- 4. features in the channel-blocked layout [K][16/4][V][4] the tensor-core convolution reads: thread = (group
+    //         of 4 channels, voxel); the selected non-zero points are de-rotated once per thread; one 16-byte store ----
+    float4 *out4 = reinterpret_cast<float4 *>(feat + (size_t)k * 16 * V);
+    for (int t = tid; t < 4 * V; t += SPT_THREADS) {
+        const int cg = t / V, v = t - cg * V;
+        float w0[4], w1[4], w2[4], bb[4], best[4];
         const int c = scnt[v];
-        const int first = c > 0 ? sel[(size_t)v * MAX_NV] : 0;
+        unsigned nzm = snz[v];
+        const bool any_zero = (c < nv) || (__popc(nzm) < c);     // padding slot, slot 0 with index 0, or an exact-zero point
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ch = cg * 4 + q;
+            w0[q] = sw[3 * ch]; w1[q] = sw[3 * ch + 1]; w2[q] = sw[3 * ch + 2]; bb[q] = sw[48 + ch];
+            best[q] = any_zero ? fmaxf(bb[q], 0.0f) : -INFINITY;   // a zeroed slot contributes relu(bn(conv(0)))
+        }
         const int a = v % azi_n;
         const float cs = srot[2 * a], sn = srot[2 * a + 1];
-        const bool any_zero = (c < nv) || (first == 0);
-        float best = any_zero ? fmaxf(bb, 0.0f) : -INFINITY;   // a zeroed slot contributes relu(bn(conv(0)))
-        for (int l = (first == 0) ? 1 : 0; l < c; ++l) {
+        while (nzm) {
+            const int l = __ffs(nzm) - 1;
+            nzm &= nzm - 1;
             const int i = sel[(size_t)v * MAX_NV + l];
             const float x = px[i], y = py[i], z = pz[i];
             const float xr = (x * cs) + (y * (-sn));
             const float yr = (x * sn) + (y * cs);
-            const float val = (((w0 * xr) + (w1 * yr)) + (w2 * z)) + bb;
-            best = fmaxf(best, fmaxf(val, 0.0f));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float val = (((w0[q] * xr) + (w1[q] * yr)) + (w2[q] * z)) + bb[q];
+                best[q] = fmaxf(best[q], fmaxf(val, 0.0f));
+            }
         }
-        out[t] = best;
+        out4[t] = make_float4(best[0], best[1], best[2], best[3]);
     }
 }
 
@@ -181,8 +251,9 @@ size_t spt_smem_bytes(int P, int V, int azi_n) {
     const int NW = (P + 31) >> 5;
     size_t bytes = sizeof(float) * (3 * (size_t)P + 3 * (size_t)V + 64 + 2 * (size_t)azi_n + 3 * MAX_RE);
     bytes += sizeof(unsigned) * ((size_t)V * NW + NW);
-    bytes += sizeof(unsigned short) * (size_t)V * MAX_NV;
-    bytes += (size_t)V + 16;
+    bytes += sizeof(unsigned short) * ((size_t)V * MAX_NV + (size_t)((P + 1) & ~1) + (size_t)V);
+    bytes += sizeof(int) * (MAX_RE + 1);
+    bytes += (size_t)P + (size_t)V + 16;
     return bytes;
 }
 
