@@ -44,6 +44,16 @@ def measured_peaks():
     return dict(hbm=6650.0, tf=1400.0, src="fallback")
 
 
+def conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc_kernel launch, averaged over the eight layers of one
+    batched descriptor pass, from the committed `ncu --set full` capture (profiles/r01_conv_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons sampled DURING the timed regions: NVML in-process (10 ms period), nvidia-smi as the
     fallback (its first answer can take longer than a short timed region)."""
@@ -197,7 +207,9 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{args.workload} synthetic pair", "note": "CPU oracle port on host cores"},
+            "config": {"workload": f"{args.workload}: 2x{len(data['src_fds_pcd'])} pts, {cfg.patch.num_fps} kpts, {cfg.patch.num_points_per_patch} pts/patch, "
+                                   f"{cfg.patch.num_scales} scales, {cfg.match.iter_n} RANSAC iters, seeded synthetic weights",
+                       "note": "CPU oracle port of the reference path on the host cores (oracle/)"},
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -374,7 +386,7 @@ def main():
                 "achieved": ach_tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf"],
                 "peak_source": f"{pk['src']} bf16 dense (sustained); the 3-pass TF32 ceiling is ~375 TFLOP/s fp32-equivalent",
                 "launches": cd["launches"], "avg_launch_ms": cd["ms"] / max(cd["launches"], 1),
-                "share_of_step": cd["ms"] / ms_eager if ms_eager else None, "traffic": None,
+                "share_of_step": cd["ms"] / ms_eager if ms_eager else None, "traffic": conv_traffic(),
                 "measured_in": "eager (non-graph) pass of this run: per-kernel CUDA-event brackets need individual launches"}
         kern = {}
         sp = prof.get("select_patches")
