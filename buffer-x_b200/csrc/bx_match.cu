@@ -305,6 +305,40 @@ BX_API int bx_hypotheses(const float *logits, int azi_n, const float *kpts_s, co
     return BX_OK;
 }
 
+namespace {
+struct ConcatOffsets { int s_off[8], t_off[8]; };
+
+// one CTA per scale: the scale's match list is appended at the prefix sum of the earlier scales' device-side counts
+__global__ void concat_matches_kernel(const int *__restrict__ s_lists, const int *__restrict__ t_lists,
+                                      const int *__restrict__ d_counts, int S, int stride, ConcatOffsets ro,
+                                      int *__restrict__ s_all, int *__restrict__ t_all, int *__restrict__ d_offs) {
+    const int i = blockIdx.x;
+    int off = 0;
+    for (int j = 0; j < i; ++j) off += d_counts[j];
+    const int M = d_counts[i];
+    if (threadIdx.x == 0) {
+        d_offs[i] = off;
+        if (i == S - 1) d_offs[S] = off + M;
+    }
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        s_all[off + m] = s_lists[(size_t)i * stride + m] + ro.s_off[i];
+        t_all[off + m] = t_lists[(size_t)i * stride + m] + ro.t_off[i];
+    }
+}
+}  // namespace
+
+BX_API int bx_concat_matches(const int32_t *s_lists, const int32_t *t_lists, const int32_t *d_counts, int S, int stride,
+                             const int32_t *h_s_off, const int32_t *h_t_off, int32_t *s_all, int32_t *t_all,
+                             int32_t *d_offs, void *stream) {
+    BX_REQUIRE(s_lists && t_lists && d_counts && h_s_off && h_t_off && s_all && t_all && d_offs, "bx_concat_matches: null pointer");
+    BX_REQUIRE(S >= 1 && S <= 8 && stride >= 0, "bx_concat_matches: 1 <= S <= 8");
+    ConcatOffsets ro = {};
+    for (int i = 0; i < S; ++i) { ro.s_off[i] = h_s_off[i]; ro.t_off[i] = h_t_off[i]; }
+    concat_matches_kernel<<<S, 256, 0, bx_stream(stream)>>>(s_lists, t_lists, d_counts, S, stride, ro, s_all, t_all, d_offs);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
 BX_API int bx_consensus(const float *ss, const float *tt, const float *R, const float *t, const int32_t *d_Mc, int maxMc,
                         int azi_n, float inlier_th, int32_t *counts, int32_t *inlier_ind, int32_t *d_I, int32_t *d_best,
                         void *stream) {

@@ -294,7 +294,29 @@ class BufferX(nn.Module):
                     jobs.append((pts_c, k_c, r_dev[i:i + 1], pm))
             batched = self.Desc.forward_multi(jobs, aligned)
             desc_t.toc()
-        for i in range(S):
+        if batched is not None and S <= 8:
+            # all scales at once: per-scale mutual matching into rows of one [S,K] buffer, one concatenation kernel
+            # (device-side prefix sums = the `offs` of the sequential flow), then CostNet, the hypothesis build and the
+            # consensus over the concatenated list -- the order of the reference's per-scale torch.cat.
+            pose_t.tic()
+            multi = self.Desc.last_multi
+            s_lists = torch.empty((S, K), dtype=torch.int32, device=dev)
+            t_lists = torch.empty((S, K), dtype=torch.int32, device=dev)
+            cnts = torch.zeros(S, dtype=torch.int32, device=dev)
+            for i in range(S):
+                ops.mutual_nn(batched[2 * i]["desc"], batched[2 * i + 1]["desc"], out=(s_lists[i], t_lists[i], cnts[i:i + 1]))
+            s_all, t_all = ops.concat_matches(s_lists, t_lists, cnts, [2 * i * K for i in range(S)],
+                                              [(2 * i + 1) * K for i in range(S)], offs)
+            d_Mall = offs[S:S + 1]
+            logits = self.Pose.logits(multi["equi"], multi["equi"], s_all, t_all, d_Mall, S * K)
+            kp_all = torch.cat([src_kpts, tgt_kpts] * S, dim=0)
+            zero_off = torch.zeros(2, dtype=torch.int32, device=dev)
+            ops.hypotheses(logits, azi_n, kp_all, kp_all, multi["R"], multi["R"], s_all, t_all, d_Mall, S * K,
+                           zero_off[0:1], zero_off[1:2], None, R_acc, t_acc, ss_acc, tt_acc)
+            scales_used = S
+            inl, dI, dbest, counts = ops.consensus(ss_acc, tt_acc, R_acc, t_acc, d_Mall, S * K, azi_n, cfg.match.inlier_th)
+            pose_t.toc()
+        for i in range(S if (batched is None or S > 8) else 0):
             desc_t.tic()
             des_r = r_dev[i:i + 1]
             ps = None if perms is None else perms[i][0]

@@ -125,12 +125,15 @@ class MiniSpinNet(nn.Module):
         Kt = sum(Ks)
         patches = torch.empty((Kt, P, 3), dtype=torch.float32, device=dev)
         delta = torch.empty_like(patches)
+        R_all = torch.empty((Kt, 3, 3), dtype=torch.float32, device=dev)
+        ra_all = torch.empty((Kt, 3), dtype=torch.float32, device=dev)
         Rs, axes = [], []
         o = 0
         for (pts, kpts, des_r, perm), K in zip(jobs, Ks):
             pts4 = ops.permute_cloud(pts.contiguous(), perm)
             ops.select_patches(pts4, kpts.contiguous(), des_r, P, patches=patches[o:o + K])
-            _, R, ra = ops.lrf(patches[o:o + K], des_r, bool(is_aligned_to_global_z), delta=delta[o:o + K])
+            _, R, ra = ops.lrf(patches[o:o + K], des_r, bool(is_aligned_to_global_z), delta=delta[o:o + K], Rt=R_all[o:o + K],
+                               ra=ra_all[o:o + K])
             Rs.append(R)
             axes.append(ra)
             o += K
@@ -147,6 +150,7 @@ class MiniSpinNet(nn.Module):
             outs.append({"desc": desc[o:o + K], "equi": equi[o:o + K], "rand_axis": ra, "R": R, "patches": delta[o:o + K],
                          "aug_rotation": None})
             o += K
+        self.last_multi = {"desc": desc, "equi": equi, "R": R_all}       # the batched buffers behind the per-job views
         return outs
 
     def get_parameter(self):

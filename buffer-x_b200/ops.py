@@ -22,7 +22,7 @@ SYMBOLS = [
     "bx_select_patches", "bx_ball_query", "bx_lrf", "bx_spt_pnt", "bx_conv_layer", "bx_conv_tc_ntile", "bx_conv_layer_tc",
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
-    "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab",
+    "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab", "bx_concat_matches",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
@@ -64,6 +64,7 @@ def load_library():
     lib.bx_conv_layer_tc.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_tc_ntile.argtypes = [c_int]
     lib.bx_costvol_ab.argtypes = [P, P, P, P, P, c_int, P, P, P, P, P, P]
+    lib.bx_concat_matches.argtypes = [P, P, P, c_int, c_int, P, P, P, P, P, P]
     lib.bx_pool_desc.argtypes = [P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_mutual_nn.argtypes = [P, c_int, P, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_hypotheses.argtypes = [P, c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P]
@@ -222,13 +223,15 @@ def ball_query(xyz: torch.Tensor, qry: torch.Tensor, radius: float, nsample: int
     return idx
 
 
-def lrf(patches: torch.Tensor, des_r, aligned: bool, delta=None):
+def lrf(patches: torch.Tensor, des_r, aligned: bool, delta=None, Rt=None, ra=None):
     K, P, _ = patches.shape
     dev = patches.device
     if delta is None:
         delta = torch.empty_like(patches)
-    Rt = torch.empty((K, 3, 3), dtype=F32, device=dev)
-    ra = torch.empty((K, 3), dtype=F32, device=dev)
+    if Rt is None:
+        Rt = torch.empty((K, 3, 3), dtype=F32, device=dev)
+    if ra is None:
+        ra = torch.empty((K, 3), dtype=F32, device=dev)
     rv, rp = (0.0, _dp(des_r, F32, "des_r")) if isinstance(des_r, torch.Tensor) else (float(des_r), None)
     with _Span("lrf", 24.0 * K * P):
         _check(load_library().bx_lrf(_dp(patches, F32, "patches"), K, P, rv, rp, int(bool(aligned)), _dp(delta), _dp(Rt), _dp(ra), _stream()), "bx_lrf")
@@ -362,18 +365,37 @@ def pool_desc(x, w1, b1, w2, b2, desc=None, equi=None, channels_last=False):
     return desc, equi
 
 
-def mutual_nn(a, b, want_nn=False):
+def mutual_nn(a, b, want_nn=False, out=None):
+    """out: optional (s_mids [>=Ka], t_mids [>=Ka], dM [1]) int32 buffers to fill (dM must be zero on entry)."""
     Ka, Kb, C = a.shape[0], b.shape[0], a.shape[1]
     dev = a.device
     keys = torch.empty(Ka + Kb + 1, dtype=torch.int64, device=dev)
-    s = torch.empty(max(Ka, 1), dtype=I32, device=dev)
-    t = torch.empty(max(Ka, 1), dtype=I32, device=dev)
-    dM = torch.zeros(1, dtype=I32, device=dev)
+    if out is not None:
+        s, t, dM = out
+    else:
+        s = torch.empty(max(Ka, 1), dtype=I32, device=dev)
+        t = torch.empty(max(Ka, 1), dtype=I32, device=dev)
+        dM = torch.zeros(1, dtype=I32, device=dev)
     snn = torch.empty(max(Ka, 1), dtype=I32, device=dev) if want_nn else None
     tnn = torch.empty(max(Kb, 1), dtype=I32, device=dev) if want_nn else None
     _check(load_library().bx_mutual_nn(_dp(a, F32, "a"), Ka, _dp(b, F32, "b"), Kb, C, _dp(keys), _dp(s), _dp(t), _dp(dM), _dp(snn), _dp(tnn), _stream()),
            "bx_mutual_nn")
     return s, t, dM, snn, tnn
+
+
+def concat_matches(s_lists, t_lists, counts, s_row_off, t_row_off, d_offs):
+    """[S,K] per-scale match lists + device counts -> (s_all, t_all) [S*K] in scale order with row offsets added;
+    d_offs [S+1] int32 receives the prefix sums."""
+    S, K = s_lists.shape
+    dev = s_lists.device
+    s_all = torch.empty(S * K, dtype=I32, device=dev)
+    t_all = torch.empty(S * K, dtype=I32, device=dev)
+    so = np.ascontiguousarray(s_row_off, dtype=np.int32)
+    to = np.ascontiguousarray(t_row_off, dtype=np.int32)
+    _check(load_library().bx_concat_matches(_dp(s_lists, I32, "s_lists"), _dp(t_lists, I32, "t_lists"), _dp(counts, I32, "counts"), S, K,
+                                            so.ctypes.data_as(c_void_p), to.ctypes.data_as(c_void_p), _dp(s_all), _dp(t_all),
+                                            _dp(d_offs, I32, "d_offs"), _stream()), "bx_concat_matches")
+    return s_all, t_all
 
 
 def hypotheses(logits, azi_n, kpts_s, kpts_t, Rt_s, Rt_t, s_mids, t_mids, d_M, maxM, d_off, d_off_out, ind_out, R_acc, t_acc,

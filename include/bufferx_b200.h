@@ -153,6 +153,15 @@ int bx_pool_desc(const float *x, int K, int C, int S, int channels_last, const f
 int bx_mutual_nn(const float *a, int Ka, const float *b, int Kb, int C, unsigned long long *keys, int32_t *s_mids,
                  int32_t *t_mids, int32_t *d_M, int32_t *snn, int32_t *tnn, void *stream);
 
+/* Concatenate the S per-scale match lists (s_lists/t_lists: [S][stride] int32, counts d_counts[S] on the device)
+ * into one list in scale order, adding the per-scale row offsets h_s_off/h_t_off[S] (host arrays) so the entries
+ * index the batched descriptor buffers of a pair; d_offs[S+1] receives the prefix sums (d_offs[S] = total).
+ * Lets CostNet and the hypothesis build of all scales run as one batch (same order as the reference's per-scale
+ * torch.cat, models/BUFFERX.py:391-402). */
+int bx_concat_matches(const int32_t *s_lists, const int32_t *t_lists, const int32_t *d_counts, int S, int stride,
+                      const int32_t *h_s_off, const int32_t *h_t_off, int32_t *s_all, int32_t *t_all,
+                      int32_t *d_offs, void *stream);
+
 /* ---- a11 tail + a12: soft arg-max and pose hypotheses ---------------------------------------
  * Replaces softmax/expectation of CostVolume.forward (models/BUFFERX.py:66-69) and the hypothesis
  * build (:382-389, kornia axis_angle_to_rotation_matrix).  logits: [maxM, azi_n].
