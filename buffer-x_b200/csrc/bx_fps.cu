@@ -46,6 +46,38 @@ __device__ __forceinline__ Cand warp_best(const Cand c) {
     return r;
 }
 
+// ---- cluster exchange without cluster.sync: remote stores + remote mbarrier arrive (release.cluster), local wait
+//      (acquire.cluster).  A cluster.sync costs ~380 cycles per FPS iteration and flushes L1; this costs one DSMEM
+//      round (~215 cycles).
+__device__ __forceinline__ uint32_t fps_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t fps_mapa(uint32_t saddr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void fps_st_cluster_v4(uint32_t a, uint4 v) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void fps_st_cluster_f32(uint32_t a, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void fps_arrive_cluster(uint32_t rbar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+__device__ __forceinline__ void fps_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "FPS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FPS_DONE;\n\t"
+        "bra FPS_WAIT;\n\t"
+        "FPS_DONE:\n\t"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, int npoint,
@@ -73,6 +105,7 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
     __shared__ float w_z[2][32];
     __shared__ uint4 c_a[2][16];
     __shared__ float c_z[2][16];
+    __shared__ __align__(8) unsigned long long cbar[2];   // one exchange barrier per parity, CL arrivals each
 
     float px[PPT], py[PPT], pz[PPT], tmp[PPT];
     const int stride = CL * THREADS;
@@ -97,7 +130,12 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
         idx[0] = 0;
         if (kp) { kp[0] = p0x; kp[1] = p0y; kp[2] = p0z; }
     }
-    cluster.sync();  // every CTA of the cluster is resident before any DSMEM store
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&cbar[0])), "r"(CL) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&cbar[1])), "r"(CL) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();  // every CTA of the cluster is resident (and its barriers initialised) before any DSMEM access
 
     for (int j = 1; j < npoint; ++j) {
         const int par = j & 1;
@@ -132,13 +170,15 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
         }
         Cand cb = warp_best(c);
         if (CL > 1) {
-            if (warp == 0 && lane < CL) {
-                uint4 *ra = cluster.map_shared_rank(&c_a[par][rank], lane);
-                float *rz = cluster.map_shared_rank(&c_z[par][rank], lane);
-                *ra = make_uint4(cb.hi, cb.lo, __float_as_uint(cb.x), __float_as_uint(cb.y));
-                *rz = cb.z;
+            if (warp == 0 && lane < CL) {   // lane = destination CTA: candidate into its slot [rank], then arrive on its barrier
+                fps_st_cluster_v4(fps_mapa(fps_smem_u32(&c_a[par][rank]), (uint32_t)lane),
+                                  make_uint4(cb.hi, cb.lo, __float_as_uint(cb.x), __float_as_uint(cb.y)));
+                fps_st_cluster_f32(fps_mapa(fps_smem_u32(&c_z[par][rank]), (uint32_t)lane), cb.z);
+                fps_arrive_cluster(fps_mapa(fps_smem_u32(&cbar[par]), (uint32_t)lane));
             }
-            cluster.sync();
+            // Buffers and barriers are double-buffered by parity: a peer can only be one iteration ahead (its next
+            // wait needs our next arrive), so slot [par] is not rewritten before everybody has read it.
+            fps_wait_cluster(fps_smem_u32(&cbar[par]), (uint32_t)(((j >> 1) - (par ? 0 : 1)) & 1));
             Cand g;
             g.hi = 0u; g.lo = 0u; g.x = p0x; g.y = p0y; g.z = p0z;
             if (lane < CL) {
@@ -204,8 +244,12 @@ BX_API int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint,
     for (int b = 0; b <= kMaxClouds; ++b) d_off.v[b] = h_offsets[b <= B ? b : B];
     if (maxN <= 4096) return launch_fps<256, 2>(xyz, d_off, B, 8, npoint, idx, kpts, st);
     if (maxN <= 8192) return launch_fps<256, 4>(xyz, d_off, B, 8, npoint, idx, kpts, st);
-    if (maxN <= 16384) return launch_fps<256, 8>(xyz, d_off, B, 8, npoint, idx, kpts, st);
-    if (maxN <= 32768) return launch_fps<256, 16>(xyz, d_off, B, 8, npoint, idx, kpts, st);
-    if (maxN <= 65536) return launch_fps<512, 16>(xyz, d_off, B, 8, npoint, idx, kpts, st);
-    return launch_fps<512, 16>(xyz, d_off, B, 16, npoint, idx, kpts, st);
+    // larger clouds: 1024 threads per CTA and few points per thread -- the per-iteration register scan is a dependent
+    // chain per thread, so its latency scales with the points per thread, while the reductions / cluster exchange
+    // do not depend on the thread count
+    if (maxN <= 16384) return launch_fps<1024, 2>(xyz, d_off, B, 8, npoint, idx, kpts, st);
+    if (maxN <= 24576) return launch_fps<1024, 3>(xyz, d_off, B, 8, npoint, idx, kpts, st);
+    if (maxN <= 32768) return launch_fps<1024, 4>(xyz, d_off, B, 8, npoint, idx, kpts, st);
+    if (maxN <= 65536) return launch_fps<1024, 8>(xyz, d_off, B, 8, npoint, idx, kpts, st);
+    return launch_fps<1024, 8>(xyz, d_off, B, 16, npoint, idx, kpts, st);
 }
