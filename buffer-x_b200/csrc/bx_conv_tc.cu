@@ -42,12 +42,17 @@ struct ConvTcParams {
     int Cin, Cout, D, H, W, kd, kh, kw, relu;
     int S_in, S_out, OD, OH, OW, T;
     int seg_len;  // stages per main-accumulator segment
+    long long *trace;   // -DBX_TC_TRACE builds only: clock64 stamps of one CTA
     const float *equi_s, *equi_t;
     const int *s_mids, *t_mids;
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 4;      // A ring (tensor memory)
+// B ring (shared memory): weights are prefetched independently of the A slots, TC_SB stages per bulk copy and per
+// barrier ("super-stage"), TC_NBS super-stages.  Narrow layers: 4 x 3 (one mbarrier wait per four stages -- the MMA
+// warp's per-stage latency is what bounds them); wide layers: 1 x 8.
+template <int NT> struct BRing { static constexpr int SB = NT == 128 ? 1 : 4, NBS = NT == 128 ? 8 : 3; };
 constexpr int TC_MAX_TAPS = 128;
 constexpr int A_STAGE_COLS = 32;  // TMEM columns of one A stage: [kstep(2)][split(hi,lo)][8 tf32 values]
 
@@ -168,21 +173,24 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CW]) {
 // TMEM columns).  Narrow layers (NT <= 64) are dominated by per-tile latencies (pipeline fill, drains, epilogue), not
 // by tensor time, so they run LG = 2 (288 threads) with at most 256 TMEM columns: TWO CTAs per SM overlap one tile's
 // prologue / drain bubbles / epilogue with the other tile's MMAs.
-template <int GEOM, int NT, int LG, int NSETS>
-__global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel(const ConvTcParams p) {
+template <int GEOM, int NT, int LG, int NSETS, int MINB, int XSEP>
+__global__ void __launch_bounds__(LG * 128 + 64, MINB) conv_tc_kernel(const ConvTcParams p) {
     constexpr int TC_LOADERS = LG * 128;
     constexpr int MMA_WARP = LG * 4;
+    constexpr int WGT_WARP = LG * 4 + 1;   // weight producer: streams the B images through the shared-memory ring
+    constexpr int TC_SB = BRing<NT>::SB, TC_NBS = BRing<NT>::NBS, TC_BSTAGES = TC_SB * TC_NBS;
     constexpr int B_STAGE_BYTES = 2 * 2 * 2 * NT * 16;  // [kstep][split][kunit][n][16B]
     constexpr int STAGE_BYTES = B_STAGE_BYTES;      // shared memory holds only the weights; A lives in tensor memory
-    constexpr int A_RING = (NSETS + 1) * NT;        // TMEM columns: main[0..NSETS), cross, then the A ring
+    constexpr int A_RING = (NSETS + XSEP) * NT;     // TMEM columns: main[0..NSETS), [cross], then the A ring
     constexpr int TMEM_NEED = A_RING + TC_STAGES * A_STAGE_COLS;
     constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
-    static_assert(LG == 4 || TMEM_NEED <= 256, "two CTAs per SM need <= 256 TMEM columns each");
+    static_assert(MINB == 1 || TMEM_NEED <= 256, "two CTAs per SM need <= 256 TMEM columns each");
     constexpr int CW = NT / LG;         // accumulator columns owned by one loader warp
     // barriers: full[ST] (4 loader-warp arrivals + 1 expect_tx arrival), empty[ST], segdone[2], accfree[2]
     constexpr int BAR_EMPTY = TC_STAGES, BAR_SEGDONE = 2 * TC_STAGES, BAR_ACCFREE = 2 * TC_STAGES + 2;
+    constexpr int BAR_BFULL = 2 * TC_STAGES + 4, BAR_BEMPTY = BAR_BFULL + TC_NBS;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 4];
+    __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 4 + 2 * TC_NBS];
     __shared__ uint32_t tmem_base_s;
     __shared__ int4 tap_tab[TC_MAX_TAPS];
 
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel
     if (row0 >= Mtotal) return;  // uniform per CTA, before any barrier / TMEM allocation
     const int tid = threadIdx.x, warp = tid >> 5;
     const int n_iters = (p.Cin / 16) * p.T;  // stage = (16-channel chunk, tap); chunk outer, tap inner
-    const int G = p.seg_len;
+    const int G = XSEP ? p.seg_len : (p.seg_len < 4 ? p.seg_len : 4);   // merged cross terms: 6 MMAs per stage in one chain
     const int nseg = (n_iters + G - 1) / G;
 
     if (warp == MMA_WARP) {
@@ -208,8 +216,12 @@ __global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel
     }
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(smem_u32(&bars[s]), 4 + 1);            // full: the 4 warps of the owning group + the expect_tx arrival
+            mbar_init(smem_u32(&bars[s]), 4);                // A full: the 4 warps of the owning group
             mbar_init(smem_u32(&bars[BAR_EMPTY + s]), 1);
+        }
+        for (int s = 0; s < TC_NBS; ++s) {
+            mbar_init(smem_u32(&bars[BAR_BFULL + s]), 1);    // B full: the producer's expect_tx arrival + the bulk copy's bytes
+            mbar_init(smem_u32(&bars[BAR_BEMPTY + s]), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&bars[BAR_SEGDONE + s]), 1);
@@ -358,7 +370,15 @@ __global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel
 
         if (grp < n_iters) load_stage();
         int next_drain = 0;
+#ifdef BX_TC_TRACE
+        const bool tr = p.trace && blockIdx.x == gridDim.x / 2 && (tid & 127) == 0;
+        long long *tb = p.trace + (size_t)grp * 3 * 64;
+        int trk = 0;
+#endif
         for (int it = grp; it < n_iters; it += LG) {
+#ifdef BX_TC_TRACE
+            if (tr && trk < 64) tb[trk * 3 + 0] = clock64();
+#endif
             if (next_drain < nseg - 1 && it >= (next_drain + 1) * G + (G < TC_STAGES ? G : TC_STAGES)) {
                 drain(next_drain, true);                  // its MMAs are several stages behind us: short wait
                 ++next_drain;
@@ -366,11 +386,9 @@ __global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel
             const int s = it % TC_STAGES;
             const uint32_t use = (uint32_t)(it / TC_STAGES);   // how many times slot s has been filled before
             if (use > 0) mbar_wait(bar_base + 8u * (BAR_EMPTY + s), (use - 1) & 1);  // tensor core has read the slot
-            if ((tid & 127) == 0) {  // weights of this stage: one bulk copy, completion counted on full[s]
-                mbar_arrive_expect_tx(bar_base + 8u * s, (uint32_t)B_STAGE_BYTES);
-                bulk_g2s(smem_base + (uint32_t)s * STAGE_BYTES,
-                         reinterpret_cast<const unsigned char *>(p.w) + (size_t)it * B_STAGE_BYTES, (uint32_t)B_STAGE_BYTES, bar_base + 8u * s);
-            }
+#ifdef BX_TC_TRACE
+            if (tr && trk < 64) tb[trk * 3 + 1] = clock64();
+#endif
             store_stage(s);
             if (it + LG < n_iters) {                      // this group's next stage: activations in flight
                 advance_lg();
@@ -379,6 +397,9 @@ __global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // tcgen05.st ordered before the arrive
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * s);
+#ifdef BX_TC_TRACE
+            if (tr && trk < 64) { tb[trk * 3 + 2] = clock64(); ++trk; }
+#endif
         }
         while (next_drain < nseg) {                      // a set must still be released if a later segment reuses it
             drain(next_drain, next_drain + NSETS < nseg);
@@ -387,8 +408,13 @@ __global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel
         // ---- epilogue: running sums + cross accumulator + bias (+ReLU) ------------------------------------
         {
             uint32_t u[CW];
-            tmem_ld<CW>(tmem_base + tm_lane + (uint32_t)(NSETS * NT + ecs * CW), u);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (XSEP) {
+                tmem_ld<CW>(tmem_base + tm_lane + (uint32_t)(NSETS * NT + ecs * CW), u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int c = 0; c < CW; ++c) u[c] = 0u;   // cross terms were accumulated with the main products
+            }
             const long long em = row0 + eq * 32 + (tid & 31);
             if (em < Mtotal) {
                 const int en = (int)(em / p.S_out);
@@ -412,8 +438,27 @@ __global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel
                 }
             }
         }
+    } else if (warp == WGT_WARP) {
+        // =========================== weight producer ====================================================
+        // The weight image of stage `it` is one contiguous block; its order is known in advance, so the producer runs
+        // up to TC_BSTAGES stages ahead of the tensor core, independent of the activation slots: the L2 -> shared
+        // memory latency of the bulk copy (~1 us) is off the stage turnaround path.
+        if ((tid & 31) == 0) {
+            const int n_super = (n_iters + TC_SB - 1) / TC_SB;
+            for (int q = 0; q < n_super; ++q) {
+                const int sb = q % TC_NBS;
+                const uint32_t useb = (uint32_t)(q / TC_NBS);
+                if (useb > 0) mbar_wait(bar_base + 8u * (BAR_BEMPTY + sb), (useb - 1) & 1);
+                const int nst = (n_iters - q * TC_SB) < TC_SB ? (n_iters - q * TC_SB) : TC_SB;
+                const uint32_t bytes = (uint32_t)nst * (uint32_t)B_STAGE_BYTES;
+                mbar_arrive_expect_tx(bar_base + 8u * (BAR_BFULL + sb), bytes);
+                bulk_g2s(smem_base + (uint32_t)(sb * TC_SB) * STAGE_BYTES,
+                         reinterpret_cast<const unsigned char *>(p.w) + (size_t)q * TC_SB * B_STAGE_BYTES, bytes, bar_base + 8u * (BAR_BFULL + sb));
+            }
+        }
+        __syncwarp();
     } else {
-        // =========================== MMA issuer (last warp) ============================================
+        // =========================== MMA issuer ==========================================================
         // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NT, M = 128
         constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
@@ -422,28 +467,52 @@ __global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel
         const uint32_t leader = elect_leader();
         const uint32_t b0 = (smem_base >> 4) | B_LBO;                            // stage 0, kstep 0, hi
         const uint32_t d_cross = tmem_base + (uint32_t)(NSETS * NT);
-        int s = 0, seg = 0, in_seg = 0;
-        uint32_t use = 0;
+        int s = 0, sb = 0, seg = 0, in_seg = 0;
+        uint32_t use = 0, useb = 0;
+#ifdef BX_TC_TRACE
+        const bool trm = p.trace && blockIdx.x == gridDim.x / 2 && (tid & 31) == 0;
+        long long *tm = p.trace + 4 * 3 * 64;
+#endif
         for (int it = 0; it < n_iters; ++it) {
+#ifdef BX_TC_TRACE
+            if (trm && it < 128) tm[it * 3 + 0] = clock64();
+#endif
             if (in_seg == 0 && seg >= NSETS) {
                 // segment `seg` reuses main set seg % NSETS: segment seg-NSETS must have been drained
                 mbar_wait(bar_base + 8u * (BAR_ACCFREE + (seg % NSETS)), (uint32_t)(((seg - NSETS) / NSETS) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            mbar_wait(bar_base + 8u * s, use & 1);
+            if (sb % TC_SB == 0)                                      // weights: one wait per TC_SB stages (usually long since there)
+                mbar_wait(bar_base + 8u * (BAR_BFULL + sb / TC_SB), useb & 1);
+#ifdef BX_TC_TRACE
+            if (trm && it < 128) tm[it * 3 + 1] = clock64();
+#endif
+            mbar_wait(bar_base + 8u * s, use & 1);                    // activations
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t so = (uint32_t)s * (uint32_t)(STAGE_BYTES >> 4);
+#ifdef BX_TC_TRACE
+            if (trm && it < 128) tm[it * 3 + 2] = clock64();
+#endif
+            const uint32_t so = (uint32_t)sb * (uint32_t)(STAGE_BYTES >> 4);
             const uint32_t d_main = tmem_base + (uint32_t)((seg % NSETS) * NT);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const uint32_t ah = tmem_base + (uint32_t)(A_RING + s * A_STAGE_COLS + ks * 16), al = ah + 8;
                 const uint32_t bh = b0 + so + (uint32_t)(ks * 2 + 0) * B_IMG, bl = b0 + so + (uint32_t)(ks * 2 + 1) * B_IMG;
-                mma_tf32_ts(leader, d_cross, al, bh, DESC_HI, IDESC, (it == 0 && ks == 0) ? 0u : 1u);
-                mma_tf32_ts(leader, d_cross, ah, bl, DESC_HI, IDESC, 1u);
-                mma_tf32_ts(leader, d_main, ah, bh, DESC_HI, IDESC, (in_seg == 0 && ks == 0) ? 0u : 1u);
+                if (XSEP) {
+                    mma_tf32_ts(leader, d_cross, al, bh, DESC_HI, IDESC, (it == 0 && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(leader, d_cross, ah, bl, DESC_HI, IDESC, 1u);
+                    mma_tf32_ts(leader, d_main, ah, bh, DESC_HI, IDESC, (in_seg == 0 && ks == 0) ? 0u : 1u);
+                } else {   // one accumulator per segment takes all three products (small terms first)
+                    mma_tf32_ts(leader, d_main, al, bh, DESC_HI, IDESC, (in_seg == 0 && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(leader, d_main, ah, bl, DESC_HI, IDESC, 1u);
+                    mma_tf32_ts(leader, d_main, ah, bh, DESC_HI, IDESC, 1u);
+                }
             }
             mma_commit(leader, bar_base + 8u * (BAR_EMPTY + s));   // slot s may be refilled once these MMAs have read it
+            if (sb % TC_SB == TC_SB - 1 || it == n_iters - 1)
+                mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sb / TC_SB));   // the whole super-stage has been read
             if (++s == TC_STAGES) { s = 0; ++use; }
+            if (++sb == TC_BSTAGES) { sb = 0; ++useb; }
             if (++in_seg == G || it == n_iters - 1) {
                 mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + (seg % NSETS)));
                 in_seg = 0;
@@ -459,37 +528,46 @@ __global__ void __launch_bounds__(LG * 128 + 32, LG == 4 ? 1 : 2) conv_tc_kernel
     }
 }
 
-template <int GEOM, int NT, int LG, int NSETS>
+template <int GEOM, int NT, int LG, int NSETS, int MINB, int XSEP>
 int launch_tc(const ConvTcParams &p, int max_n, cudaStream_t st) {
     const long long maxM = (long long)max_n * p.S_out;
     const unsigned gx = (unsigned)((maxM + TC_BM - 1) / TC_BM);
     if (gx == 0) return BX_OK;
-    constexpr int smem = TC_STAGES * (2 * 2 * 2 * NT * 16);
+    constexpr int smem = BRing<NT>::SB * BRing<NT>::NBS * (2 * 2 * 2 * NT * 16);
     static bool attr_done = false;
     if (!attr_done) {
-        BX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<GEOM, NT, LG, NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<GEOM, NT, LG, NSETS, MINB, XSEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    conv_tc_kernel<GEOM, NT, LG, NSETS><<<gx, LG * 128 + 32, smem, st>>>(p);
+    conv_tc_kernel<GEOM, NT, LG, NSETS, MINB, XSEP><<<gx, LG * 128 + 64, smem, st>>>(p);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }
 
-int g_tc_wide_only = -1;   // -1: read BX_TC_WIDE once (debug / A-B switch: 1 = every layer on the one-CTA-per-SM configuration)
+int g_tc_mode = -1;   // -1: read BX_TC_MODE once (debug / A-B switch): 0 default, 1 = every layer one CTA per SM (LG=4),
+                      // 2 = narrow layers two CTAs per SM with 16 loader warps each (60 registers per thread)
 
 template <int GEOM>
 int dispatch_nt(const ConvTcParams &p, int max_n, cudaStream_t st) {
-    if (g_tc_wide_only < 0) {
-        const char *e = getenv("BX_TC_WIDE");
-        g_tc_wide_only = (e && e[0] == '1') ? 1 : 0;
+    if (g_tc_mode < 0) {
+        const char *e = getenv("BX_TC_MODE");
+        g_tc_mode = e ? atoi(e) : 0;
     }
-    if (p.Cout > 64) return launch_tc<GEOM, 128, 4, 2>(p, max_n, st);
-    if (g_tc_wide_only) {
-        if (p.Cout > 32) return launch_tc<GEOM, 64, 4, 2>(p, max_n, st);
-        return launch_tc<GEOM, 32, 4, 2>(p, max_n, st);
+    if (p.Cout > 64) return launch_tc<GEOM, 128, 4, 2, 1, 1>(p, max_n, st);
+    if (g_tc_mode == 1) {           // every layer one CTA per SM
+        if (p.Cout > 32) return launch_tc<GEOM, 64, 4, 2, 1, 1>(p, max_n, st);
+        return launch_tc<GEOM, 32, 4, 2, 1, 1>(p, max_n, st);
     }
-    if (p.Cout > 32) return launch_tc<GEOM, 64, 2, 1>(p, max_n, st);
-    return launch_tc<GEOM, 32, 2, 2>(p, max_n, st);
+    if (g_tc_mode == 2) {           // narrow layers: two CTAs per SM with 16 loader warps each (56 registers per thread)
+        if (p.Cout > 32) return launch_tc<GEOM, 64, 4, 2, 2, 0>(p, max_n, st);
+        return launch_tc<GEOM, 32, 4, 2, 2, 1>(p, max_n, st);
+    }
+    if (g_tc_mode == 3) {           // Cout 64: single main accumulator + separate cross accumulator (drain bubble)
+        if (p.Cout > 32) return launch_tc<GEOM, 64, 2, 1, 2, 1>(p, max_n, st);
+        return launch_tc<GEOM, 32, 2, 2, 2, 1>(p, max_n, st);
+    }
+    if (p.Cout > 32) return launch_tc<GEOM, 64, 2, 2, 2, 0>(p, max_n, st);
+    return launch_tc<GEOM, 32, 2, 2, 2, 1>(p, max_n, st);
 }
 
 }  // namespace
@@ -521,6 +599,16 @@ BX_API int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const 
     p.equi_s = equi_s; p.equi_t = equi_t; p.s_mids = s_mids; p.t_mids = t_mids;
     p.T = kd * kh * kw;
     p.seg_len = g_tc_max_stages;   // main-accumulator segment: 6 stages = 12 truncating accumulations
+#ifdef BX_TC_TRACE
+    static long long *d_trace = nullptr;
+    const char *te = getenv("BX_TC_TRACE");
+    const bool do_trace = te && atoi(te) == Cin * 1000 + Cout;
+    if (do_trace) {
+        if (!d_trace) cudaMalloc(&d_trace, sizeof(long long) * 4096);
+        cudaMemset(d_trace, 0, sizeof(long long) * 4096);
+        p.trace = d_trace;
+    }
+#endif
     cudaStream_t st = bx_stream(stream);
     switch (geom) {
         case BX_GEOM_CYL3D:
@@ -530,7 +618,31 @@ BX_API int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const 
         case BX_GEOM_CYL2D:
             BX_REQUIRE(in && D == 1 && H == 7 && W == 20 && kd == 1 && kh == 3 && kw == 3, "bx_conv_layer_tc: CYL2D expects [C,7,20], k=3x3");
             p.S_in = 140; p.S_out = 140; p.OD = 1; p.OH = 7; p.OW = 20;
+#ifdef BX_TC_TRACE
+            {   // debugging aid: BX_TC_TRACE=<Cin*1000+Cout> prints the stage timeline of the middle CTA of that layer once
+                const int rc = dispatch_nt<BX_GEOM_CYL2D>(p, n, st);
+                static int printed = 0;
+                if (do_trace && printed < 1) {
+                    ++printed;
+                    cudaDeviceSynchronize();
+                    static long long h[4096];
+                    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+                    const long long t00 = h[0];
+                    for (int g = 0; g < 4; ++g)
+                        for (int k = 0; k < 24; ++k) {
+                            const long long *r = h + (g * 64 + k) * 3;
+                            if (r[2]) printf("L g%d k%2d top %7lld  empty-wait %5lld  fill %5lld\n", g, k, r[0] - t00, r[1] - r[0], r[2] - r[1]);
+                        }
+                    const long long *m = h + 4 * 3 * 64;
+                    for (int it = 0; it < 72 && m[it * 3]; ++it)
+                        printf("M it%3d top %7lld (+%5lld)  acc/b-wait %5lld  a-wait %5lld\n", it, m[it * 3] - t00, it ? m[it * 3] - m[it * 3 - 3] : 0,
+                               m[it * 3 + 1] - m[it * 3], m[it * 3 + 2] - m[it * 3 + 1]);
+                }
+                return rc;
+            }
+#else
             return dispatch_nt<BX_GEOM_CYL2D>(p, n, st);
+#endif
         case BX_GEOM_VALID3D:
             BX_REQUIRE(in && D >= kd && H >= kh && W >= kw && kd >= 1 && kh >= 1 && kw >= 1, "bx_conv_layer_tc: VALID3D kernel larger than input");
             p.OD = D - kd + 1; p.OH = H - kh + 1; p.OW = W - kw + 1;
