@@ -24,6 +24,7 @@ Workloads (BASELINE.json ``configs``):
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -248,7 +249,10 @@ def make_pair(name: str = "C2", seed: int = 0, n_src: int | None = None, n_tgt: 
     }
 
 
-def init_synthetic_weights(model, seed: int = 123, logit_gain: float = 4.0):
+POSE_TRAINED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "pose_synth_trained.npz")
+
+
+def init_synthetic_weights(model, seed: int = 123, logit_gain: float = 4.0, trained_pose: bool = False):
     """Deterministic stand-in for the (unavailable offline) trained checkpoint.
 
     Seeded He-uniform initialisation of every Conv layer (variance preserving through the ReLU stacks:
@@ -276,6 +280,15 @@ def init_synthetic_weights(model, seed: int = 123, logit_gain: float = 4.0):
         last = model.Pose.conv.ops[27]
         last.weight.mul_(logit_gain)
         last.bias.mul_(logit_gain)
+        # trained_pose=True: CostNet fitted on synthetic pairs for exactly this seeded descriptor network
+        # (tests/tools/train_costnet.py, pairs disjoint from the bench / test pairs): with it the synthetic C2 pairs
+        # actually register (RRE ~1.7 deg, RTE ~5 cm against the ground truth, ~40 consensus inliers instead of ~6),
+        # so the consensus / RANSAC / refinement stages see a meaningful problem.  Only valid for the default seed.
+        if trained_pose and seed == 123 and os.path.exists(POSE_TRAINED):
+            z = np.load(POSE_TRAINED)
+            sd = model.state_dict()
+            for k in z.files:
+                sd[k].copy_(torch.from_numpy(z[k]))
     model.eval()
     for m in model.modules():
         if hasattr(m, "invalidate"):

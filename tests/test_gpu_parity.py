@@ -328,7 +328,7 @@ def _compare_pair(model, sd, cfg, data, perms, oracle, name):
             rel = np.abs(d - od).max(1) / np.where(den > 0, den, 1)
             # 1e-4 relative (north_star).  A handful of descriptors are ill-conditioned (attention pooling with a
             # near-zero pooled vector before the L2 normalisation): even the pure-fp32 CUDA-core kernel, i.e. the
-            # reference's arithmetic in another summation order, misses 1e-4 on them (tools/desc_error.py on C3:
+            # reference's arithmetic in another summation order, misses 1e-4 on them (tests/tools/desc_error.py on C3:
             # fp32 FFMA max 1.42e-4, tensor-core path max 1.03e-4, both 99.99 % < 1e-4).  Hence: 99.9 % within
             # 1e-4 and nothing beyond 5e-4.
             assert (rel < 1e-4).mean() >= 0.999 and rel.max() < 5e-4, \
@@ -399,6 +399,25 @@ def test_batched_descriptor_pass_equals_per_scale_pass(dev, oracle):
         for j, side in ((0, "s"), (1, "t")):
             o = outs[2 * i + j]
             assert (o["desc"] == sc[side]["desc"]).all() and (o["equi"] == sc[side]["equi"]).all() and (o["R"] == sc[side]["R"]).all()
+    model.cpu()
+
+
+def test_c2_pair_registers_with_fitted_costnet(dev):
+    """With the CostNet fitted on disjoint synthetic pairs (tests/tools/train_costnet.py) the C2 pairs register: the
+    GPU pose meets the reference's 3DMatch success criterion (RRE < 15 deg, RTE < 0.3 m) against the ground truth."""
+    import bufferx_b200 as bx
+    from bufferx_b200.se3 import compute_rre, compute_rte
+    from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
+    cfg = workload_cfg("C2")
+    model = init_synthetic_weights(bx.BufferX(cfg), trained_pose=True).to(dev)
+    for seed in (0, 3):
+        data = make_pair("C2", seed)
+        np.random.seed(seed)
+        with torch.no_grad():
+            pose, _, ninl, nmut, nind, su = model(data, ransac_seed=0)
+        rre, rte = compute_rre(pose, data["relt_pose"]), compute_rte(pose, data["relt_pose"])
+        assert rre < 15.0 and rte < 0.3, f"C2 seed {seed}: RRE {rre:.2f} deg RTE {rte:.3f} m (consensus {nind}, inliers {ninl})"
+        assert nind >= 15
     model.cpu()
 
 

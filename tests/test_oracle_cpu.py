@@ -325,12 +325,14 @@ def test_product_has_no_cpu_path():
 
 
 def test_product_never_imports_oracle():
-    pkg = os.path.join(ROOT, "buffer-x_b200")
-    for d, _, fs in os.walk(pkg):
-        for f in fs:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                txt = open(os.path.join(d, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+    """oracle/ is test infrastructure: nothing in the package or in tools/ may import it (tests/, smoke() and the CPU
+    legs of bench.py are the only users)."""
+    for top in ("buffer-x_b200", "tools"):
+        for d, _, fs in os.walk(os.path.join(ROOT, top)):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    txt = open(os.path.join(d, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
 
 
 def test_library_exports_every_declared_symbol():
@@ -394,3 +396,25 @@ def test_grid_subsample_restatement_equals_reference_cpp(oracle):
         srt = lambda x: x[np.lexsort((x[:, 2], x[:, 1], x[:, 0]))]
         assert len(keys) == len(ref) and np.array_equal(srt(xyz), srt(ref))   # same barycentres, bit for bit
         assert cnt.sum() == len(pts) and (np.diff(keys.astype(np.int64)) > 0).all()
+
+
+def test_fitted_costnet_fixture_matches_the_model():
+    """buffer-x_b200/data/pose_synth_trained.npz holds exactly the floating-point Pose.conv.* tensors of the model and
+    init_synthetic_weights(trained_pose=True) changes nothing else."""
+    import bufferx_b200 as bx
+    from bufferx_b200.synth import POSE_TRAINED, init_synthetic_weights, workload_cfg
+    cfg = workload_cfg("C1")
+    a = init_synthetic_weights(bx.BufferX(cfg)).state_dict()
+    b = init_synthetic_weights(bx.BufferX(cfg), trained_pose=True).state_dict()
+    z = np.load(POSE_TRAINED)
+    assert set(z.files) == {k for k in a if k.startswith("Pose.conv.") and a[k].dtype.is_floating_point}
+    changed = 0
+    for k in a:
+        same = bool((a[k] == b[k]).all())
+        if k in z.files:
+            assert tuple(z[k].shape) == tuple(a[k].shape)
+            assert bool((b[k] == torch.from_numpy(z[k])).all())
+            changed += (not same)
+        else:
+            assert same, k
+    assert changed >= 10          # the ten conv layers were re-fitted

@@ -1,8 +1,8 @@
 """GPU experiment: per-descriptor relative error of the CUDA path against the CPU oracle for both conv kernels.
-    BX_CONV=tc|ffma python tools/desc_error.py C3"""
+    BX_CONV=tc|ffma python tests/tools/desc_error.py C3"""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bufferx_b200 as bx
 from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
 from oracle import oracle as O
