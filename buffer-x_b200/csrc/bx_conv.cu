@@ -285,75 +285,98 @@ pool_desc_kernel(const float *__restrict__ x, int K, int C, int S, int channels_
 // : 60 + 54 output positions per match instead of 972 (27 MMAC -> 1.4 MMAC per match).  The next layer's loader
 // (BX_GEOM_COSTAB) regenerates out0 from A and B, so neither the 256 KB cost volume nor the 124 KB first activation
 // of a match is ever written.  One CTA per match; d1/d2 rows 1..5 staged in shared memory, weights through L1.
-constexpr int AB_T = 256;
+constexpr int AB_T = 512;            // two matches at a time, 256 threads each
+constexpr int AB_WA = 32 * 3 * 5 * 32, AB_WB = 32 * 3 * 3 * 32;
+constexpr int AB_SMEM = (AB_WA + AB_WB + 2 * 2 * 3200) * (int)sizeof(float);
 
-__global__ void __launch_bounds__(AB_T)
+// Persistent CTAs (one per SM): the 98 KB of factor weights stay in shared memory; every thread owns 8 output channels
+// at two positions of one match (one weight fetch feeds 16 FMAs).  A and B are written channel-blocked
+// ([32/4][positions][4]) so that the consumer (BX_GEOM_COSTAB loader) reads them with 16-byte loads.
+__global__ void __launch_bounds__(AB_T, 1)
 costvol_ab_kernel(const float *__restrict__ equi_s, const float *__restrict__ equi_t, const int *__restrict__ s_mids,
                   const int *__restrict__ t_mids, const int *__restrict__ d_M, const float *__restrict__ wa,
                   const float *__restrict__ wb, const float *__restrict__ bias, float *__restrict__ A, float *__restrict__ B) {
-    __shared__ float d1[32 * 100], d2[32 * 100];   // [c][row 1..5][20]
-    const int m = blockIdx.x;
-    if (m >= *d_M) return;
-    const int tid = threadIdx.x;
-    const float *e1 = equi_s + (size_t)s_mids[m] * 32 * 140, *e2 = equi_t + (size_t)t_mids[m] * 32 * 140;
-    for (int i = tid; i < 3200; i += AB_T) {
-        const int c = i / 100, r = i - c * 100;
-        d1[i] = __ldg(e1 + c * 140 + 20 + r);
-        d2[i] = __ldg(e2 + c * 140 + 20 + r);
-    }
-    __syncthreads();
-    // items: [cg(4)][pos]: 4 x 60 for A, then 4 x 54 for B; 8 output channels each
-    for (int item = tid; item < 4 * 60 + 4 * 54; item += AB_T) {
-        float acc[8];
-        if (item < 240) {
-            const int cg = item / 60, pos = item - cg * 60, k = pos / 20, mm = pos - k * 20;
+    extern __shared__ __align__(16) float ab_smem[];
+    float *swa = ab_smem, *swb = swa + AB_WA, *sd = swb + AB_WB;   // sd: [half(2)][d1 | d2][32][100]
+    const int M = *d_M;
+    const int tid = threadIdx.x, half = tid >> 8, ht = tid & 255;
+    if ((int)blockIdx.x * 2 >= M) return;
+    for (int i = tid; i < AB_WA / 4; i += AB_T) reinterpret_cast<float4 *>(swa)[i] = __ldg(reinterpret_cast<const float4 *>(wa) + i);
+    for (int i = tid; i < AB_WB / 4; i += AB_T) reinterpret_cast<float4 *>(swb)[i] = __ldg(reinterpret_cast<const float4 *>(wb) + i);
+    float *d1 = sd + half * 6400, *d2 = d1 + 3200;
+    for (int m0 = (int)blockIdx.x * 2; m0 < M; m0 += (int)gridDim.x * 2) {
+        const int m = m0 + half;
+        __syncthreads();                       // previous round's readers are done (also covers the weight fill)
+        if (m < M) {
+            const float *e1 = equi_s + (size_t)s_mids[m] * 32 * 140, *e2 = equi_t + (size_t)t_mids[m] * 32 * 140;
+            for (int i = ht; i < 3200; i += 256) {
+                const int c = i / 100, r = i - c * 100;
+                d1[i] = __ldg(e1 + c * 140 + 20 + r);       // elevation rows 1..5
+                d2[i] = __ldg(e2 + c * 140 + 20 + r);
+            }
+        }
+        __syncthreads();
+        if (m >= M) continue;
+        float acc0[8], acc1[8];
+        if (ht < 120) {                        // A: cg(4) x k(3) x mm(10): positions (k, mm) and (k, mm + 10)
+            const int cg = ht / 30, r = ht - cg * 30, k = r / 10, mm = r - k * 10;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + cg * 8 + j);
-            int col[5];
+            for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = __ldg(bias + cg * 8 + j);
+            int c0[5], c1[5];
 #pragma unroll
             for (int e = 0; e < 5; ++e) {
                 int x = mm + e - 2;
-                col[e] = x < 0 ? x + 20 : (x >= 20 ? x - 20 : x);
+                c0[e] = x < 0 ? x + 20 : x;                 // mm + e - 2 in [-2, 11]
+                x = mm + 10 + e - 2;
+                c1[e] = x >= 20 ? x - 20 : x;               // in [8, 21]
             }
             for (int c = 0; c < 32; ++c) {
 #pragma unroll
                 for (int dk = 0; dk < 3; ++dk) {
                     const float *row = d1 + c * 100 + (k + dk) * 20;
-                    const float4 *wp = reinterpret_cast<const float4 *>(wa + ((size_t)(c * 3 + dk) * 5) * 32 + cg * 8);
+                    const float4 *wp = reinterpret_cast<const float4 *>(swa + ((c * 3 + dk) * 5) * 32 + cg * 8);
 #pragma unroll
                     for (int e = 0; e < 5; ++e) {
-                        const float x = row[col[e]];
-                        const float4 w0 = __ldg(wp + e * 8), w1 = __ldg(wp + e * 8 + 1);
-                        acc[0] += x * w0.x; acc[1] += x * w0.y; acc[2] += x * w0.z; acc[3] += x * w0.w;
-                        acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
+                        const float x0 = row[c0[e]], x1 = row[c1[e]];
+                        const float4 w0 = wp[e * 8], w1 = wp[e * 8 + 1];
+                        acc0[0] += x0 * w0.x; acc0[1] += x0 * w0.y; acc0[2] += x0 * w0.z; acc0[3] += x0 * w0.w;
+                        acc0[4] += x0 * w1.x; acc0[5] += x0 * w1.y; acc0[6] += x0 * w1.z; acc0[7] += x0 * w1.w;
+                        acc1[0] += x1 * w0.x; acc1[1] += x1 * w0.y; acc1[2] += x1 * w0.z; acc1[3] += x1 * w0.w;
+                        acc1[4] += x1 * w1.x; acc1[5] += x1 * w1.y; acc1[6] += x1 * w1.z; acc1[7] += x1 * w1.w;
                     }
                 }
             }
-            float *o = A + ((size_t)m * 32 + cg * 8) * 60 + pos;
+            float4 *o = reinterpret_cast<float4 *>(A) + ((size_t)m * 8 + cg * 2) * 60 + k * 20 + mm;
+            o[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+            o[60] = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+            o[10] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+            o[70] = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+        } else if (ht < 120 + 108) {           // B: cg(4) x k(3) x l(9): positions (k, l) and (k, l + 9)
+            const int it2 = ht - 120;
+            const int cg = it2 / 27, r = it2 - cg * 27, k = r / 9, l = r - k * 9;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j * 60] = acc[j];
-        } else {
-            const int it2 = item - 240;
-            const int cg = it2 / 54, pos = it2 - cg * 54, k = pos / 18, l = pos - k * 18;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+            for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0f;
             for (int c = 0; c < 32; ++c) {
 #pragma unroll
                 for (int dk = 0; dk < 3; ++dk) {
                     const float *row = d2 + c * 100 + (k + dk) * 20 + l;
-                    const float4 *wp = reinterpret_cast<const float4 *>(wb + ((size_t)(c * 3 + dk) * 3) * 32 + cg * 8);
+                    const float4 *wp = reinterpret_cast<const float4 *>(swb + ((c * 3 + dk) * 3) * 32 + cg * 8);
 #pragma unroll
                     for (int dl = 0; dl < 3; ++dl) {
-                        const float x = row[dl];
-                        const float4 w0 = __ldg(wp + dl * 8), w1 = __ldg(wp + dl * 8 + 1);
-                        acc[0] += x * w0.x; acc[1] += x * w0.y; acc[2] += x * w0.z; acc[3] += x * w0.w;
-                        acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
+                        const float x0 = row[dl], x1 = row[dl + 9];
+                        const float4 w0 = wp[dl * 8], w1 = wp[dl * 8 + 1];
+                        acc0[0] += x0 * w0.x; acc0[1] += x0 * w0.y; acc0[2] += x0 * w0.z; acc0[3] += x0 * w0.w;
+                        acc0[4] += x0 * w1.x; acc0[5] += x0 * w1.y; acc0[6] += x0 * w1.z; acc0[7] += x0 * w1.w;
+                        acc1[0] += x1 * w0.x; acc1[1] += x1 * w0.y; acc1[2] += x1 * w0.z; acc1[3] += x1 * w0.w;
+                        acc1[4] += x1 * w1.x; acc1[5] += x1 * w1.y; acc1[6] += x1 * w1.z; acc1[7] += x1 * w1.w;
                     }
                 }
             }
-            float *o = B + ((size_t)m * 32 + cg * 8) * 54 + pos;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j * 54] = acc[j];
+            float4 *o = reinterpret_cast<float4 *>(B) + ((size_t)m * 8 + cg * 2) * 54 + k * 18 + l;
+            o[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+            o[54] = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+            o[9] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+            o[63] = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
         }
     }
 }
@@ -416,7 +439,20 @@ BX_API int bx_costvol_ab(const float *equi_s, const float *equi_t, const int32_t
     BX_REQUIRE(maxM >= 0, "bx_costvol_ab: bad maxM");
     BX_REQUIRE(((reinterpret_cast<uintptr_t>(wa) | reinterpret_cast<uintptr_t>(wb)) & 15) == 0, "bx_costvol_ab: weights must be 16-byte aligned");
     if (maxM == 0) return BX_OK;
-    costvol_ab_kernel<<<maxM, AB_T, 0, bx_stream(stream)>>>(equi_s, equi_t, s_mids, t_mids, d_M, wa, wb, bias, A, B);
+    BX_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0, "bx_costvol_ab: A and B must be 16-byte aligned");
+    static bool attr_done = false;
+    if (!attr_done) {
+        BX_CUDA(cudaFuncSetAttribute(costvol_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+        attr_done = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        BX_CUDA(cudaGetDevice(&dev));
+        BX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = (maxM + 1) / 2 < sms ? (maxM + 1) / 2 : sms;
+    costvol_ab_kernel<<<grid, AB_T, AB_SMEM, bx_stream(stream)>>>(equi_s, equi_t, s_mids, t_mids, d_M, wa, wb, bias, A, B);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

@@ -265,12 +265,12 @@ __global__ void __launch_bounds__(LG * 128 + 64, MINB) conv_tc_kernel(const Conv
                 pb = p.equi_t + (size_t)p.t_mids[ln] * 32 * 140;
             }
         } else if (GEOM == BX_GEOM_COSTAB) {
-            pa = p.equi_s + (size_t)ln * 32 * 60;     // A [32][3][20]
-            pb = p.equi_t + (size_t)ln * 32 * 54;     // B [32][3][18]
+            pa = p.equi_s + (size_t)ln * 32 * 60;     // A, channel-blocked [8][3*20][4]
+            pb = p.equi_t + (size_t)ln * 32 * 54;     // B, channel-blocked [8][3*18][4]
         } else {
             pa = p.in + (size_t)ln * p.S_in * p.Cin;      // activations are channel-blocked: [n][Cin/4][position][4]
         }
-        constexpr int cstride = (GEOM == BX_GEOM_COSTVOL) ? 140 : 60;   // channel-first factor maps of the two cost-volume loaders
+        constexpr int cstride = 140;   // channel-first equivariant maps of the direct cost-volume loader
         // (chunk, tap) of the stage this group fills next; the tap geometry comes from the shared table
         int chunk = grp / p.T, t = grp - chunk * p.T;
         auto advance_lg = [&]() {
@@ -307,16 +307,23 @@ __global__ void __launch_bounds__(LG * 128 + 64, MINB) conv_tc_kernel(const Conv
                 offB = kk * 18 + ll;
             }
             const int c0 = chunk * 16;
-            if (GEOM == BX_GEOM_COSTVOL || GEOM == BX_GEOM_COSTAB) {
+            if (GEOM == BX_GEOM_COSTVOL) {
                 const float *src = pa + (size_t)c0 * cstride + offA;
 #pragma unroll
                 for (int kk = 0; kk < 16; ++kk) {
                     float v = 0.0f;
-                    if (ok) {
-                        if (GEOM == BX_GEOM_COSTVOL) v = src[kk * cstride] - pb[(size_t)(c0 + kk) * 140 + offB];
-                        else v = fmaxf(__ldg(src + kk * cstride) - __ldg(pb + (c0 + kk) * 54 + offB), 0.0f);
-                    }
+                    if (ok) v = src[kk * cstride] - pb[(size_t)(c0 + kk) * 140 + offB];
                     a_reg[kk] = v;
+                }
+            } else if (GEOM == BX_GEOM_COSTAB) {   // relu(A - B) from the channel-blocked factors: 2 x four 16-byte loads
+                const float4 *sa = reinterpret_cast<const float4 *>(pa) + (chunk * 4) * 60 + offA;
+                const float4 *sb4 = reinterpret_cast<const float4 *>(pb) + (chunk * 4) * 54 + offB;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va;
+                    if (ok) { va = __ldg(sa + q * 60); vb = __ldg(sb4 + q * 54); }
+                    a_reg[4 * q] = fmaxf(va.x - vb.x, 0.0f); a_reg[4 * q + 1] = fmaxf(va.y - vb.y, 0.0f);
+                    a_reg[4 * q + 2] = fmaxf(va.z - vb.z, 0.0f); a_reg[4 * q + 3] = fmaxf(va.w - vb.w, 0.0f);
                 }
             } else {  // four 16-byte loads, one per group of 4 channels; a warp's 32 rows read 512 contiguous bytes each
                 const float4 *src = reinterpret_cast<const float4 *>(pa) + (size_t)(chunk * 4) * p.S_in + offA;

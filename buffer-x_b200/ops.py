@@ -338,12 +338,12 @@ def costvol_factor_weights(Wt: torch.Tensor):
 
 
 def costvol_ab(equi_s, equi_t, s_mids, t_mids, d_M, maxM, wa, wb, bias, A=None, B=None):
-    """Factors of the first CostNet activation: out0 = relu(A[co][k][(l-n) mod 20] - B[co][k][l])."""
+    """Factors of the first CostNet activation: out0 = relu(A[co][k][(l-n) mod 20] - B[co][k][l]); A, B channel-blocked."""
     dev = equi_s.device
     if A is None:
-        A = torch.empty((maxM, 32, 3, 20), dtype=F32, device=dev)
+        A = torch.empty((maxM, 8, 60, 4), dtype=F32, device=dev)      # channel-blocked [32/4][3*20][4]
     if B is None:
-        B = torch.empty((maxM, 32, 3, 18), dtype=F32, device=dev)
+        B = torch.empty((maxM, 8, 54, 4), dtype=F32, device=dev)      # channel-blocked [32/4][3*18][4]
     with _Span("conv_cost"):
         _check(load_library().bx_costvol_ab(_dp(equi_s, F32, "equi_s"), _dp(equi_t, F32, "equi_t"), _dp(s_mids, I32, "s_mids"),
                                             _dp(t_mids, I32, "t_mids"), _dp(d_M, I32, "d_M"), int(maxM), _dp(wa, F32, "wa"), _dp(wb, F32, "wb"),

@@ -108,8 +108,8 @@ int bx_spt_pnt(const float *delta, int K, int P, const float *voxels, int V, int
 #define BX_GEOM_VALID3D 2  /* in [C,D,H,W]  -> out [C,D-kd+1,H-kh+1,W-kw+1] */
 #define BX_GEOM_COSTVOL 3  /* VALID3D 3x3x3 whose input is the on-the-fly cost volume (models/BUFFERX.py:51-65) */
 #define BX_GEOM_COSTAB 4   /* VALID3D 3x3x3 on [32,18,3,18] whose input is the first CostNet activation regenerated from
-                              bx_costvol_ab's factors: relu(A[c][k][(l-n) mod 20] - B[c][k][l]); equi_s = A [n][32][3][20],
-                              equi_t = B [n][32][3][18], s_mids/t_mids unused (bx_conv_layer_tc only) */
+                              bx_costvol_ab's factors: relu(A[c][k][(l-n) mod 20] - B[c][k][l]); equi_s = A, equi_t = B
+                              (channel-blocked [n][8][3*20][4] / [n][8][3*18][4]), s_mids/t_mids unused (bx_conv_layer_tc only) */
 int bx_conv_layer(int geom, const float *in, const float *w, const float *bias, float *out, int n, const int32_t *d_n,
                   int Cin, int Cout, int D, int H, int W, int kd, int kh, int kw, int relu,
                   const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
@@ -134,7 +134,8 @@ int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const float *
  * the layer is linear before its ReLU, so out0[co][n][k][l] = relu(A[co][k][(l-n) mod 20] - B[co][k][l]) with
  * A/B small convolutions of the source/target equivariant maps (60 + 54 positions per match instead of 972).
  * wa: [32 c][3 dk][5 e][32 co] = sum over (dn,dl) with dl-dn = e-2 of the folded weight; wb: [32][3][3 dl][32] = sum
- * over dn; bias [32] is added into A.  A: [maxM][32][3][20], B: [maxM][32][3][18]; rows >= *d_M untouched. */
+ * over dn; bias [32] is added into A.  A: [maxM][8][3*20][4], B: [maxM][8][3*18][4] (channel-blocked like the
+ * activations of bx_conv_layer_tc; 16-byte aligned); rows >= *d_M untouched. */
 int bx_costvol_ab(const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
                   const int32_t *d_M, int maxM, const float *wa, const float *wb, const float *bias, float *A,
                   float *B, void *stream);

@@ -571,10 +571,11 @@ def test_cost_volume_factorised_first_layer(dev, oracle, c1):
     a1 = torch.zeros((M, 64, 256), device=dev)
     ops.conv_layer(ops.GEOM_VALID3D, a0, L1["w"], L1["b"], a1, M, 32, 64, 18, 3, 18, 3, 3, 3, True, d_n=dM)
     wa, wb = ops.costvol_factor_weights(L0["w"])
-    A = torch.zeros((M, 32, 3, 20), device=dev)
-    B = torch.zeros((M, 32, 3, 18), device=dev)
-    ops.costvol_ab(es, et, sm, tm, dM, M, wa, wb, L0["b"], A, B)
-    assert (A[M - 2:] == 0).all() and (B[M - 2:] == 0).all()        # rows beyond the device-side count are untouched
+    Ab = torch.zeros((M, 8, 60, 4), device=dev)                      # channel-blocked factors
+    Bb = torch.zeros((M, 8, 54, 4), device=dev)
+    ops.costvol_ab(es, et, sm, tm, dM, M, wa, wb, L0["b"], Ab, Bb)
+    assert (Ab[M - 2:] == 0).all() and (Bb[M - 2:] == 0).all()      # rows beyond the device-side count are untouched
+    A, B = ops.from_blocked(Ab).view(M, 32, 3, 20), ops.from_blocked(Bb).view(M, 32, 3, 18)
     # rebuild the first activation from the factors on the host: out0[n,k,l] = relu(A[k,(l-n) mod 20] - B[k,l])
     n = torch.arange(18, device=dev).view(18, 1, 1)
     l = torch.arange(18, device=dev).view(1, 1, 18)
@@ -584,7 +585,7 @@ def test_cost_volume_factorised_first_layer(dev, oracle, c1):
     ref0 = a0.cpu().numpy()[: M - 2]
     assert np.abs(re0.cpu().numpy()[: M - 2] - ref0).max() < 2e-5 * max(1.0, np.abs(ref0).max())
     b1 = torch.zeros((M, 16, 256, 4), device=dev)                     # channel-blocked
-    ops.conv_layer_tc(ops.GEOM_COSTAB, None, L1["w_tc"], L1["b"], b1, M, 32, 64, 18, 3, 18, 3, 3, 3, True, d_n=dM, equi_s=A, equi_t=B)
+    ops.conv_layer_tc(ops.GEOM_COSTAB, None, L1["w_tc"], L1["b"], b1, M, 32, 64, 18, 3, 18, 3, 3, 3, True, d_n=dM, equi_s=Ab, equi_t=Bb)
     assert (b1[M - 2:] == 0).all()
     assert relerr(ops.from_blocked(b1).cpu().numpy(), a1.cpu().numpy()) < 2e-5
     model.cpu()
