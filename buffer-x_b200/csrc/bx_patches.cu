@@ -26,50 +26,92 @@ __global__ void permute_cloud_kernel(const float *__restrict__ pts, const int *_
     out[i] = make_float4(pts[3 * (size_t)s], pts[3 * (size_t)s + 1], pts[3 * (size_t)s + 2], 0.0f);
 }
 
-// One warp per key-point.  UN = points tested per lane per step.
-constexpr int SP_WARPS = 8;
-constexpr int UN = 4;
+// SP_KP key-points per CTA, SP_SPLIT warps per key-point.  The cloud is streamed through shared memory in chunks of
+// SP_CH points; the SP_SPLIT warps of a key-point scan consecutive quarters of a chunk, exchange their hit counts
+// through shared memory and write their hits at the ordered offsets -- the serial scan of one warp per key-point was a
+// ~100 K-cycle dependent chain with 10 warps per SM; splitting it four ways (and keeping 16 warps per CTA) cuts the
+// chain and raises the occupancy.  The scan order, and with it every index and coordinate, is unchanged.
+constexpr int SP_KP = 4;
+constexpr int SP_SPLIT = 4;
+constexpr int SP_WARPS = SP_KP * SP_SPLIT;
+constexpr int SP_CH = 2048;
+constexpr int SP_SUB = SP_CH / SP_SPLIT;      // points of a chunk scanned by one warp
+constexpr int SP_STEPS = SP_SUB / 32;         // ballots per warp and chunk
+constexpr int BQ_WARPS = 8;
 
 __global__ void __launch_bounds__(SP_WARPS * 32)
 select_patches_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ kpts, int K, float radius,
                       const float *__restrict__ d_radius, int P, int *__restrict__ idx, float *__restrict__ patches) {
-    const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
-    if (k >= K) return;
+    __shared__ float4 tile[SP_CH];
+    __shared__ int s_cnt[SP_KP][SP_SPLIT], s_first[SP_KP][SP_SPLIT];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kl = warp / SP_SPLIT, part = warp % SP_SPLIT;      // key-point of the CTA, quarter of the chunk
+    const int k = blockIdx.x * SP_KP + kl;
+    const bool valid = k < K;
+    const int kk = valid ? k : K - 1;
     const float r = d_radius ? *d_radius : radius;
     const float r2 = r * r;
-    const float qx = kpts[3 * (size_t)k], qy = kpts[3 * (size_t)k + 1], qz = kpts[3 * (size_t)k + 2];
-    int *row = idx ? idx + (size_t)k * P : nullptr;
-    float *out = patches + (size_t)k * P * 3;
-    int cnt = 0, first = 0;
-    for (int base = 0; base < N && cnt < P; base += 32 * UN) {
-        float4 p[UN];
+    const float qx = kpts[3 * (size_t)kk], qy = kpts[3 * (size_t)kk + 1], qz = kpts[3 * (size_t)kk + 2];
+    int *row = idx ? idx + (size_t)kk * P : nullptr;
+    float *out = patches + (size_t)kk * P * 3;
+    int cnt = 0, first = 0;                    // hits of the key-point so far / index of its first hit (same in its 4 warps)
+    bool done = !valid;
+    for (int base0 = 0; base0 < N; base0 += SP_CH) {
+        for (int i = tid; i < SP_CH; i += SP_WARPS * 32)
+            tile[i] = (base0 + i < N) ? pts4[base0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        const int lim = min(SP_CH, N - base0);
+        unsigned masks[SP_STEPS];
+        int c_w = 0, f_w = 0x7fffffff;
+        if (!done) {
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const int i = base + u * 32 + lane;
-            p[u] = (i < N) ? pts4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const int i = base + u * 32 + lane;
-            const float d2 = bx_d2(qx - p[u].x, qy - p[u].y, qz - p[u].z);
-            const bool hit = (i < N) && (d2 < r2);
-            const unsigned m = __ballot_sync(BX_FULL, hit);
-            if (m) {
-                if (cnt == 0) first = base + u * 32 + (__ffs(m) - 1);
-                const int slot = cnt + __popc(m & ((1u << lane) - 1u));
-                if (hit && slot < P) {
-                    if (row) row[slot] = i;
-                    // slot P-1 always holds the key-point itself (patch_embedder.py:109)
-                    const bool centre = (slot == P - 1);
-                    out[3 * slot] = centre ? qx : p[u].x;
-                    out[3 * slot + 1] = centre ? qy : p[u].y;
-                    out[3 * slot + 2] = centre ? qz : p[u].z;
-                }
-                cnt += __popc(m);
+            for (int st = 0; st < SP_STEPS; ++st) {
+                const int j = part * SP_SUB + st * 32 + lane;
+                const float4 p = tile[j];
+                const float d2 = bx_d2(qx - p.x, qy - p.y, qz - p.z);
+                const unsigned m = __ballot_sync(BX_FULL, (j < lim) && (d2 < r2));
+                masks[st] = m;
+                if (m && c_w == 0) f_w = base0 + part * SP_SUB + st * 32 + (__ffs(m) - 1);
+                c_w += __popc(m);
             }
+            if (lane == 0) { s_cnt[kl][part] = c_w; s_first[kl][part] = f_w; }
         }
+        __syncthreads();
+        if (!done) {
+            int off = cnt, tot = 0;
+#pragma unroll
+            for (int w = 0; w < SP_SPLIT; ++w) {
+                const int c = s_cnt[kl][w];
+                if (w < part) off += c;
+                if (cnt == 0 && tot == 0 && c > 0) first = s_first[kl][w];
+                tot += c;
+            }
+            if (c_w > 0 && off < P) {
+#pragma unroll
+                for (int st = 0; st < SP_STEPS; ++st) {
+                    const unsigned m = masks[st];
+                    if (m) {
+                        const int slot = off + __popc(m & ((1u << lane) - 1u));
+                        if (((m >> lane) & 1u) && slot < P) {
+                            const int j = part * SP_SUB + st * 32 + lane;
+                            const float4 p = tile[j];
+                            if (row) row[slot] = base0 + j;
+                            // slot P-1 always holds the key-point itself (patch_embedder.py:109)
+                            const bool centre = (slot == P - 1);
+                            out[3 * slot] = centre ? qx : p.x;
+                            out[3 * slot + 1] = centre ? qy : p.y;
+                            out[3 * slot + 2] = centre ? qz : p.z;
+                        }
+                        off += __popc(m);
+                    }
+                }
+            }
+            cnt += tot;
+            if (cnt >= P) done = true;
+        }
+        if (!__syncthreads_or(!done)) break;    // barrier: tile / counters may be overwritten; all key-points full -> stop
     }
+    if (!valid || part != 0) return;
     if (cnt > P) cnt = P;
     // padding: ball_query repeats the first hit; the fix-up replaces those slots by the key-point.
     // No hit at all: index row = 0, slot 0 = point 0 of the permuted cloud, every other slot = key-point.
@@ -87,11 +129,11 @@ select_patches_kernel(const float4 *__restrict__ pts4, int N, const float *__res
 }
 
 // plain ordered ball query over a packed [n,3] cloud (pointnet2_ops.ball_query semantics)
-__global__ void __launch_bounds__(SP_WARPS * 32)
+__global__ void __launch_bounds__(BQ_WARPS * 32)
 ball_query_kernel(const float *__restrict__ xyz, int n, const float *__restrict__ qry, int m, float radius, int nsample,
                   int *__restrict__ idx) {
     const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
+    const int j = blockIdx.x * BQ_WARPS + (threadIdx.x >> 5);
     if (j >= m) return;
     const float r2 = radius * radius;
     const float qx = qry[3 * (size_t)j], qy = qry[3 * (size_t)j + 1], qz = qry[3 * (size_t)j + 2];
@@ -252,7 +294,7 @@ BX_API int bx_select_patches(const float *pts4, int N, const float *kpts, int K,
     BX_REQUIRE(N >= 1 && K >= 0 && P >= 1, "bx_select_patches: bad sizes N=%d K=%d P=%d", N, K, P);
     BX_REQUIRE((reinterpret_cast<uintptr_t>(pts4) & 15) == 0, "bx_select_patches: pts4 must be 16-byte aligned");
     if (K == 0) return BX_OK;
-    select_patches_kernel<<<(K + SP_WARPS - 1) / SP_WARPS, SP_WARPS * 32, 0, bx_stream(stream)>>>(
+    select_patches_kernel<<<(K + SP_KP - 1) / SP_KP, SP_WARPS * 32, 0, bx_stream(stream)>>>(
         reinterpret_cast<const float4 *>(pts4), N, kpts, K, radius, d_radius, P, idx, patches);
     BX_LAUNCH_CHECK();
     return BX_OK;
@@ -262,7 +304,7 @@ BX_API int bx_ball_query(const float *xyz, int n, const float *qry, int m, float
                          void *stream) {
     BX_REQUIRE(xyz && qry && idx && n >= 1 && m >= 0 && nsample >= 1, "bx_ball_query: bad arguments");
     if (m == 0) return BX_OK;
-    ball_query_kernel<<<(m + SP_WARPS - 1) / SP_WARPS, SP_WARPS * 32, 0, bx_stream(stream)>>>(xyz, n, qry, m, radius,
+    ball_query_kernel<<<(m + BQ_WARPS - 1) / BQ_WARPS, BQ_WARPS * 32, 0, bx_stream(stream)>>>(xyz, n, qry, m, radius,
                                                                                                 nsample, idx);
     BX_LAUNCH_CHECK();
     return BX_OK;
