@@ -56,10 +56,22 @@ select_patches_kernel(const float4 *__restrict__ pts4, int N, const float *__res
     float *out = patches + (size_t)kk * P * 3;
     int cnt = 0, first = 0;                    // hits of the key-point so far / index of its first hit (same in its 4 warps)
     bool done = !valid;
+    constexpr int LD = SP_CH / (SP_WARPS * 32);          // float4 loads per thread and chunk
+    float4 stage[LD];                                    // the next chunk travels through registers: its L2 latency
+#pragma unroll                                           // overlaps the scan of the current one
+    for (int q = 0; q < LD; ++q) {
+        const int i = q * SP_WARPS * 32 + tid;
+        stage[q] = (i < N) ? __ldg(pts4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     for (int base0 = 0; base0 < N; base0 += SP_CH) {
-        for (int i = tid; i < SP_CH; i += SP_WARPS * 32)
-            tile[i] = (base0 + i < N) ? pts4[base0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < LD; ++q) tile[q * SP_WARPS * 32 + tid] = stage[q];
         __syncthreads();
+#pragma unroll
+        for (int q = 0; q < LD; ++q) {
+            const int i = base0 + SP_CH + q * SP_WARPS * 32 + tid;
+            stage[q] = (i < N) ? __ldg(pts4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         const int lim = min(SP_CH, N - base0);
         unsigned masks[SP_STEPS];
         int c_w = 0, f_w = 0x7fffffff;
