@@ -421,6 +421,29 @@ def test_c2_pair_registers_with_fitted_costnet(dev):
     model.cpu()
 
 
+def test_degenerate_pair_unrelated_clouds(dev, oracle):
+    """Two unrelated clouds (a plane patch and a sphere shell, metres apart): a handful of mutual matches, a consensus
+    set of at most one member, fewer than three RANSAC correspondences -> identity pose with 0 inliers, exactly like
+    the oracle; nothing may crash on the empty / near-empty device-side lists."""
+    import bufferx_b200 as bx
+    from bufferx_b200.synth import init_synthetic_weights, workload_cfg
+    cfg = workload_cfg("C1")
+    model = init_synthetic_weights(bx.BufferX(cfg))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    rng = np.random.default_rng(5)
+    src = np.c_[rng.uniform(-1, 1, (3000, 2)), rng.normal(0, 0.002, 3000)].astype(np.float32) + np.float32([5, 0, 0])
+    v = rng.normal(size=(2500, 3))
+    tgt = (v / np.linalg.norm(v, axis=1, keepdims=True) * 0.7).astype(np.float32) + np.float32([0, 4, 1])
+    data = dict(src_fds_pcd=src, tgt_fds_pcd=tgt, relt_pose=np.eye(4, dtype=np.float32), is_aligned_to_global_z=False)
+    perms = oracle.draw_perms(cfg, len(src), len(tgt), 0)
+    model = model.to(dev)
+    pose, o_pose, rep = _compare_pair(model, sd, cfg, data, perms, oracle, "degenerate")
+    with torch.no_grad():
+        out = model(data, perms=perms, ransac_seed=0)
+    assert out[2] == 0 and np.allclose(out[0], np.eye(4))            # no inliers, identity
+    model.cpu()
+
+
 def test_forward_draws_host_permutations_like_the_reference(dev, oracle, c1):
     """Without explicit perms forward() must consume NumPy's global RNG exactly like the reference
     (one np.random.choice(N, N, replace=False) per Desc call, src then tgt, per scale)."""
