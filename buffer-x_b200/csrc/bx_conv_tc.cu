@@ -12,24 +12,29 @@
 //      round-to-nearest into fp32 running sums held in the loader threads' registers while the tensor core
 //      already fills the other accumulator.  The cross terms (2^-11 smaller) keep one long chain.
 //
-// Warp-specialised CTA (544 threads, 1 CTA / SM, 128 GEMM rows = one M=128 tile, N = NT columns):
-//   warps 0-15  loaders : four groups of four warps; group g owns the stages it = g, g+4, g+8, ... so a warp
-//               touches a barrier once per FOUR stages (mbarrier / proxy-fence latencies stay off the critical
-//               path).  thread -> row = t & 127.  Per owned stage (16 input channels of one tap; chunk-outer /
-//               tap-inner order keeps a chunk's activations in L1 across its taps) a thread fetches its row's 16
-//               activations, splits them and writes hi/lo with tcgen05.st (32x32b.x8) into the A ring in TENSOR
-//               MEMORY (32 columns per stage: [kstep][hi,lo][8 values]); the MMAs read A from TMEM (TS form),
-//               which takes the activation operand off the shared-memory read port -- with A in shared memory
-//               the kernel was bound by smem bandwidth (3 MMAs re-read the same 128x8 tile), not by the tensor
-//               pipe.  The B (weight) image of a stage
-//                   [kstep][split][kunit][n(NT)][16 B]      K-major no-swizzle, LBO = NT*16 B, SBO = 128 B
-//               is host-arranged, contiguous, and fetched by ONE cp.async.bulk per stage whose transaction count
-//               lands on the same full[stage] barrier -- the weights never touch registers.
-//               Every seg_len stages each loader warp drains its 32 lanes x NT/4 columns of the finished main
+// Warp-specialised CTA (LG*128 + 64 threads, 128 GEMM rows = one M=128 tile, N = NT columns):
+//   loader warps  LG groups of four warps; group g owns the stages it = g, g+LG, ... so a warp touches a barrier once
+//               per LG stages.  thread -> row = t & 127.  Per owned stage (16 input channels of one tap; chunk-outer /
+//               tap-inner order keeps a chunk's activations in L1 across its taps; tap geometry from a shared table)
+//               a thread fetches its row's 16 activations with four 16-byte loads (channel-blocked activations
+//               [n][C/4][position][4]), splits them and writes hi/lo with tcgen05.st (32x32b.x8) into the A ring in
+//               TENSOR MEMORY (4 stages x 32 columns: [kstep][hi,lo][8 values]); the MMAs read A from TMEM (TS
+//               form), which takes the activation operand off the shared-memory read port -- with A in shared
+//               memory the kernel was bound by smem bandwidth (3 MMAs re-read the same 128x8 tile).
+//               Every seg_len stages each loader warp drains its 32 lanes x NT/LG columns of the finished main
 //               accumulator (tcgen05.ld) into its running sums and releases the accumulator (accfree barrier).
-//   warp 16     MMA issuer: waits full[stage], issues 6 tcgen05.mma (2 k-steps x {al*bh, ah*bl, ah*bh}),
-//               tcgen05.commit -> empty[stage]; 4 stages in flight, no __syncthreads in the main loop.
-//   epilogue    running sums + cross accumulator + bias (+ReLU) -> coalesced stores of out[n][co][pos].
+//   weight warp   streams the host-arranged B (weight) images
+//                   [kstep][split][kunit][n(NT)][16 B]      K-major no-swizzle, LBO = NT*16 B, SBO = 128 B
+//               through a shared-memory ring with cp.async.bulk + mbarrier transaction counts, 8-12 stages AHEAD of
+//               the tensor core and independent of the A slots (the weights never touch registers and their L2
+//               latency is off the slot turnaround path).
+//   MMA warp      waits a_full[stage] (and b_full once per weight super-stage), issues 6 tcgen05.mma
+//               (2 k-steps x {al*bh, ah*bl, ah*bh}), tcgen05.commit -> a_empty / b_empty; no __syncthreads in the
+//               main loop.
+//   epilogue    running sums (+ cross accumulator) + bias (+ReLU) -> 16-byte channel-blocked stores.
+// Configurations (dispatch_nt): Cout 128 -> LG=4, ping-pong main + separate cross accumulator, 1 CTA/SM;
+// Cout 64 -> LG=2, ping-pong accumulators that also take the cross terms (segments of 4 stages), 2 CTAs/SM;
+// Cout <= 32 -> LG=2, ping-pong + separate cross, 2 CTAs/SM.  -DBX_TC_TRACE adds a clock64 stage timeline.
 #include "bx_common.cuh"
 
 namespace {
