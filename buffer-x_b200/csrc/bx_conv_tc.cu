@@ -204,6 +204,9 @@ __global__ void __launch_bounds__(LG * 128 + 64, MINB) conv_tc_kernel(const Conv
     const long long row0 = (long long)blockIdx.x * TC_BM;
     if (row0 >= Mtotal) return;  // uniform per CTA, before any barrier / TMEM allocation
     const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef BX_TC_TRACE
+    if (p.trace && blockIdx.x == gridDim.x / 2 && tid == 0) p.trace[4000] = clock64();   // CTA start
+#endif
     const int n_iters = (p.Cin / 16) * p.T;  // stage = (16-channel chunk, tap); chunk outer, tap inner
     const int G = XSEP ? p.seg_len : (p.seg_len < 4 ? p.seg_len : 4);   // merged cross terms: 6 MMAs per stage in one chain
     const int nseg = (n_iters + G - 1) / G;
@@ -413,6 +416,9 @@ __global__ void __launch_bounds__(LG * 128 + 64, MINB) conv_tc_kernel(const Conv
             if (tr && trk < 64) { tb[trk * 3 + 2] = clock64(); ++trk; }
 #endif
         }
+#ifdef BX_TC_TRACE
+        if (tr) p.trace[4002] = clock64();               // loader group: main loop done
+#endif
         while (next_drain < nseg) {                      // a set must still be released if a later segment reuses it
             drain(next_drain, next_drain + NSETS < nseg);
             ++next_drain;
@@ -535,6 +541,9 @@ __global__ void __launch_bounds__(LG * 128 + 64, MINB) conv_tc_kernel(const Conv
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+#ifdef BX_TC_TRACE
+    if (p.trace && blockIdx.x == gridDim.x / 2 && tid == 0) p.trace[4001] = clock64();   // CTA end (before dealloc)
+#endif
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
@@ -645,6 +654,8 @@ BX_API int bx_conv_layer_tc(int geom, const float *in, const float *w_tc, const 
                             const long long *r = h + (g * 64 + k) * 3;
                             if (r[2]) printf("L g%d k%2d top %7lld  empty-wait %5lld  fill %5lld\n", g, k, r[0] - t00, r[1] - r[0], r[2] - r[1]);
                         }
+                    printf("CTA start %lld  end %lld  (total %lld cycles); a loader group left its main loop at %lld\n", h[4000] - t00, h[4001] - t00,
+                           h[4001] - h[4000], h[4002] - t00);
                     const long long *m = h + 4 * 3 * 64;
                     for (int it = 0; it < 72 && m[it * 3]; ++it)
                         printf("M it%3d top %7lld (+%5lld)  acc/b-wait %5lld  a-wait %5lld\n", it, m[it * 3] - t00, it ? m[it * 3] - m[it * 3 - 3] : 0,
