@@ -3,7 +3,8 @@
 // Same implicit GEMM as bx_conv.cu (rows = (sample, output position), cols = Cout, K = taps*Cin, padding
 // geometry folded into the loader), but the inner product runs as tcgen05.mma kind::tf32 with fp32
 // accumulators in tensor memory.  fp32-grade accuracy (descriptor parity 1e-4 rel) needs two things:
-//   1. the 3xTF32 split  x = hi + lo  (hi = x with the 13 low mantissa bits cleared, lo = x - hi, exact):
+//   1. the 3xTF32 split  x = hi + lo  (hi = x with the 13 low mantissa bits cleared -- the tensor core ignores them,
+//      so the hi operand is x itself -- lo = x - hi, exact):
 //          a*b ~= ah*bh + ah*bl + al*bh          (dropped al*bl ~ 2^-20 relative)
 //   2. short accumulation chains: the tensor core accumulates with truncation, so the error of a chain grows
 //      linearly with its length (measured on B200, K = 1152: 5x the fp32-FFMA error for one chain, below it
@@ -344,18 +345,20 @@ __global__ void __launch_bounds__(LG * 128 + 64, MINB) conv_tc_kernel(const Conv
             }
         };
         const uint32_t a_lane = (uint32_t)((warp & 3) * 32) << 16;   // this warp's TMEM lanes = its 32 GEMM rows
-        auto store_stage = [&](int s) {                  // registers -> tensor memory: [kstep][hi,lo][8]
+        // registers -> tensor memory: [kstep][hi,lo][8].  The hi operand is the fp32 value itself: kind::tf32 reads only the
+        // upper 19 bits of a 32-bit operand (truncation -- verified by the 2e-5 layer tests, which fail if the hardware
+        // rounded), so x and (x & 0xFFFFE000) are the same operand and lo = x - (x & 0xFFFFE000) stays exact.
+        auto store_stage = [&](int s) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-                float hi[8], lo[8];
+                float xr[8], lo[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float x = a_reg[ks * 8 + j];
-                    hi[j] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-                    lo[j] = x - hi[j];
+                    xr[j] = a_reg[ks * 8 + j];
+                    lo[j] = xr[j] - __uint_as_float(__float_as_uint(xr[j]) & 0xFFFFE000u);
                 }
                 const uint32_t col = (uint32_t)(A_RING + s * A_STAGE_COLS + ks * 16);
-                tmem_st8(tmem_base + a_lane + col, hi);
+                tmem_st8(tmem_base + a_lane + col, xr);
                 tmem_st8(tmem_base + a_lane + col + 8, lo);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
