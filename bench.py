@@ -225,9 +225,9 @@ def main():
     ap.add_argument("--cpu-frac", type=float, default=None,
                     help="fraction of the key-points the CPU sample runs the per-key-point stages on (default: 1.0 for the\n"
                          "cpu_baseline leg = whole pairs, 0.25 per step for --impl reference)")
-    ap.add_argument("--depth", type=int, default=4,
-                    help="pairs in flight per GPU (CUDA-graph slots on separate streams).  Measured on 1xB200: 2 -> 92.6, 3 -> 97.3, "
-                         "4 -> 100.3, 6 -> 102.5, 8 -> 103.8 pairs/s")
+    ap.add_argument("--depth", type=int, default=6,
+                    help="pairs in flight per GPU (CUDA-graph slots on separate streams).  Measured on 1xB200 at the final commit "
+                         "(20 steps): 4 -> 111.7, 6 -> 112.8, 8 -> 114.3 pairs/s; earlier 2 -> 92.6, 3 -> 97.3, 4 -> 100.3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--short", action="store_true", help="profiling runs under ncu: allow < 3 warm-up steps, skip the e2e leg")
     args = ap.parse_args()
