@@ -20,7 +20,8 @@ PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libbufferx_b200.so")
 OBJ = os.path.join(HERE, "_obj")
 
-EXACT = ["bx_api.cu", "bx_fps.cu", "bx_radius.cu", "bx_patches.cu", "bx_spt.cu", "bx_match.cu", "bx_ransac.cu", "bx_neighbors.cu"]
+EXACT = ["bx_api.cu", "bx_fps.cu", "bx_radius.cu", "bx_patches.cu", "bx_spt.cu", "bx_match.cu", "bx_ransac.cu", "bx_neighbors.cu",
+         "bx_bootstrap.cu"]
 FAST = ["bx_conv.cu", "bx_conv_tc.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -23,6 +23,7 @@ SYMBOLS = [
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
     "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab", "bx_concat_matches",
+    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
@@ -65,6 +66,9 @@ def load_library():
     lib.bx_conv_tc_ntile.argtypes = [c_int]
     lib.bx_costvol_ab.argtypes = [P, P, P, P, P, c_int, P, P, P, P, P, P]
     lib.bx_concat_matches.argtypes = [P, P, P, c_int, c_int, P, P, P, P, P, P]
+    lib.bx_pca_analysis.argtypes = [P, c_int, P, c_int, P, P, P]
+    lib.bx_project_range.argtypes = [P, c_int, P, P, P, P]
+    lib.bx_voxel_down_sample.argtypes = [P, c_int, ctypes.c_double, P, P, c_int, P, P, P, P, P, P]
     lib.bx_pool_desc.argtypes = [P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_mutual_nn.argtypes = [P, c_int, P, c_int, c_int, P, P, P, P, P, P, P]
     lib.bx_hypotheses.argtypes = [P, c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P]
@@ -493,5 +497,52 @@ def grid_subsample(points, dl: float):
     dm = torch.zeros(1, dtype=I32, device=dev)
     _check(lib.bx_grid_subsample(_dp(points, F32, "points"), n, float(dl), _dp(tkeys), _dp(tacc), cap, _dp(mm), _dp(keys), _dp(xyz), _dp(cnt),
                                  _dp(dm), _stream()), "bx_grid_subsample")
+    m = int(dm.item())
+    return keys[:m], xyz[:m], cnt[:m]
+
+
+F64 = torch.float64
+
+
+def pca_analysis(points: torch.Tensor, sample_idx: torch.Tensor | None = None):
+    """sklearn-PCA of the sampled points (reference utils/tools.py:132-149).  Returns (mean [3], variance [3] desc,
+    components [3,3] rows) as float64 CUDA tensors (views of one 15-double block)."""
+    n = points.shape[0]
+    dev = points.device
+    ns = n if sample_idx is None else int(sample_idx.shape[0])
+    acc = torch.empty(9, dtype=F64, device=dev)
+    out = torch.empty(15, dtype=F64, device=dev)
+    _check(load_library().bx_pca_analysis(_dp(points, F32, "points"), n, _dp(sample_idx, I32, "sample_idx"), ns, _dp(acc), _dp(out), _stream()),
+           "bx_pca_analysis")
+    return out[0:3], out[3:6], out[6:15].view(3, 3)
+
+
+def project_range(points: torch.Tensor, mean: torch.Tensor, axis: torch.Tensor):
+    """(min, max) of (p - mean) . axis over the cloud, float64 CUDA tensor [2]."""
+    dev = points.device
+    ma = torch.cat([mean.reshape(3), axis.reshape(3)]).to(F64).contiguous()
+    work = torch.empty(2, dtype=torch.int64, device=dev)
+    out = torch.empty(2, dtype=F64, device=dev)
+    _check(load_library().bx_project_range(_dp(points, F32, "points"), points.shape[0], _dp(ma), _dp(work), _dp(out), _stream()), "bx_project_range")
+    return out
+
+
+def voxel_down_sample(points: torch.Tensor, voxel: float):
+    """Open3D voxel_down_sample: returns (keys [m] int64 = ix | iy << 21 | iz << 42, xyz [m,3] f32, counts [m]), hash order."""
+    lib = load_library()
+    n = points.shape[0]
+    dev = points.device
+    cap = 1
+    while cap < 2 * n:
+        cap <<= 1
+    tkeys = torch.empty(cap, dtype=torch.int64, device=dev)
+    tacc = torch.empty((cap, 4), dtype=F64, device=dev)
+    mm = torch.empty(6, dtype=torch.int64, device=dev)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    xyz = torch.empty((n, 3), dtype=F32, device=dev)
+    cnt = torch.empty(n, dtype=I32, device=dev)
+    dm = torch.zeros(1, dtype=I32, device=dev)
+    _check(lib.bx_voxel_down_sample(_dp(points, F32, "points"), n, float(voxel), _dp(tkeys), _dp(tacc), cap, _dp(mm), _dp(keys), _dp(xyz),
+                                    _dp(cnt), _dp(dm), _stream()), "bx_voxel_down_sample")
     m = int(dm.item())
     return keys[:m], xyz[:m], cnt[:m]

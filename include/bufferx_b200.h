@@ -216,6 +216,25 @@ int bx_grid_subsample(const float *pts, int n, float dl, unsigned long long *tab
                       float *minmax6, unsigned long long *keys_out, float *xyz_out, int32_t *cnt_out, int32_t *d_m,
                       void *stream);
 
+/* ---- loader-side geometric bootstrapping ---------------------------------------
+ * bx_pca_analysis replaces compute_pca_alignment (utils/tools.py:132-149) = sklearn PCA(n_components=3) of the
+ * sampled points pts[sample_idx[0..n_sample)] (sample_idx NULL: all n points), fp64.  acc9: 9-double workspace.
+ * out15: mean[3], explained variance[3] (descending), components[3][3] (rows; largest-magnitude entry positive).
+ * bx_project_range: min / max over the whole cloud of (p - mean) . axis (mean_axis6 = mean[3], axis[3], on the
+ * device) = the z-range of pca.transform (utils/tools.py:181-182).  work2: 2 x u64 workspace, out2: {min, max}.
+ * bx_voxel_down_sample replaces open3d PointCloud.voxel_down_sample (Open3D 0.18; dataset/*.py, utils/tools.py:
+ * 218-219): voxel_min_bound = min - voxel/2, index = floor((p - voxel_min_bound)/voxel) in fp64, output = mean of the
+ * points of a voxel.  table_keys [table_cap] u64, table_acc [table_cap,4] f64 (table_cap = power of two >= 2n) and
+ * minmax6 [6] u64 are workspaces; keys_out [n] = ix | iy << 21 | iz << 42, xyz_out [n,3], cnt_out [n] (may be NULL),
+ * *d_m = voxels.  Emitted in hash-table order (Open3D: unordered_map order). */
+int bx_pca_analysis(const float *pts, int n, const int32_t *sample_idx, int n_sample, double *acc9, double *out15,
+                    void *stream);
+int bx_project_range(const float *pts, int n, const double *mean_axis6, unsigned long long *work2, double *out2,
+                     void *stream);
+int bx_voxel_down_sample(const float *pts, int n, double voxel, unsigned long long *table_keys, double *table_acc,
+                         int table_cap, unsigned long long *minmax6, unsigned long long *keys_out, float *xyz_out,
+                         int32_t *cnt_out, int32_t *d_m, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

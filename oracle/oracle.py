@@ -551,3 +551,62 @@ def ref_grid_subsampling(points, dl: float) -> np.ndarray:
     arr = np.ctypeslib.as_array(ctypes.cast(out, POINTER(c_float)), shape=(max(3 * m, 1),))[: 3 * m].reshape(m, 3).copy()
     ref_lib().ref_free(out)
     return arr
+
+
+# --------------------------------------------------------------------------- #
+# loader-side geometric bootstrapping (float64 NumPy restatements)
+# --------------------------------------------------------------------------- #
+def pca_alignment(pts, sample_idx):
+    """compute_pca_alignment (/root/reference/utils/tools.py:132-149) with the random sample made explicit.
+    sklearn.decomposition.PCA(n_components=3).fit(X) on [n,3] float64 data: explained_variance_ = eigenvalues of the
+    centred sample covariance (1/(n-1)), descending; components_ = eigenvectors as rows, each signed so that its entry of
+    largest magnitude is positive (sklearn >= 1.5: svd_flip(u_based_decision=False)).  Pinned against sklearn itself in
+    tests/test_oracle_cpu.py.  Returns (sphericity, is_aligned, mean, variance[3], components[3,3])."""
+    X = np.asarray(pts, dtype=np.float64)[np.asarray(sample_idx)]
+    mean = X.mean(axis=0)
+    Xc = X - mean
+    C = (Xc.T @ Xc) / (X.shape[0] - 1)
+    w, V = np.linalg.eigh(C)
+    order = np.argsort(w)[::-1]
+    w, V = w[order], V[:, order]
+    comps = V.T.copy()
+    for r in range(3):
+        if comps[r, np.argmax(np.abs(comps[r]))] < 0:
+            comps[r] = -comps[r]
+    sphericity = w[2] / w[0]
+    z = comps[2] / np.linalg.norm(comps[2])
+    is_aligned = bool(abs(float(np.dot(z, np.array([0.0, 0.0, 1.0])))) > 0.98)
+    return float(sphericity), is_aligned, mean, w, comps
+
+
+def sphericity_based_voxel_analysis(src, tgt, idx_src, idx_tgt):
+    """/root/reference/utils/tools.py:152-198 -> (voxel_size, sphericity, is_aligned_to_global_z)."""
+    s_s, a_s, m_s, _, c_s = pca_alignment(src, idx_src)
+    s_t, a_t, m_t, _, c_t = pca_alignment(tgt, idx_tgt)
+    if len(src) > len(tgt):
+        ref, sph, mean, comps = src, s_s, m_s, c_s
+    else:
+        ref, sph, mean, comps = tgt, s_t, m_t, c_t
+    zt = (np.asarray(ref, dtype=np.float64) - mean) @ comps[2]
+    z_range = zt.max() - zt.min()
+    alpha = 1.0 if sph < 0.05 else 1.5
+    voxel = max(np.sqrt(z_range) / 100 * alpha, 0.001)
+    zs, zg = c_s[2] / np.linalg.norm(c_s[2]), c_t[2] / np.linalg.norm(c_t[2])
+    same = float(np.dot(zs, zg)) > 0.96
+    return round(float(voxel), 4), sph, bool(a_s and a_t and same)
+
+
+def voxel_down_sample(pts, voxel: float):
+    """open3d.geometry.PointCloud.voxel_down_sample (Open3D 0.18.0, cpp/open3d/geometry/PointCloud.cpp VoxelDownSample;
+    not under /root/reference -- restated from the published algorithm, anchored on the call sites dataset/*.py and
+    utils/tools.py:218-219): voxel_min_bound = min_bound - voxel*0.5; index = floor((p - voxel_min_bound)/voxel);
+    output = mean of the points of a voxel (double accumulation).  Returns (keys [m] = ix | iy<<21 | iz<<42 sorted
+    ascending, means [m,3] float64, counts [m]) -- Open3D's own output order is that of an unordered_map."""
+    P = np.asarray(pts, dtype=np.float64)
+    vmb = P.min(axis=0) - voxel * 0.5
+    iv = np.floor((P - vmb) / voxel).astype(np.int64)
+    keys = (iv[:, 0] & 0x1FFFFF) | ((iv[:, 1] & 0x1FFFFF) << 21) | ((iv[:, 2] & 0x1FFFFF) << 42)
+    uk, inv, cnt = np.unique(keys, return_inverse=True, return_counts=True)
+    sums = np.zeros((len(uk), 3))
+    np.add.at(sums, inv, P)
+    return uk, sums / cnt[:, None], cnt

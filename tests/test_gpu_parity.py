@@ -693,3 +693,42 @@ def test_grid_subsample_matches_oracle(dev, oracle):
         o = np.argsort(k)
         assert (k[o] == ek).all() and (cnt.cpu().numpy()[o] == ecnt).all()             # cell ids and counts: bit-exact
         assert np.abs(xyz.cpu().numpy()[o] - exyz).max() < 2e-6                         # barycentres: fp32 summation order
+
+
+# ------------------------------------------------------------------ geometric bootstrapping
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,ns,nt", [("C1", 5000, 5000), ("C3", 30000, 24000), ("C5", 20000, 9000)])
+def test_sphericity_based_voxel_analysis(dev, oracle, name, ns, nt):
+    """GPU PCA / z-range against the float64 oracle (itself pinned against sklearn): variances 1e-9 rel, components
+    1e-8, identical (voxel_size, is_aligned_to_global_z), sphericity 1e-9."""
+    from bufferx_b200 import ops
+    from bufferx_b200.synth import make_pair
+    from bufferx_b200.utils.tools import sphericity_based_voxel_analysis
+    data = make_pair(name, 2, n_src=ns, n_tgt=nt)
+    src, tgt = data["src_fds_pcd"], data["tgt_fds_pcd"]
+    st = np.random.RandomState(7)
+    i_s = st.choice(ns, size=ns // 10, replace=False)
+    i_t = st.choice(nt, size=nt // 10, replace=False)
+    mean, var, comps = ops.pca_analysis(cu(src, dev), cu(i_s.astype(np.int32), dev, torch.int32))
+    _, _, o_mean, o_var, o_comps = oracle.pca_alignment(src, i_s)
+    assert np.allclose(mean.cpu().numpy(), o_mean, atol=1e-10)
+    assert np.allclose(var.cpu().numpy(), o_var, rtol=1e-9)
+    assert np.allclose(comps.cpu().numpy(), o_comps, atol=1e-8)
+    got = sphericity_based_voxel_analysis(src, tgt, i_s, i_t, device=dev)
+    exp = oracle.sphericity_based_voxel_analysis(src, tgt, i_s, i_t)
+    assert got[0] == exp[0] and got[2] == exp[2] and abs(got[1] - exp[1]) < 1e-9 * max(1.0, abs(exp[1]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,voxel", [(5000, 0.035), (60000, 0.3), (1, 0.5), (777, 10.0)])
+def test_voxel_down_sample(dev, oracle, n, voxel):
+    """Same occupied voxels and counts as the oracle (exact), means within 1e-6 (fp64 sums, fp32 output)."""
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(n)
+    pts = (rng.normal(size=(n, 3)) * np.array([8.0, 5.0, 1.5])).astype(np.float32)
+    keys, xyz, cnt = ops.voxel_down_sample(cu(pts, dev), voxel)
+    order = torch.argsort(keys)
+    k, x, c = keys[order].cpu().numpy(), xyz[order].cpu().numpy(), cnt[order].cpu().numpy()
+    ek, em, ec = oracle.voxel_down_sample(pts, voxel)
+    assert (k == ek).all() and (c == ec).all()
+    assert np.abs(x - em).max() <= 1e-6 * max(1.0, np.abs(em).max())

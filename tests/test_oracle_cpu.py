@@ -418,3 +418,44 @@ def test_fitted_costnet_fixture_matches_the_model():
         else:
             assert same, k
     assert changed >= 10          # the ten conv layers were re-fitted
+
+
+# ------------------------------------------------------------------ geometric bootstrapping
+def test_pca_restatement_matches_sklearn(oracle):
+    """oracle.pca_alignment against sklearn.decomposition.PCA itself (the reference's compute_pca_alignment,
+    utils/tools.py:132-149): variances, components (including their signs), sphericity."""
+    from sklearn.decomposition import PCA
+    from bufferx_b200.synth import make_pair
+    for name, seed in (("C1", 0), ("C3", 1)):
+        data = make_pair(name, seed, n_src=6000, n_tgt=5000)
+        pts = data["src_fds_pcd"].astype(np.float64)
+        idx = np.random.RandomState(seed).choice(len(pts), size=len(pts) // 10, replace=False)
+        pca = PCA(n_components=3).fit(pts[idx])
+        sph, aligned, mean, var, comps = oracle.pca_alignment(pts, idx)
+        assert np.allclose(mean, pca.mean_, rtol=0, atol=1e-12)
+        assert np.allclose(var, pca.explained_variance_, rtol=1e-10)
+        assert np.allclose(comps, pca.components_, atol=1e-8)
+        l1, l2, l3 = sorted(pca.explained_variance_, reverse=True)
+        assert abs(sph - l3 / l1) < 1e-12
+        z = pca.components_[-1] / np.linalg.norm(pca.components_[-1])
+        assert aligned == bool(abs(z[2]) > 0.98)
+
+
+def test_voxel_down_sample_restatement(oracle):
+    """oracle.voxel_down_sample against a literal per-point dictionary walk of Open3D's VoxelDownSample."""
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-2, 3, (4000, 3)).astype(np.float32)
+    voxel = 0.21
+    P = pts.astype(np.float64)
+    vmb = P.min(0) - voxel * 0.5
+    acc = {}
+    for p in P:
+        k = tuple(np.floor((p - vmb) / voxel).astype(np.int64))
+        a = acc.setdefault(k, [np.zeros(3), 0])
+        a[0] += p
+        a[1] += 1
+    keys, means, cnt = oracle.voxel_down_sample(pts, voxel)
+    assert len(keys) == len(acc) and cnt.sum() == len(pts)
+    ref = {(k[0] | (k[1] << 21) | (k[2] << 42)): v for k, v in acc.items()}
+    for k, m, c in zip(keys.tolist(), means, cnt):
+        assert c == ref[k][1] and np.allclose(m, ref[k][0] / ref[k][1], atol=1e-12)
