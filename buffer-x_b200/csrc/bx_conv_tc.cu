@@ -361,7 +361,6 @@ __global__ void __launch_bounds__(LG * 128 + 64, MINB) conv_tc_kernel(const Conv
                 tmem_st8(tmem_base + a_lane + col, xr);
                 tmem_st8(tmem_base + a_lane + col + 8, lo);
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         };
 
         // ---- accumulator ownership of this warp: TMEM lanes 32*(warp&3).., columns CW*(warp>>2).. ----------
@@ -407,11 +406,12 @@ __global__ void __launch_bounds__(LG * 128 + 64, MINB) conv_tc_kernel(const Conv
 #ifdef BX_TC_TRACE
             if (tr && trk < 64) tb[trk * 3 + 1] = clock64();
 #endif
-            store_stage(s);
-            if (it + LG < n_iters) {                      // this group's next stage: activations in flight
+            store_stage(s);                               // tcgen05.st issued (sources are read at issue) ...
+            if (it + LG < n_iters) {                      // ... this group's next activations go in flight behind them ...
                 advance_lg();
                 load_stage();
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // ... and only then wait for the stores
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // tcgen05.st ordered before the arrive
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar_base + 8u * s);
