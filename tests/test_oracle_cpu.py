@@ -459,3 +459,23 @@ def test_voxel_down_sample_restatement(oracle):
     ref = {(k[0] | (k[1] << 21) | (k[2] << 42)): v for k, v in acc.items()}
     for k, m, c in zip(keys.tolist(), means, cnt):
         assert c == ref[k][1] and np.allclose(m, ref[k][0] / ref[k][1], atol=1e-12)
+
+
+def test_make_cfg_equals_the_reference_for_every_dataset():
+    """tests/golden/reference_configs.json = the reference's own make_cfg(name) for all 14 dataset names
+    (tests/tools/gen_config_golden.py imports /root/reference/config); ours must agree key by key, value by value."""
+    import json
+    from pathlib import Path
+    from bufferx_b200 import make_cfg
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_configs.json")))
+    assert len(gold) == 14
+
+    def plain(x):
+        if isinstance(x, dict):
+            return {k: plain(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return [plain(v) for v in x]
+        return str(x) if isinstance(x, Path) else x
+
+    for name, ref in gold.items():
+        assert plain(make_cfg(name, "../datasets")) == ref, name
