@@ -444,6 +444,34 @@ def test_degenerate_pair_unrelated_clouds(dev, oracle):
     model.cpu()
 
 
+@pytest.mark.parametrize("trained,expect_scales", [(True, 1), (False, 3)])
+def test_early_exit_mode(dev, oracle, trained, expect_scales):
+    """a16: cfg.match.enable_early_exit = True (reference BUFFERX.py:424-439).  With the fitted CostNet the first scale
+    already yields >= early_exit_min_inliers RANSAC inliers and the pair stops after one scale; with the random CostNet
+    it runs all three (4 inliers < 5).  Same decision, counts and pose as the oracle."""
+    import bufferx_b200 as bx
+    from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
+    cfg = workload_cfg("C2")
+    cfg.match.enable_early_exit = True
+    cfg.match.early_exit_min_inliers = 5      # the weak seeded descriptor gives ~27 inliers at the first scale (the reference's 50 needs a real checkpoint)
+    cfg.match.iter_n = 20000
+    model = init_synthetic_weights(bx.BufferX(cfg), trained_pose=trained)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    data = make_pair("C2", 3)
+    perms = oracle.draw_perms(cfg, 20000, 20000, 3)
+    model = model.to(dev)
+    with torch.no_grad():
+        pose, _, ninl, nmut, nind, su = model(data, perms=perms, ransac_seed=0)
+    o_pose, o_ninl, o_nmut, o_nind, o_su, _ = oracle.register_pair(sd, cfg, data, perms, 0)
+    assert su == o_su == expect_scales
+    assert abs(nmut - o_nmut) <= max(2, o_nmut // 200)
+    if nmut == o_nmut:
+        assert (ninl, nind) == (o_ninl, o_nind)
+        from bufferx_b200.se3 import compute_rre, compute_rte
+        assert compute_rre(pose, o_pose) < 0.1 and compute_rte(pose, o_pose) < 0.005
+    model.cpu()
+
+
 def test_forward_draws_host_permutations_like_the_reference(dev, oracle, c1):
     """Without explicit perms forward() must consume NumPy's global RNG exactly like the reference
     (one np.random.choice(N, N, replace=False) per Desc call, src then tgt, per scale)."""
