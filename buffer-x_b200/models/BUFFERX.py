@@ -213,8 +213,21 @@ class BufferX(nn.Module):
         cfg = self.config
         return not cfg.match.get("enable_early_exit", True) and not cfg.test.get("enable_timing", False)
 
+    MAX_GRAPH_SHAPES = 8      # graphs are per (Ns, Nt, aligned) shape; least recently used shapes are dropped beyond this
+
     def _slot(self, Ns, Nt, aligned):
         key = (Ns, Nt, bool(aligned))
+        if key not in self._slots and len(self._slots) >= self.MAX_GRAPH_SHAPES:
+            # datasets with a different size for every pair would otherwise pin one set of graph pools per pair; for
+            # those, run eager (`enable_cuda_graphs(False)`) or pad/bucket the clouds upstream
+            for old in list(self._slots):
+                if all(not sl.busy for sl in self._slots[old]):
+                    del self._slots[old]
+                    self._rr.pop(old, None)
+                    break
+        else:
+            if key in self._slots:          # keep insertion order = recency order
+                self._slots[key] = self._slots.pop(key)
         lst = self._slots.setdefault(key, [])
         i = self._rr.get(key, 0)
         if len(lst) < self._slots_per_shape:
