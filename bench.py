@@ -419,7 +419,7 @@ def main():
                 "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "kernels": kern}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # the CPU baseline is reported at N = 1 only
             from oracle import oracle as O
             t0 = time.perf_counter()
             secs, stages = [], {}
