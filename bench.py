@@ -316,8 +316,6 @@ def main():
                     h = model.forward_async(devd[j][0], perms=devd[j][1])
                 else:
                     h = model.forward_async(host[j][0], perms=host[j][1])
-            with torch.cuda.stream(h.stream):
-                pass
             handles.append((h, s))
         while handles:
             collect(*handles.pop(0))

@@ -334,7 +334,7 @@ class BufferX(nn.Module):
             des_r = r_dev[i:i + 1]
             ps = None if perms is None else perms[i][0]
             pt = None if perms is None else perms[i][1]
-            if batched is not None:
+            if batched is not None:         # only with more than 8 scales (the batched tail above handles S <= 8)
                 sd, td = batched[2 * i], batched[2 * i + 1]
             else:
                 sd = self.Desc(src[None], src_kpts[None], des_r, aligned, perm=ps, debug=debug)
