@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- registration pairs/sec of the BUFFER-X hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3|C4|C5|C1]
 
-A "step" is one synthetic pair (BASELINE config C2: 2x20000 points, 1500 FPS key-points, 512 points
-per patch, 3 scales, 50000 RANSAC iterations, seeded synthetic weights) through the whole hot path
-(FPS -> radius estimation -> 6x [patch gathering, LRF, SPT, conv stack, pooling] -> 3x [matching,
-cost volume, hypotheses] -> consensus -> RANSAC -> refinement).
-  value : pairs/s with the clouds + permutations already resident in HBM (device-event timed,
-          max over ranks, summed over ranks: every rank runs its own K pairs = weak scaling)
-  e2e   : the same metric through the public API ``BufferX.forward(data_source)`` with HOST (pinned)
-          tensors: H2D of both clouds and the six permutations and D2H of the result block inside
-          the timed region.
-  roofline     : the dominant kernel (conv_gemm_kernel of the descriptor conv stack), algorithmic
-                 FLOPs / CUDA-event time of its launches inside the timed region.
-  kernels      : the two HBM-side kernels north_star names (neighbour gather, RANSAC), same method.
-  cpu_baseline : the CPU oracle port timed on the host cores on a bounded sample of the same workload.
-``--impl reference`` times that CPU path alone (rank 0 only).
+A "step" is one pass of the hot path over one BATCH of synthetic pairs (``--pairs-per-step``, default 32 C2 pairs: a
+step is ~0.28 s of GPU work, the default 20 steps a 5-6 s timed region through 32 distinct pairs per rank).  Every pair
+goes through the whole path (FPS -> radius estimation -> 6x [patch gathering, LRF, SPT, conv stack, pooling] -> 3x
+[matching, cost volume, hypotheses] -> consensus -> RANSAC -> refinement); the one collective of the path, the
+all-gather of the 32-float result records, is INSIDE the timed region.
+  value : pairs/s with the clouds + permutations already resident in HBM (device-event timed, max over ranks; every
+          rank runs its own K batches = weak scaling; C4 = 512 pairs split over the ranks = strong scaling)
+  e2e   : the same metric through the public API ``BufferX.forward_async(data_source)`` with HOST (pinned) tensors:
+          H2D of both clouds and the six permutations and D2H of the result block inside the timed region;
+          ``e2e_single_call`` = latency of the reference-style serial ``model(data_source)`` call (eager and graph mode).
+  roofline     : the dominant kernel (conv_tc_kernel of the descriptor conv stack), algorithmic FLOPs / CUDA-event time
+                 of its launches in an eager pass of this run.
+  kernels      : the HBM-side kernels north_star names (neighbour gather, RANSAC inlier count) as GB/s, and the shares of
+                 the other stages.
+  cpu_baseline : the CPU oracle port (oracle/) timed on the host cores on whole pairs, thread count chosen by a measured sweep.
+``--impl reference`` times that CPU path alone (rank 0 only): one whole pair per step.
 """
 import argparse
+import copy
 import json
 import os
 import subprocess
@@ -34,6 +37,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "registration pairs/sec (20k-pt clouds, 1500 kpts, 50k RANSAC)"
+DEFAULT_BATCH = {"C1": 32, "C2": 32, "C3": 8, "C5": 16, "C4": 512}
 
 
 def measured_peaks():
@@ -45,13 +49,31 @@ def measured_peaks():
 
 
 def conv_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc_kernel launch, averaged over the eight layers of one
-    batched descriptor pass, from the committed `ncu --set full` capture (profiles/r01_conv_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-    try:
-        return float(json.load(open(p))["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc_kernel launch, averaged over the layers of one batched
+    descriptor pass, from the committed `ncu --set full` capture (profiles/r02_conv_traffic.json, else round 1's)."""
+    for name in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+        try:
+            return float(json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
+
+
+def workload_desc(name, cfg, ns, nt):
+    base = "C2" if name == "C4" else name
+    s = (f"{base}: {ns}+{nt} pts, {cfg.patch.num_fps} kpts, {cfg.patch.num_points_per_patch} pts/patch, "
+         f"{cfg.patch.num_scales} scales, {cfg.match.iter_n} RANSAC iters, seeded synthetic weights (CostNet fitted on disjoint synthetic pairs)")
+    if name == "C4":
+        s = "C4: 512 pairs of " + s + ", pair i -> rank i mod world, one gather"
+    return s
+
+
+def static_config(name, cfg, ns, nt):
+    """The part of `config` that identifies the workload: identical in the `ours` and `reference` arms."""
+    return {"workload": workload_desc(name, cfg, ns, nt),
+            "sharding": "pair i -> rank i mod world; one all_gather of 32-float records inside the timed region",
+            "l2": "every pair's working set (~1 GB of activations) exceeds the 126 MB L2 and a batch cycles through >= 32 distinct pairs; "
+                  "the eager roofline pass flushes 256 MB between pairs"}
 
 
 class ClockSampler(threading.Thread):
@@ -110,126 +132,110 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "sm_mhz_min": sm[0] if sm else None, "reasons": reasons, "samples": len(self.rows)}
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(workload, cfg, sd, data, perms, frac=0.08):
-    """Bounded CPU sample of one pair: full FPS / radius / matching / consensus / RANSAC / refinement, and the
-    per-key-point stages (patch gathering, LRF, SPT, conv stack, cost volume) on a `frac` subset of the
-    key-points, scaled back linearly.  Returns (seconds per pair estimate, cores, description, stage dict)."""
+# CPU arm: the oracle port of the reference path on whole pairs
+# ------------------------------------------------------------------------------------------------
+def _set_cpu_threads(n):
+    from oracle import oracle as O
+    torch.set_num_threads(n)
+    O.lib().bxo_set_num_threads(n)
+
+
+def cpu_thread_sweep(cfg, sd, data, perms, fixed=None):
+    """Measured choice of the host thread count: a reduced pair (160 key-points per cloud and scale, 5000 RANSAC
+    iterations, every stage of the path) at 8 / 16 / 32 / 64 / all hardware threads; the fastest is kept.
+    -> (best thread count, {threads: seconds})."""
     from oracle import oracle as O
     O.build()
-    # all the host threads the port can USE: beyond ~16 threads the small per-patch convolutions of the
-    # torch-CPU stacks and the OpenMP loops over a few hundred key-points only lose time to oversubscription
-    nthr = max(1, min(os.cpu_count() or 1, 16))
-    torch.set_num_threads(nthr)
-    O.lib().bxo_set_num_threads(nthr)
-    src, tgt = data["src_fds_pcd"], data["tgt_fds_pcd"]
-    Kr, K, S = cfg.patch.num_points_radius_estimate, cfg.patch.num_fps, cfg.patch.num_scales
-    st = {}
-    t0 = time.perf_counter()
-    si, ti = O.fps(src, max(Kr, K)), O.fps(tgt, max(Kr, K))
-    st["fps"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    big, bk = (src, src[si[:Kr]]) if len(src) > len(tgt) else (tgt, tgt[ti[:Kr]])
-    cum = O.radius_hist(bk, big)
-    radii = [O.radius_estimation(src, src[si[:Kr]], tgt, tgt[ti[:Kr]], [th], cum=cum)[0] for th in cfg.patch.search_radius_thresholds]
-    st["radius_estimation"] = time.perf_counter() - t0
-    ks = max(16, int(K * frac))
-    sub = {}
-    scale_k = K / ks
-    desc_s = desc_t = None
-    for i in range(S):
-        a = O.describe(sd, cfg, src, src[si[:ks]], radii[i], bool(data["is_aligned_to_global_z"]), perms[i][0], timings=sub)
-        b = O.describe(sd, cfg, tgt, tgt[ti[:ks]], radii[i], bool(data["is_aligned_to_global_z"]), perms[i][1], timings=sub)
+    ncpu = os.cpu_count() or 1
+    if fixed:
+        return int(fixed), {}
+    small = copy.deepcopy(cfg)
+    small.patch.num_fps = 160
+    small.patch.num_points_radius_estimate = 400
+    small.match.iter_n = 5000
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu} | {ncpu})
+    res = {}
+    for c in cands:
+        _set_cpu_threads(c)
         t0 = time.perf_counter()
-        sm, tm, _, _ = O.mutual_nn(a["desc"].numpy(), b["desc"].numpy())
-        sub["mutual_nn_sub"] = sub.get("mutual_nn_sub", 0.0) + time.perf_counter() - t0
-        t0 = time.perf_counter()
-        smi, tmi = torch.from_numpy(sm.astype(np.int64)), torch.from_numpy(tm.astype(np.int64))
-        with torch.no_grad():
-            O.cost_volume(a["equi"][smi][:, :, 1:cfg.patch.ele_n - 1], b["equi"][tmi][:, :, 1:cfg.patch.ele_n - 1], sd, cfg.patch.azi_n)
-        sub["cost_volume"] = sub.get("cost_volume", 0.0) + time.perf_counter() - t0
-    for k in ("ball_query_group", "lrf", "spt", "conv_desc", "cost_volume"):
-        st[k] = sub.get(k, 0.0) * scale_k
-    # full-size matching / consensus / RANSAC / refinement on synthetic descriptors / correspondences of the right size
-    rng = np.random.default_rng(0)
-    da = rng.normal(size=(K, 32)).astype(np.float32)
-    db = rng.normal(size=(K, 32)).astype(np.float32)
+        O.register_pair(sd, small, data, perms, 0)
+        res[c] = round(time.perf_counter() - t0, 3)
+    best = min(res, key=res.get)
+    return best, res
+
+
+def cpu_whole_pair(cfg, sd, data, perms, threads):
+    """One whole pair through the CPU port -> (seconds, per-stage seconds)."""
+    from oracle import oracle as O
+    _set_cpu_threads(threads)
+    tm = {}
     t0 = time.perf_counter()
-    for _ in range(S):
-        O.mutual_nn(da, db)
-    st["mutual_nn"] = time.perf_counter() - t0
-    Mc = int(0.35 * K) * S
-    ss = rng.uniform(-3, 3, (Mc, 3)).astype(np.float32)
-    tt = (ss + rng.normal(scale=0.02, size=(Mc, 3))).astype(np.float32)
-    tt[Mc // 3:] = rng.uniform(-3, 3, (Mc - Mc // 3, 3))
-    R = np.tile(np.eye(3, dtype=np.float32), (Mc, 1, 1))
-    tv = rng.normal(scale=0.5, size=(Mc, 3)).astype(np.float32)
-    tv[::5] = 0
-    t0 = time.perf_counter()
-    ind, _, _ = O.consensus(ss, tt, R, tv, cfg.patch.azi_n, cfg.match.inlier_th)
-    st["consensus"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    r = O.ransac(ss, tt, ind, cfg.match.dist_th, cfg.match.similar_th, cfg.match.confidence, cfg.match.iter_n, 0)
-    st["ransac"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    O.refine(ss, tt, r["T"].astype(np.float32), cfg.match.dist_th)
-    st["refine"] = time.perf_counter() - t0
-    total = sum(st.values())
-    desc = (f"{workload}: FPS, radius estimation, matching, consensus, RANSAC, refinement at full size; patch gathering/LRF/SPT/"
-            f"conv stack/cost volume on {ks} of {K} key-points per cloud and scale, scaled x{scale_k:.1f}")
-    return total, O.num_threads(), desc, st
+    O.register_pair(sd, cfg, data, perms, 0, timings=tm)
+    return time.perf_counter() - t0, tm
 
 
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the reference path (the reference's own GPU path needs pointnet2_ops, knn_cuda,
-    torch_batch_svd and open3d, none of which exist offline) on the host cores; rank 0 only."""
+    torch_batch_svd and open3d, none of which exist offline) on the host cores; rank 0 only.  A step = ONE WHOLE pair of
+    the workload (a bounded sample of the GPU arm's batch); the warm-up is the thread-count sweep."""
     if rank != 0:
         return
     import bufferx_b200 as bx
     from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
     from oracle import oracle as O
-    cfg = workload_cfg(args.workload)
+    wl = "C2" if args.workload == "C4" else args.workload
+    cfg = workload_cfg(wl)
     model = init_synthetic_weights(bx.BufferX(cfg), trained_pose=True)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    times = []
-    cores, desc = 1, ""
-    for s in range(args.warmup + args.steps):
-        data = make_pair(args.workload, s % 4)
-        perms = O.draw_perms(cfg, len(data["src_fds_pcd"]), len(data["tgt_fds_pcd"]), s)
-        t, cores, desc, _ = cpu_sample(args.workload, cfg, sd, data, perms, frac=args.cpu_frac or 0.25)
-        if s >= args.warmup:
-            times.append(t)
+    d0 = make_pair(wl, 0)
+    ns, nt = len(d0["src_fds_pcd"]), len(d0["tgt_fds_pcd"])
+    best, sweep = cpu_thread_sweep(cfg, sd, d0, O.draw_perms(cfg, ns, nt, 0), fixed=args.cpu_threads)
+    for s in range(max(0, args.warmup - len(sweep))):      # any remaining warm-up steps: reduced pairs at the chosen count
+        cpu_thread_sweep(cfg, sd, d0, O.draw_perms(cfg, ns, nt, 0), fixed=best)
+    times, stages = [], {}
+    for s in range(args.steps):
+        data = make_pair(wl, s)
+        perms = O.draw_perms(cfg, ns, nt, s)
+        t, tm = cpu_whole_pair(cfg, sd, data, perms, best)
+        times.append(t)
+        for k, v in tm.items():
+            stages[k] = stages.get(k, 0.0) + v / args.steps
     sec = float(np.mean(times))
     val = 1.0 / sec
     line = {"metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{args.workload}: 2x{len(data['src_fds_pcd'])} pts, {cfg.patch.num_fps} kpts, {cfg.patch.num_points_per_patch} pts/patch, "
-                                   f"{cfg.patch.num_scales} scales, {cfg.match.iter_n} RANSAC iters, seeded synthetic weights",
-                       "note": "CPU oracle port of the reference path on the host cores (oracle/)"},
-            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc},
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if args.workload == "C4" else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": static_config(args.workload, cfg, ns, nt),
+            "run": {"pairs_per_step": 1, "note": "CPU oracle port of the reference path (oracle/), one WHOLE pair per step, nothing extrapolated",
+                    "thread_sweep_s": {str(k): v for k, v in sweep.items()}},
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": best, "host_cpus": os.cpu_count(), "kind": "port",
+                             "sample": f"{args.steps} whole {wl} pairs, one per step, {best} threads (measured sweep over 8/16/32/64/all of a reduced pair)",
+                             "stage_seconds_per_pair": {k: round(v, 4) for k, v in stages.items()}},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C5"])
-    ap.add_argument("--cpu-frac", type=float, default=None,
-                    help="fraction of the key-points the CPU sample runs the per-key-point stages on (default: 1.0 for the\n"
-                         "cpu_baseline leg = whole pairs, 0.25 per step for --impl reference)")
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="BASELINE.json configs; C4 = 512 C2 pairs split round-robin over the ranks (strong scaling, one step = the whole job)")
+    ap.add_argument("--pairs-per-step", type=int, default=None, help="pairs per step and rank (default: C2 32, C3 8, C5 16; C4: 512 / world)")
     ap.add_argument("--depth", type=int, default=6,
-                    help="pairs in flight per GPU (CUDA-graph slots on separate streams).  Measured on 1xB200 at the final commit "
-                         "(20 steps): 4 -> 111.7, 6 -> 112.8, 8 -> 114.3 pairs/s; earlier 2 -> 92.6, 3 -> 97.3, 4 -> 100.3")
+                    help="pairs in flight per GPU (CUDA-graph slots on separate streams).  Measured on 1xB200 (round 1): "
+                         "2 -> 92.6, 3 -> 97.3, 4 -> 111.7, 6 -> 112.8, 8 -> 114.3 pairs/s")
+    ap.add_argument("--cpu-threads", type=int, default=None, help="skip the CPU thread sweep and use this many threads")
+    ap.add_argument("--cpu-pairs", type=int, default=2, help="whole pairs of the cpu_baseline leg (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--short", action="store_true", help="profiling runs under ncu: allow < 3 warm-up steps, skip the e2e leg")
+    ap.add_argument("--short", action="store_true", help="profiling runs under ncu: allow < 3 warm-up steps, skip the e2e legs")
     args = ap.parse_args()
     if args.impl == "ours" and not args.short:
         args.warmup = max(args.warmup, 3)
@@ -254,43 +260,55 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops.load_library()
-    cfg = workload_cfg(args.workload)
+    strong = args.workload == "C4"
+    wl = "C2" if strong else args.workload
+    cfg = workload_cfg(wl)
     model = init_synthetic_weights(bx.BufferX(cfg), trained_pose=True).to(dev)
     sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     S = cfg.patch.num_scales
 
-    # ---- a pool of distinct synthetic pairs; rank r starts at pair r (round-robin sharding of a virtual list)
-    pool = 4
+    # ---- this rank's pairs: pair i of the (virtual) list lives on rank i mod world ------------------
+    if strong:
+        total_pairs = args.pairs_per_step or 512
+        my_ids = list(range(rank, total_pairs, world))
+    else:
+        per = args.pairs_per_step or DEFAULT_BATCH[wl]
+        total_pairs = per * world
+        my_ids = [j * world + rank for j in range(per)]
+    B = len(my_ids)                                   # pairs per step on this rank
     host, devd = [], []
-    for j in range(pool):
-        d = make_pair(args.workload, rank * pool + j)
+    for pid in my_ids:
+        d = make_pair(wl, pid)
         ns, nt = len(d["src_fds_pcd"]), len(d["tgt_fds_pcd"])
-        st = np.random.RandomState(1000 + rank * pool + j)
+        st = np.random.RandomState(1000 + pid)
         perms = [(st.choice(ns, ns, replace=False).astype(np.int32), st.choice(nt, nt, replace=False).astype(np.int32)) for _ in range(S)]
         h = dict(d)
         h["src_fds_pcd"] = torch.from_numpy(d["src_fds_pcd"]).pin_memory()
         h["tgt_fds_pcd"] = torch.from_numpy(d["tgt_fds_pcd"]).pin_memory()
         hp = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in perms]
-        host.append((h, hp, d, perms))
+        host.append((h, hp, d, perms, pid))
         g = dict(d)
         g["src_fds_pcd"] = h["src_fds_pcd"].to(dev)
         g["tgt_fds_pcd"] = h["tgt_fds_pcd"].to(dev)
         devd.append((g, [(a.to(dev), b.to(dev)) for a, b in hp]))
     ns, nt = len(host[0][2]["src_fds_pcd"]), len(host[0][2]["tgt_fds_pcd"])
-    h2d_bytes = (ns + nt) * 12 + S * (ns + nt) * 4
-    d2h_bytes = (18 + S + 2 + 16) * 8
+    h2d_pair = (ns + nt) * 12 + S * (ns + nt) * 4
+    d2h_pair = (18 + S + 2 + 16) * 8
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    rte_th, rre_th = cfg.test.rte_thresh, cfg.test.rre_thresh
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    DEPTH = max(1, args.depth)   # pairs in flight per GPU (separate streams; one captured CUDA graph per slot)
+    DEPTH = max(1, min(args.depth, B))   # pairs in flight per GPU (separate streams; one captured CUDA graph per slot)
     model.enable_cuda_graphs(True, slots_per_shape=DEPTH)
 
     def run_pipelined(mode, steps, timed):
-        """mode 'dev': inputs resident in HBM; 'e2e': pinned host tensors through the public forward_async()."""
+        """`steps` batches of this rank's B pairs, DEPTH pairs in flight, then (when timed) the all-gather of the records --
+        everything between two CUDA events.  mode 'dev': inputs resident in HBM; 'e2e': pinned host tensors through the
+        public forward_async()."""
         recs, handles = [], []
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -299,50 +317,77 @@ def main():
             for sl in slots:
                 sl.stream.wait_event(a)
 
-        def collect(h, s):
+        def collect(h, s, j):
             out = h.result()
             if timed:
-                gt = host[s % pool][2]["relt_pose"]
+                gt = host[j][2]["relt_pose"]
                 rte, rre = compute_rte(out[0], gt), compute_rre(out[0], gt)
-                recs.append(pack_record(rank + world * s, out[0], out[1], out[2], out[3], out[4], out[5], rte, rre,
-                                        float(rre < 15.0 and rte < 0.3)))   # 3DMatch success criterion of the reference
+                recs.append(pack_record(s * total_pairs + host[j][4], out[0], out[1], out[2], out[3], out[4], out[5], rte, rre,
+                                        float(rre < rre_th and rte < rte_th)))   # success criterion of the reference (test.py:168-172)
 
+        allrec = None
         for s in range(steps):
-            j = s % pool
-            if len(handles) == DEPTH:
-                collect(*handles.pop(0))
-            with torch.no_grad():
-                if mode == "dev":
-                    h = model.forward_async(devd[j][0], perms=devd[j][1])
-                else:
-                    h = model.forward_async(host[j][0], perms=host[j][1])
-            handles.append((h, s))
+            for j in range(B):
+                if len(handles) == DEPTH:
+                    collect(*handles.pop(0))
+                with torch.no_grad():
+                    if mode == "dev":
+                        h = model.forward_async(devd[j][0], perms=devd[j][1])
+                    else:
+                        h = model.forward_async(host[j][0], perms=host[j][1])
+                handles.append((h, s, j))
+            if strong:                                  # C4: every step is the whole job, gather included
+                while handles:
+                    collect(*handles.pop(0))
+                if timed:
+                    allrec = gather_records(np.stack(recs[-B:]), total_pairs, device=dev)
         while handles:
             collect(*handles.pop(0))
         cur = torch.cuda.current_stream()
         for slots in model._slots.values():
             for sl in slots:
                 cur.wait_stream(sl.stream)
+        if timed and not strong:
+            allrec = gather_records(np.stack(recs), steps * total_pairs, device=dev)   # the one collective of the path
         b.record()
         b.synchronize()
-        return a.elapsed_time(b), recs
+        return a.elapsed_time(b), allrec
 
-    def run_eager(steps):
+    ransac_stats = []
+
+    def run_eager(steps, record=False):
         """Per-kernel event brackets (ops.Profiler) need eager launches: the roofline pass."""
         model.enable_cuda_graphs(False)
         ms = 0.0
         for s in range(steps):
-            j = s % pool
+            j = s % B
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             with torch.no_grad():
-                model(devd[j][0], perms=devd[j][1], ransac_seed=s)
+                out = model(devd[j][0], perms=devd[j][1], ransac_seed=s)
             b.record()
             b.synchronize()
             ms += a.elapsed_time(b)
+            if record:
+                ransac_stats.append((out[4], model._last_ransac["iters"]))
         model.enable_cuda_graphs(True, slots_per_shape=DEPTH)
         return ms
+
+    def single_call_latency(n, graphs):
+        """The reference's serial loop (test.py:132-146): one `model(data_source)` at a time with host tensors."""
+        model.enable_cuda_graphs(graphs, slots_per_shape=1 if graphs else DEPTH)
+        ts = []
+        for s in range(n + 2):
+            j = s % B
+            np.random.seed(s)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                model(host[j][0], perms=host[j][1])
+            ts.append((time.perf_counter() - t0) * 1e3)
+        model.enable_cuda_graphs(True, slots_per_shape=DEPTH)
+        return float(np.median(ts[2:]))
 
     l0 = ops.launch_count()
     run_eager(1)                                            # also sets every kernel attribute before graph capture
@@ -350,25 +395,28 @@ def main():
     # ---- roofline pass: eager launches with per-kernel CUDA-event brackets (before the graph pools exist) ----
     run_eager(2)
     ops.profiler = ops.Profiler()
-    n_eager = min(args.steps, 5)
-    ms_eager = run_eager(n_eager)
+    n_eager = min(B, 6)
+    ms_eager = run_eager(n_eager, record=True)
     prof = ops.profiler.summary()
     ops.profiler = None
-    run_pipelined("dev", max(args.warmup, DEPTH), False)    # captures the graphs, warms up
+    single = None
+    if not args.short:
+        single = {"eager_ms": single_call_latency(8, False), "graph_ms": single_call_latency(8, True)}
+    run_pipelined("dev", 1 if strong else max(1, min(args.warmup, 2)), False)    # captures the graphs
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     # ---- timed region 1: inputs resident in HBM ----------------------------------------------------
+    if not strong:
+        run_pipelined("dev", args.warmup, False)
     barrier()
-    ms_dev, recs = run_pipelined("dev", args.steps, True)
-    allrec = gather_records(np.stack(recs), world * args.steps, device=dev)   # the one collective of the path
+    ms_dev, allrec = run_pipelined("dev", args.steps, True)
     barrier()
-    launches = launches_per_pair * args.steps
     # ---- timed region 2: host buffers through the public API --------------------------------------
     if args.short:
         ms_e2e = float("nan")
     else:
-        run_pipelined("e2e", DEPTH, False)
+        run_pipelined("e2e", 1, False)
         barrier()
         ms_e2e, _ = run_pipelined("e2e", args.steps, True)
         barrier()
@@ -380,8 +428,9 @@ def main():
     ms_dev, ms_e2e = float(t[0]), float(t[1])
     if rank == 0:
         pk = measured_peaks()
-        value = world * args.steps / (ms_dev / 1e3)
-        e2e = world * args.steps / (ms_e2e / 1e3)
+        n_pairs_timed = args.steps * total_pairs
+        value = n_pairs_timed / (ms_dev / 1e3)
+        e2e = n_pairs_timed / (ms_e2e / 1e3)
         cd = prof.get("conv_desc", dict(launches=0, ms=0.0, work=0.0))
         ach_tf = cd["work"] / (cd["ms"] / 1e3) / 1e12 if cd["ms"] > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (Cylindrical_Net layers; tcgen05 kind::tf32, 3xTF32 split, fp32-equivalent FLOPs)",
@@ -395,39 +444,50 @@ def main():
         if sp and sp["ms"] > 0:
             gbs = sp["work"] / (sp["ms"] / 1e3) / 1e9
             kern["select_patches"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-                                      "launches": sp["launches"], "avg_launch_ms": sp["ms"] / sp["launches"]}
-        for k in ("conv_cost", "spt", "lrf", "fps", "ransac"):
+                                      "launches": sp["launches"], "avg_launch_ms": sp["ms"] / sp["launches"],
+                                      "algorithmic_bytes_per_launch": sp["work"] / sp["launches"]}
+        rs = prof.get("ransac")
+        if rs and rs["ms"] > 0 and ransac_stats:
+            comp = sum(24.0 * i for i, _ in ransac_stats)                    # 24*I bytes read once
+            logical = sum(24.0 * i * it for i, it in ransac_stats)           # iterations_run * I * 24 if nothing were cached
+            kern["ransac"] = {"bound": "hbm", "achieved": comp / (rs["ms"] / 1e3) / 1e9, "achieved_logical": logical / (rs["ms"] / 1e3) / 1e9,
+                              "peak": pk["hbm"], "unit": "GB/s", "frac": comp / (rs["ms"] / 1e3) / 1e9 / pk["hbm"],
+                              "frac_logical": logical / (rs["ms"] / 1e3) / 1e9 / pk["hbm"], "launches": rs["launches"],
+                              "avg_ms": rs["ms"] / rs["launches"], "mean_correspondences": float(np.mean([i for i, _ in ransac_stats])),
+                              "mean_iterations_run": float(np.mean([it for _, it in ransac_stats])),
+                              "note": "compulsory = 24*I bytes (the consensus set lives in shared memory / L1 after the first read); "
+                                      "logical = iterations_run*I*24, what a cache-less inlier counter would stream"}
+        for k in ("conv_cost", "spt", "lrf", "fps"):
             if k in prof:
                 kern[k] = {"launches": prof[k]["launches"], "avg_ms": prof[k]["ms"] / max(prof[k]["launches"], 1),
                            "share_of_step": prof[k]["ms"] / ms_eager}
+        cfgd = static_config(args.workload, cfg, ns, nt)
+        run = {"pairs_per_step_per_rank": B, "pairs_per_step": total_pairs, "pairs_timed": n_pairs_timed, "distinct_pairs_per_rank": B,
+               "timed_region_s": ms_dev / 1e3, "pairs_in_flight": DEPTH, "cuda_graphs": True,
+               "eager_ms_per_pair": ms_eager / max(n_eager, 1), "ms_per_pair": ms_dev / (args.steps * B),
+               "registration_success": float(np.mean(allrec[:, 25])), "median_rre_deg": float(np.median(allrec[:, 24])),
+               "median_rte_m": float(np.median(allrec[:, 23])), "mean_mutual_matches": float(np.mean(allrec[:, 20])),
+               "mean_consensus_inliers": float(np.mean(allrec[:, 21])), "records_gathered": int(allrec.shape[0])}
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: 2x{ns} pts, {cfg.patch.num_fps} kpts, {cfg.patch.num_points_per_patch} pts/patch, "
-                                       f"{S} scales, {cfg.match.iter_n} RANSAC iters, seeded synthetic weights",
-                           "pairs_per_rank": args.steps, "sharding": "pair i -> rank i mod world, one all_gather of 32-float records",
-                           "l2": "per-pair working set (~1 GB of activations) exceeds the 126 MB L2; eager pass flushes 256 MB between steps",
-                           "pairs_in_flight": DEPTH, "cuda_graphs": True, "eager_ms_per_step": ms_eager / max(n_eager, 1),
-                           "weights": "seeded synthetic descriptor weights; CostNet fitted on disjoint synthetic pairs "
-                                      "(tests/tools/train_costnet.py) so that the pairs register",
-                           "registration_success": float(np.mean(allrec[:, 25])),
-                           "median_rre_deg": float(np.median(allrec[:, 24])), "median_rte_m": float(np.median(allrec[:, 23])),
-                           "mean_mutual_matches": float(np.mean(allrec[:, 20])),
-                           "mean_consensus_inliers": float(np.mean(allrec[:, 21]))},
-                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfgd, "run": run,
+                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d_pair * total_pairs, "d2h_bytes_per_step": d2h_pair * total_pairs,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "kernels": kern}
-        if not args.no_cpu_baseline and world == 1:       # the CPU baseline is reported at N = 1 only
-            from oracle import oracle as O
+                "e2e_single_call": single,
+                "gpu_launches": int(launches_per_pair * args.steps * B), "clocks": sampler.summary(), "roofline": roof, "kernels": kern}
+        if not args.no_cpu_baseline and world == 1 and not args.short:       # the CPU baseline is reported at N = 1 only
             t0 = time.perf_counter()
+            best, sweep = cpu_thread_sweep(cfg, sd_cpu, host[0][2], host[0][3], fixed=args.cpu_threads)
             secs, stages = [], {}
-            for h in host[:2]:                              # two whole pairs: ~10 s of CPU work on the box
-                sec, cores, desc, st = cpu_sample(args.workload, cfg, sd_cpu, h[2], h[3], frac=args.cpu_frac or 1.0)
+            for h in host[:max(1, args.cpu_pairs)]:          # whole pairs: ~10 s of CPU work each on the box
+                sec, st = cpu_whole_pair(cfg, sd_cpu, h[2], h[3], best)
                 secs.append(sec)
                 for k, v in st.items():
-                    stages[k] = stages.get(k, 0.0) + v / 2
+                    stages[k] = stages.get(k, 0.0) + v / max(1, args.cpu_pairs)
             sec = float(np.mean(secs))
-            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": f"{len(secs)} pairs; " + desc,
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "pairs/s", "cores": best, "host_cpus": os.cpu_count(), "kind": "port",
+                                    "sample": f"{len(secs)} whole {wl} pairs through the CPU oracle port, {best} threads "
+                                              f"(measured sweep of a reduced pair, seconds per thread count: {sweep})",
                                     "stage_seconds_per_pair": {k: round(v, 4) for k, v in stages.items()},
                                     "wall_s": round(time.perf_counter() - t0, 2)}
         print(json.dumps(line), flush=True)

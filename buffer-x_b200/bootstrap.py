@@ -1,5 +1,9 @@
 """GPU mirror of the reference's loader-side geometric bootstrapping.
 
+Lives INSIDE the package (``bufferx_b200.bootstrap``), not in a top-level ``utils/`` directory: the reference's
+``utils`` is a namespace package (no ``__init__.py``) and a regular ``utils`` package ahead of it on ``sys.path`` would
+hide ``utils.timer`` / ``utils.SE3`` / ... from the reference's ``test.py``.
+
 ``sphericity_based_voxel_analysis`` keeps the reference's name, argument order and return tuple
 (/root/reference/utils/tools.py:152-198); clouds are [N,3] arrays / CUDA tensors (or objects with a ``.points``
 attribute, like the reference's Open3D clouds).  ``voxel_down_sample`` replaces

@@ -21,8 +21,11 @@ BX_API int bx_version(void) { return 100; }
 BX_API unsigned long long bx_launch_count(void) { return g_bx_launches; }
 
 BX_API int bx_device_sm_count(void) {
+    static int cache[BX_MAX_DEVICES] = {};      // per device ordinal (0 = not queried yet)
     int dev = 0, n = 0;
     BX_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < BX_MAX_DEVICES && cache[dev]) return cache[dev];
     BX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < BX_MAX_DEVICES) cache[dev] = n;
     return n;
 }

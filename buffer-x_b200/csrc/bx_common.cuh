@@ -44,6 +44,21 @@ extern unsigned long long g_bx_launches;  // kernels launched by this library si
 
 static inline cudaStream_t bx_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are PER-DEVICE: one flag / value per device ordinal,
+// so a process that drives several GPUs configures each of them (a plain `static bool` configured only the first).
+constexpr int BX_MAX_DEVICES = 64;
+struct BxPerDevice {
+    size_t v[BX_MAX_DEVICES];   // 0 = not configured yet on that device; otherwise the configured value
+};
+// true when `want` exceeds what this device has been configured with (and records it)
+static inline bool bx_needs_attr(BxPerDevice &f, size_t want = 1) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= BX_MAX_DEVICES) return true;
+    if (f.v[d] >= want) return false;
+    f.v[d] = want;
+    return true;
+}
+
 #define BX_FULL 0xffffffffu
 
 __device__ __forceinline__ int bx_lane() { return threadIdx.x & 31; }

@@ -440,17 +440,11 @@ BX_API int bx_costvol_ab(const float *equi_s, const float *equi_t, const int32_t
     BX_REQUIRE(((reinterpret_cast<uintptr_t>(wa) | reinterpret_cast<uintptr_t>(wb)) & 15) == 0, "bx_costvol_ab: weights must be 16-byte aligned");
     if (maxM == 0) return BX_OK;
     BX_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0, "bx_costvol_ab: A and B must be 16-byte aligned");
-    static bool attr_done = false;
-    if (!attr_done) {
+    static BxPerDevice attr_done = {};
+    if (bx_needs_attr(attr_done))
         BX_CUDA(cudaFuncSetAttribute(costvol_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-        attr_done = true;
-    }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        BX_CUDA(cudaGetDevice(&dev));
-        BX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int sms = bx_device_sm_count();
+    if (sms <= 0) sms = 148;
     const int grid = (maxM + 1) / 2 < sms ? (maxM + 1) / 2 : sms;
     costvol_ab_kernel<<<grid, AB_T, AB_SMEM, bx_stream(stream)>>>(equi_s, equi_t, s_mids, t_mids, d_M, wa, wb, bias, A, B);
     BX_LAUNCH_CHECK();

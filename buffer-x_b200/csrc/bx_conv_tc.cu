@@ -558,11 +558,9 @@ int launch_tc(const ConvTcParams &p, int max_n, cudaStream_t st) {
     const unsigned gx = (unsigned)((maxM + TC_BM - 1) / TC_BM);
     if (gx == 0) return BX_OK;
     constexpr int smem = BRing<NT>::SB * BRing<NT>::NBS * (2 * 2 * 2 * NT * 16);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static BxPerDevice attr_done = {};
+    if (bx_needs_attr(attr_done))
         BX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<GEOM, NT, LG, NSETS, MINB, XSEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
     conv_tc_kernel<GEOM, NT, LG, NSETS, MINB, XSEP><<<gx, LG * 128 + 64, smem, st>>>(p);
     BX_LAUNCH_CHECK();
     return BX_OK;

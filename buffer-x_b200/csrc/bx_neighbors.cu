@@ -201,11 +201,9 @@ BX_API int bx_radius_neighbors(const float *queries, int nq, const float *suppor
     BX_CUDA(cudaMemsetAsync(d_max_count, 0, sizeof(int), st));
     if (nq == 0) return BX_OK;
     const size_t smem = RN_CAP * (sizeof(double) + sizeof(int));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static BxPerDevice attr_done = {};
+    if (bx_needs_attr(attr_done))
         BX_CUDA(cudaFuncSetAttribute(radius_neighbors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
     radius_neighbors_kernel<<<nq, RN_THREADS, smem, st>>>(queries, nq, supports, bt, radius, out, cap, d_max_count);
     BX_LAUNCH_CHECK();
     return BX_OK;

@@ -202,8 +202,9 @@ __device__ __forceinline__ void jacobi_rot3(double (&A)[3][3], double (&V)[3][3]
 constexpr int LRF_WARPS = 4;
 
 __global__ void __launch_bounds__(LRF_WARPS * 32)
-lrf_kernel(const float *__restrict__ patches, int K, int P, float des_r_v, const float *__restrict__ d_des_r, int aligned,
+lrf_kernel(const float *__restrict__ patches, int K, int P, float des_r_v, const float *__restrict__ d_des_r, int flags,
            float *__restrict__ delta, float *__restrict__ Rt, float *__restrict__ rand_axis) {
+    const int aligned = flags & 1, stable = flags & 2;
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * LRF_WARPS + (threadIdx.x >> 5);
     if (k >= K) return;
@@ -258,7 +259,15 @@ lrf_kernel(const float *__restrict__ patches, int K, int P, float des_r_v, const
         z0 = z0 / nz; z1 = z1 / nz; z2 = z2 / nz;
         const float n = sqrtf(((z0 * z0) + (z1 * z1)) + (z2 * z2));
         const float sn = sqrtf((z0 * z0) + (z1 * z1));
-        const float ct = z2 / n, st = sn / n;
+        float ct = z2 / n, st = sn / n;
+        if (!stable) {
+            // RodsRotatFormula literally (utils/common.py:506, 522): theta = acos(cosine_similarity(z, e_z)), then
+            // sin(theta) / cos(theta).  fp32 results are the correctly rounded ones (evaluated in fp64, rounded once),
+            // which the CPU oracle reproduces bit for bit; CUDA's acosf/sinf/cosf are 1-2 ulp routines of their own.
+            const float theta = (float)acos((double)ct);
+            st = (float)sin((double)theta);
+            ct = (float)cos((double)theta);
+        }
         const float den = sn > 1e-12f ? sn : 1e-12f;
         const float a0 = z1 / den, a1 = (-z0) / den;
         const float kk = 1.0f - ct;
@@ -322,13 +331,13 @@ BX_API int bx_ball_query(const float *xyz, int n, const float *qry, int m, float
     return BX_OK;
 }
 
-BX_API int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r, int aligned, float *delta,
+BX_API int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r, int flags, float *delta,
                   float *Rt, float *rand_axis, void *stream) {
     BX_REQUIRE(patches && delta && Rt && rand_axis, "bx_lrf: null pointer");
     BX_REQUIRE(K >= 0 && P >= 1, "bx_lrf: bad sizes");
     if (K == 0) return BX_OK;
     lrf_kernel<<<(K + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, 0, bx_stream(stream)>>>(patches, K, P, des_r, d_des_r,
-                                                                                           aligned, delta, Rt, rand_axis);
+                                                                                           flags, delta, Rt, rand_axis);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

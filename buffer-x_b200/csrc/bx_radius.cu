@@ -141,11 +141,9 @@ BX_API int bx_radius_estimate(const float *kpts, int Kr, const float *pts, int N
     cudaStream_t st = bx_stream(stream);
     BX_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (NB + 2), st));
     const size_t smem = sizeof(float) * (NB + 1) + sizeof(uint32_t) * (NB + 3) + sizeof(float4) * KT;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static BxPerDevice attr_done = {};
+    if (bx_needs_attr(attr_done))
         BX_CUDA(cudaFuncSetAttribute(radius_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
     int sms = bx_device_sm_count();
     if (sms <= 0) sms = 148;
     const int gy = (Kr + KT - 1) / KT;

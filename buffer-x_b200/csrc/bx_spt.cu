@@ -268,11 +268,9 @@ BX_API int bx_spt_pnt(const float *delta, int K, int P, const float *voxels, int
     if (K == 0) return BX_OK;
     const size_t smem = spt_smem_bytes(P, V, azi_n);
     BX_REQUIRE(smem <= 200 * 1024, "bx_spt_pnt: P=%d V=%d needs %zu bytes of shared memory", P, V, smem);
-    static size_t attr = 0;
-    if (smem > attr) {
+    static BxPerDevice attr = {};
+    if (bx_needs_attr(attr, smem))
         BX_CUDA(cudaFuncSetAttribute(spt_pnt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
     spt_pnt_kernel<<<K, SPT_THREADS, smem, bx_stream(stream)>>>(delta, K, P, voxels, V, azi_n, rot, voxel_r, nv, w, b,
                                                              feat, dbg_vidx, dbg_inv);
     BX_LAUNCH_CHECK();

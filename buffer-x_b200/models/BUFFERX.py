@@ -103,7 +103,7 @@ class _PairSlot:
         self.tail = None
         self.busy = False
         if use_graph:
-            with torch.cuda.stream(self.stream):
+            with torch.cuda.device(dev), torch.cuda.stream(self.stream):
                 self.src.zero_(); self.tgt.zero_()
                 base = torch.arange(max(Ns, Nt), dtype=torch.int32, device=dev)
                 self.perm_s.copy_(base[:Ns].expand(S, Ns)); self.perm_t.copy_(base[:Nt].expand(S, Nt))
@@ -112,7 +112,7 @@ class _PairSlot:
                 self._enqueue()                                            # eager warm-up on this stream
             self.stream.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=self.stream):
+            with torch.cuda.device(dev), torch.cuda.graph(self.graph, stream=self.stream):
                 self.tail = self._enqueue()
         # pinned landing buffer for the result block
         n_tail = 18 + (S + 1) + 1 + 1 + 16   # RANSAC block, scale offsets, consensus count, scales used, refined pose
@@ -124,10 +124,15 @@ class _PairSlot:
 
     def launch(self, data_source, perms):
         """H2D of the inputs (pinned staging when they arrive as host arrays), the pair, D2H of the result."""
-        with torch.cuda.stream(self.stream):
+        # CUDA inputs may still be in flight on the caller's stream (`.cuda(non_blocking=True)`, a voxel_down_sample
+        # kernel): the slot stream starts after everything the caller has enqueued so far, and the caching allocator is
+        # told that the slot stream reads them (so the memory is not handed out again before the copy has run).
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
             for dst, hbuf, x in ((self.src, self.h_src, data_source["src_fds_pcd"]), (self.tgt, self.h_tgt, data_source["tgt_fds_pcd"])):
                 x = torch.as_tensor(x)
                 if x.is_cuda:
+                    x.record_stream(self.stream)
                     dst.copy_(x.reshape(-1, 3), non_blocking=True)
                 else:
                     if x.is_pinned():
@@ -143,6 +148,7 @@ class _PairSlot:
                 else:
                     ps, pt = perms[i]
                     if isinstance(ps, torch.Tensor) and ps.is_cuda:
+                        ps.record_stream(self.stream); pt.record_stream(self.stream)
                         self.perm_s[i].copy_(ps, non_blocking=True); self.perm_t[i].copy_(pt, non_blocking=True)
                         continue
                     self.h_perm_s[i].copy_(torch.as_tensor(ps, dtype=torch.int32)); self.h_perm_t[i].copy_(torch.as_tensor(pt, dtype=torch.int32))
@@ -183,6 +189,34 @@ class BufferX(nn.Module):
     def get_parameter(self):
         return list(self.parameters())
 
+    # Captured graphs bake in the device pointers of the folded weights (and live on one device): anything that can
+    # replace the parameters -- load_state_dict(), .to()/.cuda()/.half()/.float() -- drops the captured slots and the
+    # per-stream RANSAC workspaces, so the next forward re-captures against the new buffers.
+    def _drop_captured_state(self):
+        for slots in self._slots.values():
+            for sl in slots:
+                if sl.busy:
+                    sl.done.synchronize()
+        self._slots.clear()
+        self._rr.clear()
+        pe = getattr(self, "pose_estimator", None)
+        if pe is not None and hasattr(pe, "_ws"):
+            pe._ws.clear()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_slots"):
+            self._drop_captured_state()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._drop_captured_state()
+        for m in self.modules():
+            if hasattr(m, "invalidate"):
+                m.invalidate()
+        return out
+
     # ------------------------------------------------------------------------------------------------
     def mutual_matching(self, src_des, tgt_des):
         """[M,C],[N,C] -> (s_mids, t_mids) int64, like the reference (one device->host read for M)."""
@@ -222,6 +256,10 @@ class BufferX(nn.Module):
             # those, run eager (`enable_cuda_graphs(False)`) or pad/bucket the clouds upstream
             for old in list(self._slots):
                 if all(not sl.busy for sl in self._slots[old]):
+                    pe = getattr(self, "pose_estimator", None)
+                    for sl in self._slots[old]:
+                        if pe is not None and hasattr(pe, "_ws"):
+                            pe._ws.pop((str(sl.dev), sl.stream.cuda_stream), None)
                     del self._slots[old]
                     self._rr.pop(old, None)
                     break
@@ -303,7 +341,9 @@ class BufferX(nn.Module):
                     if pm is None:
                         pm = np.random.choice(pts_c.shape[0], pts_c.shape[0], replace=False)
                     if not isinstance(pm, torch.Tensor):
-                        pm = torch.from_numpy(np.ascontiguousarray(pm, dtype=np.int32)).to(dev, non_blocking=True)
+                        pm = torch.from_numpy(np.ascontiguousarray(pm, dtype=np.int32))
+                    if not pm.is_cuda or pm.dtype != torch.int32:
+                        pm = pm.to(dev, dtype=torch.int32, non_blocking=True)
                     jobs.append((pts_c, k_c, r_dev[i:i + 1], pm))
             batched = self.Desc.forward_multi(jobs, aligned)
             desc_t.toc()
@@ -410,14 +450,14 @@ class BufferX(nn.Module):
             x = torch.as_tensor(x)
             return x.to(dev, dtype=torch.float32, non_blocking=True).reshape(-1, 3).contiguous()
 
-        src, tgt = _cloud(data_source["src_fds_pcd"]), _cloud(data_source["tgt_fds_pcd"])
         aligned = bool(data_source["is_aligned_to_global_z"])
         enable_timing = cfg.test.get("enable_timing", False)
-        timers = (_Timer(enable_timing), _Timer(enable_timing), _Timer(enable_timing))
-        tail, dbg = self._enqueue(src, tgt, aligned, perms, ransac_seed, debug, timers)
-        timers[2].tic()
+        with torch.cuda.device(dev):        # kernels launch on the model's device, whatever the caller's current device
+            src, tgt = _cloud(data_source["src_fds_pcd"]), _cloud(data_source["tgt_fds_pcd"])
+            timers = (_Timer(enable_timing), _Timer(enable_timing), _Timer(enable_timing))
+            tail, dbg = self._enqueue(src, tgt, aligned, perms, ransac_seed, debug, timers)
         tail_h = tail.cpu()                 # the one device->host read of the pair
-        timers[2].toc()
+        timers[2].toc()                     # pairs with the tic before RANSAC / refinement in _enqueue (pose_optim time)
         out = self._decode(tail_h, [timers[0].total, timers[1].total, timers[2].total])
         if debug:
             dbg.update(self._last_ransac)

@@ -96,6 +96,11 @@ def _dp(t, dtype=None, name="tensor"):
         raise BufferXError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise BufferXError(f"{name}: tensor must be contiguous")
+    if t.device.index != torch.cuda.current_device():
+        # the C-ABI launches on the CURRENT device and stream: a tensor of another GPU would be dereferenced by a kernel
+        # running on the wrong one.  BufferX.forward enters torch.cuda.device(model device) itself.
+        raise BufferXError(f"{name}: tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "call under `with torch.cuda.device(tensor.device):`")
     return t.data_ptr()
 
 
@@ -238,7 +243,8 @@ def lrf(patches: torch.Tensor, des_r, aligned: bool, delta=None, Rt=None, ra=Non
         ra = torch.empty((K, 3), dtype=F32, device=dev)
     rv, rp = (0.0, _dp(des_r, F32, "des_r")) if isinstance(des_r, torch.Tensor) else (float(des_r), None)
     with _Span("lrf", 24.0 * K * P):
-        _check(load_library().bx_lrf(_dp(patches, F32, "patches"), K, P, rv, rp, int(bool(aligned)), _dp(delta), _dp(Rt), _dp(ra), _stream()), "bx_lrf")
+        flags = int(bool(aligned)) | (2 if os.environ.get("BX_LRF", "").lower() == "stable" else 0)
+        _check(load_library().bx_lrf(_dp(patches, F32, "patches"), K, P, rv, rp, flags, _dp(delta), _dp(Rt), _dp(ra), _stream()), "bx_lrf")
     return delta, Rt, ra
 
 

@@ -82,8 +82,10 @@ int bx_ball_query(const float *xyz, int n, const float *qry, int m, float radius
 /* ---- a4+a5: local reference frame + normalisation -------------------------------------------
  * Replaces MiniSpinNet.axis_align / normalize (models/patch_embedder.py:122-148, 167-170),
  * cal_Z_axis (utils/common.py:709-726, torch_batch_svd) and RodsRotatFormula (:501-525).
- * delta: [K,P,3]; Rt: [K,3,3] (the reference's returned "R"); rand_axis: [K,3]. */
-int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r, int aligned, float *delta,
+ * delta: [K,P,3]; Rt: [K,3,3] (the reference's returned "R"); rand_axis: [K,3].
+ * flags: bit 0 = is_aligned_to_global_z (identity frame); bit 1 = well-conditioned Rodrigues (cos = z_z/|z|,
+ * sin = |z x e_z|/|z|) instead of the reference's theta = acos(cos) -> sin(theta), cos(theta) (default, literal). */
+int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r, int flags, float *delta,
            float *Rt, float *rand_axis, void *stream);
 
 /* ---- a6+a7: spherical-voxel transformer + point layer ---------------------------------------

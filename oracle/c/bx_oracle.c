@@ -225,8 +225,14 @@ static void jacobi3(double A[3][3], double V[3][3]) {
     }
 }
 
-BX_EXPORT int bxo_lrf(const float *patches, int K, int P, float des_r, int aligned, float *delta, float *Rt,
-                      float *rand_axis) {
+BX_EXPORT int bxo_lrf(const float *patches, int K, int P, float des_r, int flags, float *delta, float *Rt,
+                      float *rand_axis, const float *z_override, float *z_out) {
+    /* flags: bit 0 = is_aligned_to_global_z; bit 1 = well-conditioned Rodrigues (cos = z_z/|z|, sin = |z x e_z|/|z|,
+     * NOT the reference's formula; kept for the sensitivity report of oracle/ref_check.py).
+     * z_override [K,3] (optional): the disambiguated, normalised z axes to use instead of this function's own
+     * covariance + Jacobi result -- ref_check.py feeds the reference run's axes through it so that everything
+     * downstream of the (BLAS-order dependent) covariance sum can be compared exactly.  z_out [K,3] (optional). */
+    const int aligned = flags & 1, stable = flags & 2;
 #pragma omp parallel for schedule(static)
     for (int k = 0; k < K; ++k) {
         const float *pt = patches + (size_t)k * P * 3;
@@ -273,10 +279,21 @@ BX_EXPORT int bxo_lrf(const float *patches, int K, int P, float des_r, int align
             if (sgn < 0.0f) { z0 = -z0; z1 = -z1; z2 = -z2; }
             const float nz = sqrtf(((z0 * z0) + (z1 * z1)) + (z2 * z2));
             z0 = z0 / nz; z1 = z1 / nz; z2 = z2 / nz;
+            if (z_override) { z0 = z_override[3 * k]; z1 = z_override[3 * k + 1]; z2 = z_override[3 * k + 2]; }
+            if (z_out) { z_out[3 * k] = z0; z_out[3 * k + 1] = z1; z_out[3 * k + 2] = z2; }
             /* Rodrigues z -> e_z */
             const float n = sqrtf(((z0 * z0) + (z1 * z1)) + (z2 * z2));
             const float sn = sqrtf((z0 * z0) + (z1 * z1));
-            const float ct = z2 / n, st = sn / n;
+            float ct = z2 / n, st = sn / n;
+            if (!stable) {
+                /* RodsRotatFormula literally (utils/common.py:506, 522-523): theta = acos(cosine_similarity(z, e_z))
+                 * in fp32, then sin(theta), cos(theta) in fp32.  "fp32" = the correctly rounded value (fp64 libm
+                 * rounded once), the one definition a CPU and a GPU can both reproduce bit for bit; torch's own
+                 * acos/sin/cos (Sleef on CPU, CUDA libm on the GPU) are each within 1 ulp of it. */
+                const float theta = (float)acos((double)ct);
+                st = (float)sin((double)theta);
+                ct = (float)cos((double)theta);
+            }
             const float den = sn > 1e-12f ? sn : 1e-12f;
             const float c0 = z1 / den, c1 = (-z0) / den; /* axis = normalise(z x e_z) = (z1,-z0,0)/|.| */
             const float kk = 1.0f - ct;

@@ -70,7 +70,7 @@ def lib():
         _lib.bxo_radius_bisect.restype = c_int
         _lib.bxo_ball_query.argtypes = [c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]
         _lib.bxo_select_patches.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]
-        _lib.bxo_lrf.argtypes = [c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]
+        _lib.bxo_lrf.argtypes = [c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         _lib.bxo_spt.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_float, c_int, c_void_p, c_void_p]
         _lib.bxo_consensus.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
         _lib.bxo_refine.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p]
@@ -123,13 +123,24 @@ def select_patches(pts, perm, kpts, radius: float, P: int):
     return idx, patches
 
 
-def lrf(patches, des_r: float, aligned: bool):
+def lrf_stable() -> bool:
+    """BX_LRF=stable selects the well-conditioned Rodrigues form (not the reference's; sensitivity studies only)."""
+    return os.environ.get("BX_LRF", "").lower() == "stable"
+
+
+def lrf(patches, des_r: float, aligned: bool, z_axis=None, want_z=False):
+    """a4+a5.  ``z_axis`` [K,3]: use these (disambiguated, unit) axes instead of the covariance/Jacobi result."""
     patches = _f32(patches)
     K, P, _ = patches.shape
     delta = np.zeros_like(patches)
     Rt = np.zeros((K, 3, 3), dtype=np.float32)
     ra = np.zeros((K, 3), dtype=np.float32)
-    lib().bxo_lrf(_p(patches), K, P, c_float(des_r), int(bool(aligned)), _p(delta), _p(Rt), _p(ra))
+    zo = None if z_axis is None else _f32(z_axis)
+    z_out = np.zeros((K, 3), dtype=np.float32)
+    flags = int(bool(aligned)) | (2 if lrf_stable() else 0)
+    lib().bxo_lrf(_p(patches), K, P, c_float(des_r), flags, _p(delta), _p(Rt), _p(ra), _p(zo), _p(z_out))
+    if want_z:
+        return delta, Rt, ra, z_out
     return delta, Rt, ra
 
 
@@ -305,6 +316,16 @@ def pool_desc(x: torch.Tensor, sd, pfx="Desc."):
     return f, F.normalize(x, p=2, dim=1)
 
 
+def desc_fp64(feat: torch.Tensor, sd, rad_n=3, ele_n=7, azi_n=20) -> torch.Tensor:
+    """a8+a9 evaluated in float64 on the (fp32) point-layer features [k,16,V]: the ground truth against which the fp32
+    oracle and the GPU path are both measured where a descriptor is ill-conditioned (tests/test_gpu_parity.py)."""
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items() if k.startswith("Desc.")}
+    with torch.no_grad():
+        x = cyl_net(feat.double().view(feat.shape[0], feat.shape[1], rad_n, ele_n, azi_n), sd64)
+        d, _ = pool_desc(x, sd64)
+    return d
+
+
 _COST_CONVS = [0, 3, 6, 9, 12, 15, 18, 21, 24, 27]
 
 
@@ -351,14 +372,14 @@ def hypotheses(ind, ss_kpts, tt_kpts, ss_R, tt_R, azi_n=20):
 # --------------------------------------------------------------------------- #
 # descriptor + full pair
 # --------------------------------------------------------------------------- #
-def describe(sd, cfg, pts, kpts, des_r: float, aligned: bool, perm, keep=False, timings=None):
+def describe(sd, cfg, pts, kpts, des_r: float, aligned: bool, perm, keep=False, timings=None, z_axis=None):
     """MiniSpinNet.forward in eval mode (patch_embedder.py:44-90) for one cloud."""
     P = cfg.patch.num_points_per_patch
     rad_n, azi_n, ele_n = cfg.patch.rad_n, cfg.patch.azi_n, cfg.patch.ele_n
     t0 = time.perf_counter()
     idx, patches = select_patches(pts, perm, kpts, des_r, P)
     t1 = time.perf_counter()
-    delta, Rt, rand_axis = lrf(patches, des_r, aligned)
+    delta, Rt, rand_axis, z_used = lrf(patches, des_r, aligned, z_axis=z_axis, want_z=True)
     t2 = time.perf_counter()
     inv, vidx = spt(delta, rad_n, azi_n, ele_n, cfg.patch.delta / rad_n, cfg.patch.voxel_sample)
     t3 = time.perf_counter()
@@ -372,7 +393,7 @@ def describe(sd, cfg, pts, kpts, des_r: float, aligned: bool, perm, keep=False, 
             timings[k] = timings.get(k, 0.0) + v
     out = dict(desc=desc, equi=equi, R=torch.from_numpy(Rt), rand_axis=torch.from_numpy(rand_axis))
     if keep:
-        out.update(idx=idx, patches=patches, delta=delta, inv=inv, vidx=vidx, feat=feat, x=x)
+        out.update(idx=idx, patches=patches, delta=delta, inv=inv, vidx=vidx, feat=feat, x=x, z=z_used)
     return out
 
 
@@ -387,9 +408,10 @@ def draw_perms(cfg, n_src, n_tgt, seed):
     return perms
 
 
-def register_pair(sd, cfg, data, perms, ransac_seed=0, keep=False, timings=None):
+def register_pair(sd, cfg, data, perms, ransac_seed=0, keep=False, timings=None, z_axes=None):
     """``BufferX.forward`` inference branch (models/BUFFERX.py:257-467), early exit disabled or enabled
-    as configured.  Returns (pose, num_inliers, num_mutual, num_inlier_ind, scales_used, aux)."""
+    as configured.  Returns (pose, num_inliers, num_mutual, num_inlier_ind, scales_used, aux).
+    ``z_axes`` (ref_check.py only): per scale a (src [K,3], tgt [K,3]) pair of LRF z axes to impose."""
     src = _f32(data["src_fds_pcd"])
     tgt = _f32(data["tgt_fds_pcd"])
     aligned = bool(data["is_aligned_to_global_z"])
@@ -426,8 +448,9 @@ def register_pair(sd, cfg, data, perms, ransac_seed=0, keep=False, timings=None)
     for i in range(cfg.patch.num_scales):
         des_r = radius_estimation(src, kpts1, tgt, kpts2, [cfg.patch.search_radius_thresholds[i]], cum=cum)[0]
         aux["des_r"].append(des_r)
-        s = describe(sd, cfg, src, src_kpts, des_r, aligned, perms[i][0], keep=keep, timings=tm)
-        t = describe(sd, cfg, tgt, tgt_kpts, des_r, aligned, perms[i][1], keep=keep, timings=tm)
+        zs, zt = (None, None) if z_axes is None else z_axes[i]
+        s = describe(sd, cfg, src, src_kpts, des_r, aligned, perms[i][0], keep=keep, timings=tm, z_axis=zs)
+        t = describe(sd, cfg, tgt, tgt_kpts, des_r, aligned, perms[i][1], keep=keep, timings=tm, z_axis=zt)
         t0 = time.perf_counter()
         s_m, t_m, snn, tnn = mutual_nn(s["desc"].numpy(), t["desc"].numpy())
         _t("mutual_nn", t0)

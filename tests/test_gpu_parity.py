@@ -307,6 +307,11 @@ def test_refine_close_to_oracle(dev, oracle):
 
 
 # ------------------------------------------------------------------------------------------- whole pair
+def _rel_rows(a, b):
+    den = np.abs(b).max(1)
+    return np.abs(a - b).max(1) / np.where(den > 0, den, 1)
+
+
 def _compare_pair(model, sd, cfg, data, perms, oracle, name):
     from bufferx_b200.se3 import compute_rre, compute_rte
     with torch.no_grad():
@@ -318,32 +323,50 @@ def _compare_pair(model, sd, cfg, data, perms, oracle, name):
     assert (dbg["fps_idx"][1].cpu().numpy()[:len(aux["t_fps"])] == aux["t_fps"]).all()
     assert np.allclose(dbg["des_r"].cpu().numpy(), np.array(aux["des_r"], dtype=np.float32), atol=0)
     rep = {}
+    worst = 0.0
     for i, (sc, osc) in enumerate(zip(dbg["scales"], aux["scales"])):
         for side, key in (("s", "src"), ("t", "tgt")):
             assert (sc[side]["idx"].cpu().numpy() == osc[key]["idx"]).all(), f"{name} scale {i} {key}: neighbour lists differ"
             assert (sc[side]["vidx"].cpu().numpy() == osc[key]["vidx"]).all(), f"{name} scale {i} {key}: voxel selections differ"
             assert (sc[side]["R"].cpu().numpy() == osc[key]["R"].numpy()).all()
             d, od = sc[side]["desc"].cpu().numpy(), osc[key]["desc"].numpy()
-            den = np.abs(od).max(1)
-            rel = np.abs(d - od).max(1) / np.where(den > 0, den, 1)
-            # 1e-4 relative (north_star).  A handful of descriptors are ill-conditioned (attention pooling with a
-            # near-zero pooled vector before the L2 normalisation): even the pure-fp32 CUDA-core kernel, i.e. the
-            # reference's arithmetic in another summation order, misses 1e-4 on them (tests/tools/desc_error.py on C3:
-            # fp32 FFMA max 1.42e-4, tensor-core path max 1.03e-4, both 99.99 % < 1e-4).  Hence: 99.9 % within
-            # 1e-4 and nothing beyond 5e-4.
+            rel = _rel_rows(d, od)
+            worst = max(worst, float(rel.max()))
+            # north_star: descriptors within 1e-4 relative.  The fp32 oracle is itself only an approximation of the
+            # network: a few descriptors are ill-conditioned (attention pooling with a near-zero pooled vector before the
+            # L2 normalisation).  So (1) 99.9 % within 1e-4 and nothing beyond 5e-4 against the oracle, and (2) against the
+            # float64 evaluation of the same network on the same inputs (oracle.desc_fp64) the GPU path is never further
+            # from the truth than 1.5x the fp32 oracle plus 3e-5 -- checked on the worst rows and on a strided sample.
             assert (rel < 1e-4).mean() >= 0.999 and rel.max() < 5e-4, \
                 f"{name} scale {i} {key}: descriptor rel err max {rel.max()}, within 1e-4: {(rel < 1e-4).mean()}"
+            sel = np.unique(np.concatenate([np.argsort(rel)[-8:], np.arange(0, len(rel), max(1, len(rel) // 24))]))
+            t64 = oracle.desc_fp64(osc[key]["feat"][torch.from_numpy(sel)], sd).numpy()
+            e_gpu, e_orc = _rel_rows(d[sel].astype(np.float64), t64), _rel_rows(od[sel].astype(np.float64), t64)
+            bad = e_gpu > 1.5 * e_orc + 3e-5
+            assert not bad.any(), f"{name} scale {i} {key}: GPU vs fp64 {e_gpu[bad]} against oracle vs fp64 {e_orc[bad]}"
+            assert np.median(e_gpu) < 2e-5
         M, oM = int(sc["dM"].item()), len(osc["s_mids"])
-        rep[f"M{i}"] = (M, oM)
-        # arg-min flips between near-tied descriptors are possible at 1e-7 differences; allow a handful
         gs = set(zip(sc["s_mids"][:M].cpu().numpy().tolist(), sc["t_mids"][:M].cpu().numpy().tolist()))
         es = set(zip(osc["s_mids"].tolist(), osc["t_mids"].tolist()))
+        rep[f"M{i}"] = (M, oM, len(gs ^ es))
+        # arg-min flips between near-tied descriptors are possible at 1e-7 differences; allow a handful
         assert len(gs ^ es) <= max(2, oM // 200), f"{name} scale {i}: match sets differ by {len(gs ^ es)}"
     assert su == o_su and abs(nmut - o_nmut) <= max(2, o_nmut // 200)
-    if rep and all(a == b for a, b in rep.values()):
-        # identical match lists -> identical consensus set and RANSAC outcome
+    rre, rte = compute_rre(pose, o_pose), compute_rte(pose, o_pose)
+    identical = all(a == b and x == 0 for a, b, x in rep.values())
+    if identical:
+        # identical match lists -> identical consensus set and RANSAC outcome, pose to rounding
         assert nind == o_nind and ninl == o_ninl
-        assert compute_rre(pose, o_pose) < 0.1 and compute_rte(pose, o_pose) < 0.005
+        assert rre < 0.1 and rte < 0.005, f"{name}: identical match lists but pose differs (RRE {rre}, RTE {rte})"
+    # north_star: final (R,t) within the reference's own RRE/RTE success threshold of the oracle's (test.py:168-172),
+    # whatever happened to individual arg-mins.  Only a pair without a consensus (both sides < 3 RANSAC correspondences or
+    # no inliers: identity / arbitrary pose by construction) is exempt.
+    if min(ninl, o_ninl) >= 3:
+        assert rre < cfg.test.rre_thresh and rte < cfg.test.rte_thresh, \
+            f"{name}: pose differs from the oracle's beyond the dataset thresholds (RRE {rre}, RTE {rte}; matches {rep})"
+    else:
+        assert max(ninl, o_ninl) < 3 or identical
+    print(f"[{name}] matches {rep} inliers {ninl}/{o_ninl} consensus {nind}/{o_nind} RRE {rre:.4f} RTE {rte:.5f} worst desc rel {worst:.2e}")
     return pose, o_pose, rep
 
 
@@ -421,6 +444,49 @@ def test_c2_pair_registers_with_fitted_costnet(dev):
     model.cpu()
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_c2_pairs_against_the_reference_forward(dev, oracle, seed):
+    """The CUDA path against what the REFERENCE's own ``BufferX.forward`` produced (tests/golden/c2_seed*_reference.npz,
+    written by oracle/ref_check.py in the build container: full C2 configuration, fitted CostNet, 21-52 RANSAC inliers,
+    non-identity refined pose) and against the committed oracle fixture: same consensus set, same counts, final (R,t)
+    within 0.1 deg / 5 mm of the reference's, >= 99.5 % of the reference's mutual matches."""
+    import bufferx_b200 as bx
+    from bufferx_b200.se3 import compute_rre, compute_rte
+    from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"c2_seed{seed}.npz"))
+    r = np.load(os.path.join(ROOT, "tests", "golden", f"c2_seed{seed}_reference.npz"))
+    cfg = workload_cfg("C2")
+    model = init_synthetic_weights(bx.BufferX(cfg), trained_pose=True).to(dev)
+    data = make_pair("C2", seed)
+    perms = oracle.draw_perms(cfg, 20000, 20000, seed)
+    with torch.no_grad():
+        pose, _, ninl, nmut, nind, su = model(data, perms=perms, ransac_seed=0, debug=True)
+    dbg = model.last_debug
+    assert (dbg["fps_idx"][0].cpu().numpy() == g["s_fps"]).all() and (dbg["fps_idx"][1].cpu().numpy() == g["t_fps"]).all()
+    assert np.allclose(dbg["des_r"].cpu().numpy().astype(np.float64), g["des_r"], atol=1e-6)
+    common = total = 0
+    stride = int(g["stride"])
+    for i, sc in enumerate(dbg["scales"]):
+        M = int(sc["dM"].item())
+        gs = set(zip(sc["s_mids"][:M].cpu().numpy().tolist(), sc["t_mids"][:M].cpu().numpy().tolist()))
+        rs = set(zip(r[f"s{i}_s_mids"].tolist(), r[f"s{i}_t_mids"].tolist()))
+        common += len(gs & rs)
+        total += len(rs)
+        for side, key in (("s", "src"), ("t", "tgt")):
+            rel = _rel_rows(sc[side]["desc"].cpu().numpy()[::stride], r[f"s{i}_{key}_desc"])
+            assert (rel < 1e-4).mean() >= 0.99 and np.median(rel) < 2e-5     # vs the reference run itself (LRF-ulp voxel flips < 1 %)
+    assert common >= 0.995 * total
+    last = dbg["scales"][-1]
+    inl = last["inlier_ind"][:int(last["dI"].item())].cpu().numpy()
+    assert (inl == r["inlier_ind"]).all(), "consensus set differs from the reference run's"
+    assert [ninl, nind, su] == [int(r["counts"][0]), int(r["counts"][2]), int(r["counts"][3])]
+    assert abs(nmut - int(r["counts"][1])) <= 2
+    assert np.abs(np.asarray(dbg["init_pose"]) - r["ransac_T"]).max() < 1e-6
+    assert compute_rre(pose, r["pose"]) < 0.1 and compute_rte(pose, r["pose"]) < 0.005
+    assert np.abs(r["pose"] - np.eye(4)).max() > 0.1 and ninl >= 20          # non-vacuous
+    model.cpu()
+
+
 def test_degenerate_pair_unrelated_clouds(dev, oracle):
     """Two unrelated clouds (a plane patch and a sphere shell, metres apart): a handful of mutual matches, a consensus
     set of at most one member, fewer than three RANSAC correspondences -> identity pose with 0 inliers, exactly like
@@ -491,7 +557,7 @@ def test_c2_full_size_pair(dev, oracle):
     import bufferx_b200 as bx
     from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
     cfg = workload_cfg("C2")
-    model = init_synthetic_weights(bx.BufferX(cfg))
+    model = init_synthetic_weights(bx.BufferX(cfg), trained_pose=True)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     data = make_pair("C2", 0)
     perms = oracle.draw_perms(cfg, 20000, 20000, 0)
@@ -731,7 +797,7 @@ def test_sphericity_based_voxel_analysis(dev, oracle, name, ns, nt):
     1e-8, identical (voxel_size, is_aligned_to_global_z), sphericity 1e-9."""
     from bufferx_b200 import ops
     from bufferx_b200.synth import make_pair
-    from bufferx_b200.utils.tools import sphericity_based_voxel_analysis
+    from bufferx_b200.bootstrap import sphericity_based_voxel_analysis
     data = make_pair(name, 2, n_src=ns, n_tgt=nt)
     src, tgt = data["src_fds_pcd"], data["tgt_fds_pcd"]
     st = np.random.RandomState(7)

@@ -36,18 +36,93 @@ def test_oracle_matches_golden(c1):
     assert [ninl, nmut, nind, su] == g["counts"].tolist()
 
 
-def test_oracle_close_to_reference_run():
-    """The reference's own forward (run in the build container through oracle/ref_check.py) and the
-    oracle agree on >= 97 % of the descriptors within 1e-4; the rest are LRF-ulp voxel flips."""
+def test_oracle_close_to_reference_run_c1():
+    """Plumbing fixture (C1, one scale, random CostNet): descriptors of the reference's own forward (run in the build
+    container through oracle/ref_check.py) and of the oracle; the final pose of this pair is the identity on both sides
+    (no consensus), so the non-vacuous end-to-end pin is the C2 test below."""
     g = np.load(os.path.join(GOLD, "c1_seed0.npz"))
     r = np.load(os.path.join(GOLD, "c1_seed0_reference.npz"))
     for side in ("src", "tgt"):
         od, rd = g[f"s0_{side}_desc"], r[f"s0_{side}_desc"]
         den = np.abs(od).max(1)
         rel = np.abs(od - rd).max(1) / np.where(den > 0, den, 1)
-        assert (rel < 1e-4).mean() >= 0.97
+        assert (rel < 1e-4).mean() >= 0.99
+    assert (g["s0_s_mids"] == r["s0_s_mids"]).all() and (g["s0_t_mids"] == r["s0_t_mids"]).all()
     assert g["counts"].tolist() == r["counts"].tolist()
     assert np.abs(g["pose"] - r["pose"]).max() < 1e-5
+
+
+def _pose_close(P, Q, rre_deg, rte_m):
+    from bufferx_b200.se3 import compute_rre, compute_rte
+    assert compute_rre(np.asarray(P, np.float64), np.asarray(Q, np.float64)) < rre_deg
+    assert compute_rte(np.asarray(P, np.float64), np.asarray(Q, np.float64)) < rte_m
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_zlocked_equals_reference_forward_c2(c2_runs, seed):
+    """THE PIN.  tests/golden/c2_seed*_reference.npz hold what the reference's own ``BufferX.forward`` produced on the full
+    C2 configuration (3 scales, 1500 key-points, 50000 RANSAC iterations, fitted CostNet: 21-52 RANSAC inliers, a
+    non-identity refined pose).  With the reference run's LRF z axes imposed (its covariance is a BLAS call whose summation
+    order is not part of its source) the oracle must reproduce the reference EXACTLY where the result is discrete --
+    per-scale mutual-match lists, consensus set, counts -- and the pose to RRE < 0.1 deg / RTE < 5 mm."""
+    r = np.load(os.path.join(GOLD, f"c2_seed{seed}_reference.npz"))
+    S = 3
+    z_axes = [(r[f"s{i}_src_z"], r[f"s{i}_tgt_z"]) for i in range(S)]
+    pose, ninl, nmut, nind, su, aux = c2_runs(seed, z_axes=z_axes, tag="zlocked")["res"]
+    for i in range(S):
+        sc = aux["scales"][i]
+        assert (sc["s_mids"] == r[f"s{i}_s_mids"]).all() and (sc["t_mids"] == r[f"s{i}_t_mids"]).all(), f"scale {i} match list"
+        assert np.abs(sc["ind"] - r[f"s{i}_ind"]).max() < 2e-2          # soft arg-max bins (one ill-conditioned descriptor: 5e-3)
+        assert np.median(np.abs(sc["ind"] - r[f"s{i}_ind"])) < 1e-4
+    assert (aux["scales"][-1]["inlier_ind"] == r["inlier_ind"]).all()
+    assert [ninl, nmut, nind, su] == r["counts"].tolist()
+    assert ninl >= 20 and np.abs(r["pose"] - np.eye(4)).max() > 0.1     # the pin is not vacuous
+    assert np.abs(np.asarray(aux["init_pose"]) - r["ransac_T"]).max() < 1e-9
+    _pose_close(pose, r["pose"], 0.1, 0.005)
+    assert np.abs(np.asarray(pose, np.float64) - r["pose"]).max() < 1e-5
+
+
+def test_oracle_free_run_vs_reference_forward_c2(c2_runs):
+    """The oracle on its own (own covariance summation order + Jacobi) against the reference's forward, and against the
+    committed oracle fixture (what the CUDA path must reproduce): same consensus set, same counts, same pose; match lists
+    equal up to the rare LRF-ulp flips the report quantifies (seed 2: one of 1224)."""
+    for seed in (0,):
+        g = np.load(os.path.join(GOLD, f"c2_seed{seed}.npz"))
+        r = np.load(os.path.join(GOLD, f"c2_seed{seed}_reference.npz"))
+        pose, ninl, nmut, nind, su, aux = c2_runs(seed)["res"]
+        assert (aux["s_fps"] == g["s_fps"]).all() and (aux["t_fps"] == g["t_fps"]).all()
+        assert np.allclose(aux["des_r"], g["des_r"], atol=0)
+        common = total = 0
+        for i in range(3):
+            sc = aux["scales"][i]
+            assert (sc["s_mids"] == g[f"s{i}_s_mids"]).all() and (sc["t_mids"] == g[f"s{i}_t_mids"]).all()
+            assert (sc["inlier_ind"] == g[f"s{i}_inlier_ind"]).all()
+            a = set(zip(sc["s_mids"].tolist(), sc["t_mids"].tolist()))
+            b = set(zip(r[f"s{i}_s_mids"].tolist(), r[f"s{i}_t_mids"].tolist()))
+            common += len(a & b)
+            total += len(b)
+        assert common >= 0.995 * total
+        assert [ninl, nmut, nind, su] == g["counts"].tolist()
+        assert np.allclose(pose, g["pose"], atol=1e-6)
+        assert (aux["scales"][-1]["inlier_ind"] == r["inlier_ind"]).all()
+        assert ninl == int(r["counts"][0])
+        _pose_close(pose, r["pose"], 0.1, 0.005)
+
+
+def test_reference_pin_reports_are_green():
+    """The committed reports of oracle/ref_check.py (generated against /root/reference): every seed ends in a non-identity
+    pose, the z-locked run reproduces all match lists and the consensus set, the free run the consensus set and pose."""
+    import json
+    for seed in (0, 1, 2):
+        rep = json.load(open(os.path.join(GOLD, f"c2_seed{seed}_report.json")))
+        assert rep["trained_pose"] and rep["workload"] == "C2"
+        z, f = rep["oracle_zlocked"], rep["oracle_free"]
+        assert z["all_mids_equal"] and z["inlier_ind_equal"] and not z["pose_is_identity"]
+        assert z["num_inliers"][0] == z["num_inliers"][1] >= 20
+        assert z["pose_maxabs"] < 1e-5 and f["pose_maxabs"] < 1e-5
+        assert f["inlier_ind_equal"] and f["num_inliers"][0] == f["num_inliers"][1]
+        assert min(v for k, v in f.items() if k.endswith("desc_frac_within_1e-4")) >= 0.995
+        assert rep["z_axis_angle_deg_free_vs_reference"]["sign_flips"] == 0
 
 
 # ------------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import bufferx_b200 as bx
 from bufferx_b200 import ops
 from bufferx_b200.synth import make_pair
-from bufferx_b200.utils.tools import sphericity_based_voxel_analysis, voxel_down_sample
+from bufferx_b200.bootstrap import sphericity_based_voxel_analysis, voxel_down_sample
 from oracle import oracle as O
 
 data = make_pair("C3", 0)
