@@ -22,7 +22,7 @@ OBJ = os.path.join(HERE, "_obj")
 
 EXACT = ["bx_api.cu", "bx_fps.cu", "bx_radius.cu", "bx_patches.cu", "bx_spt.cu", "bx_match.cu", "bx_ransac.cu", "bx_neighbors.cu",
          "bx_bootstrap.cu"]
-FAST = ["bx_conv.cu", "bx_conv_tc.cu"]
+FAST = ["bx_conv.cu", "bx_conv_tc.cu", "bx_conv_sd.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 if os.environ.get("BX_BUILD_TRACE"):      # debugging aid: clock64 stage timeline in the tensor-core convolution

@@ -1,0 +1,461 @@
+// bx_conv_sd.cu -- a8: the cylindrical descriptor convolutions as a SHIFTED-DESCRIPTOR implicit GEMM on tcgen05.
+//
+// Replaces, for the eight layers of Cylindrical_Net (/root/reference/models/patchnet.py:16-84 with the padding of
+// utils/common.py:265-310), the im2col-style loader of bx_conv_tc.cu: there every activation was delivered to the tensor
+// core NINE times (once per 3x3 tap, through registers and tensor memory) and the narrow layers were bound by that
+// delivery.  Here an activation is written to shared memory ONCE per tile and the nine taps are nine VIEWS of the same
+// bytes:
+//
+//   row space   every sample is a padded (8 x 22) raster: padded row y' = 0 is a zero row (elevation padding, shared with
+//               the previous sample's bottom), y' = 1..7 are the elevations; padded column x' = 0 / 21 are the circular
+//               copies of azimuth 19 / 0, x' = 1..20 the azimuths.  GEMM row R = 176 s + 22 y + x is output (s, y, x); the
+//               input it needs for tap (dy, dx) sits at padded row R + 22 dy + dx -- ONE constant shift per tap for all
+//               128 rows of a tile.  Rows with x >= 20 or y == 7 are computed and dropped (140 of 176 rows are real).
+//   A operand   a tile's 176 (= 128 + 48 halo) padded rows of one 16-channel chunk live in shared memory as the canonical
+//               K-major no-swizzle image [split(hi,lo)][kcore(2)][row][8 x fp16 = 16 B]: rows are linear with a 16-byte
+//               stride (SBO = 128 B), so the descriptor of tap (dy, dx) is the chunk's base descriptor with its start
+//               address advanced by (22 dy + dx) * 16 B.  The 3x3x3 first layer is the same thing with its three radial
+//               slices as three chunks of 16 channels.
+//   precision   fp32-grade results (descriptor parity 1e-4 rel) from fp16 tensor-core operands: x = hi + lo * 2^-11 with
+//               hi = fp16(x), lo = fp16((x - hi) * 2^11) (22 mantissa bits, the same as the 3xTF32 split, at twice the
+//               tensor rate and half the operand bytes):  a*b ~= ah*bh + (al*bh + ah*bl) * 2^-11.  The ah*bh products go to
+//               a ping-pong pair of TMEM accumulators cut after every 16-channel chunk (nine MMAs, K = 144) and are added with round-to-nearest into
+//               fp32 running sums in registers (the tensor core accumulates with truncation: bx_conv_tc.cu header); the
+//               cross terms keep one chain per tile in their own ping-pong accumulator and are scaled by 2^-11 at the end.
+//               |x| >= 65504 cannot be represented: the loader raises *flag and the host re-runs the layer on the TF32 kernel.
+//
+// Persistent warp-specialised CTA, one per SM:
+//   4 loader warps    fill the A ring (NA chunk slots): fp32 channel-blocked activations [n][C/4][pos][4] -> fp16 hi/lo,
+//                     padding rows / wrap columns materialised by index arithmetic; fence.proxy.async + mbarrier.
+//   1 weight warp     streams the host-arranged weight image [chunk][tap][split][kcore][n][8 x fp16] through the B ring with
+//                     cp.async.bulk + mbarrier transaction counts (SB stages per copy).
+//   1 MMA warp        per (chunk, tap): 3 x tcgen05.mma.kind::f16 (SS form, M = 128, N = NT, K = 16); tcgen05.commit to the
+//                     slot / segment / tile barriers.  No thread ever touches an activation between shared memory and the MMA.
+//   4*ECS epilogue warps   drain finished segments (tcgen05.ld) into running sums, then bias (+ReLU) and 16-byte
+//                     channel-blocked stores of the valid rows -- while the tensor core already works on the next tile.
+#include <cuda_fp16.h>
+
+#include "bx_common.cuh"
+#include "bx_tcgen05.cuh"
+
+namespace {
+
+constexpr int SD_BM = 128;                       // GEMM rows per tile
+constexpr int SD_AROWS = 176;                    // tile rows + halo (2*22 + 2 = 46 -> 48)
+constexpr int SD_SROWS = 176;                    // padded rows per sample (8 x 22)
+constexpr int SD_KCORE = SD_AROWS * 16;          // bytes of one (split, kcore) image of a chunk: [row][8 x fp16]
+constexpr int SD_CHUNK = 4 * SD_KCORE;           // [split(hi,lo)][kcore(2)]
+constexpr int SD_NL = 4;                         // loader warps
+
+struct ConvSdParams {
+    const float *in;
+    const __half *w;
+    const float *bias;
+    float *out;
+    int *flag;
+    int n, Cout, nchunks, is3d, S_in, G_in, relu, n_tiles, NA, dbg;
+    const __half *in_sd;       // IN_SD: presplit padded input  [nchunks][split,kcore (4)][rows_in][8 x fp16]
+    __half *out_sd;            // OUT_SD: presplit padded output [Cout/16][4][rows_out][8 x fp16] = the next layer's in_sd
+    long long rows_in, rows_out;
+};
+
+// B ring: one bulk copy / one mbarrier per SUPER-STAGE of three taps (the MMA warp's issue loop is the critical resource:
+// every barrier wait costs it ~90 cycles), NBS super-stages deep.
+template <int NT> struct SdRing { static constexpr int SB = 3, NBS = NT == 128 ? 3 : (NT == 64 ? 4 : 6); };
+
+__device__ __forceinline__ void mma_f16_ss(uint32_t leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "mov.b64 da, {%2, %4};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %5, p;\n\t"
+        "}\n" ::"r"(leader),
+        "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// IN_SD = 0: fp32 channel-blocked input converted by the loader warps; 1: presplit padded fp16 images fetched with bulk copies.
+// OUT_SD = 0: fp32 channel-blocked output; 1: presplit padded fp16 images (zero rows and wrap columns written here).
+template <int NT, int ECS, int IN_SD, int OUT_SD>
+__global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(const ConvSdParams p) {
+    constexpr int NE = 4 * ECS, MMA_WARP = NE + SD_NL, WGT_WARP = NE + SD_NL + 1;
+    constexpr int CW = NT / ECS;                  // accumulator columns of one epilogue warp
+    constexpr int SB = SdRing<NT>::SB, NBS = SdRing<NT>::NBS;
+    constexpr int B_STAGE = 64 * NT;              // [split][kcore][n][16 B]
+    constexpr int TMEM_COLS = 4 * NT;             // main[2], cross[2]
+    constexpr int MAXNA = 12;
+    // barriers
+    constexpr int BAR_AFULL = 0, BAR_AEMPTY = MAXNA, BAR_BFULL = 2 * MAXNA, BAR_BEMPTY = BAR_BFULL + NBS;
+    constexpr int BAR_SEGDONE = BAR_BEMPTY + NBS, BAR_ACCFREE = BAR_SEGDONE + 2, BAR_XDONE = BAR_ACCFREE + 2, BAR_XFREE = BAR_XDONE + 2;
+    constexpr int NBARS = BAR_XFREE + 2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bars[NBARS];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NA = p.NA, nchunks = p.nchunks;
+    const int n_stages = nchunks * 9;
+    const int nseg = nchunks;                    // one accumulator segment per 16-channel chunk (nine main MMAs, K = 144)
+
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < MAXNA; ++s) {
+            mbar_init(smem_u32(&bars[BAR_AFULL + s]), IN_SD ? 1 : SD_NL);
+            mbar_init(smem_u32(&bars[BAR_AEMPTY + s]), 1);
+        }
+        for (int s = 0; s < NBS; ++s) {
+            mbar_init(smem_u32(&bars[BAR_BFULL + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_BEMPTY + s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bars[BAR_SEGDONE + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_ACCFREE + s]), NE);
+            mbar_init(smem_u32(&bars[BAR_XDONE + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_XFREE + s]), NE);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base = tmem_base_s;
+    uint32_t a_base = smem_u32(smem);
+    uint32_t b_base = a_base + (uint32_t)NA * SD_CHUNK;
+    uint32_t bar_base = smem_u32(&bars[0]);
+    asm volatile("" : "+r"(tmem_base), "+r"(a_base), "+r"(b_base), "+r"(bar_base));
+
+    if (warp < NE) {
+        // =========================== epilogue: segment drains, bias, ReLU, stores ==========================
+        const int quarter = warp & 3, ecs = warp >> 2;
+        const uint32_t tm_lane = (uint32_t)(quarter * 32) << 16;
+        float run[CW];
+        int seg = 0, k = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++k) {
+#pragma unroll
+            for (int c = 0; c < CW; ++c) run[c] = 0.0f;
+            for (int jj = 0; jj < nseg; ++jj, ++seg) {
+                const int set = seg & 1;
+                mbar_wait(bar_base + 8u * (BAR_SEGDONE + set), (uint32_t)((seg >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c0 = 0; c0 < CW; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld<32>(tmem_base + tm_lane + (uint32_t)(set * NT + ecs * CW + c0), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) run[c0 + c] += __uint_as_float(v[c]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_ACCFREE + set));
+            }
+            const int xset = k & 1;
+            mbar_wait(bar_base + 8u * (BAR_XDONE + xset), (uint32_t)((k >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long R = (long long)t * SD_BM + quarter * 32 + lane;
+            const int s = (int)(R / SD_SROWS), q = (int)(R - (long long)s * SD_SROWS);
+            const int y = q / 22, x = q - y * 22;
+            const bool valid = s < p.n && y < 7 && x < 20;
+            float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)s * (p.Cout >> 2) + ((ecs * CW) >> 2)) * 140 + (y * 20 + x);
+            // OUT_SD: this row's value goes to padded row R + 23 (= (y + 1) * 22 + (x + 1)); azimuth 19 / 0 are duplicated into the
+            // wrap columns x' = 0 / 21; the rows that land on a zero row write zeros; everything else is dropped.
+            const bool live = s < p.n;
+            const bool wz = live && ((y == 7 && x <= 20) || (y == 6 && x == 21));       // zero row of sample s + 1
+            const long long pmain = R + 23, pdup = x == 19 ? R + 3 : (x == 0 ? R + 43 : -1);
+            float omax = 0.0f;
+#pragma unroll
+            for (int c0 = 0; c0 < CW; c0 += 32) {
+                uint32_t u[32];
+                tmem_ld<32>(tmem_base + tm_lane + (uint32_t)(2 * NT + xset * NT + ecs * CW + c0), u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 >= CW) {           // last piece read: the cross accumulator may be overwritten by tile k + 2
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_XFREE + xset));
+                }
+                if (OUT_SD ? live : valid) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8) {
+                        const int co = ecs * CW + c0 + c;
+                        if (co < p.Cout) {
+                            float r[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                r[e] = fmaf(__uint_as_float(u[c + e]), 0.00048828125f, run[c0 + c + e]) + __ldg(p.bias + co + e);
+                                if (p.relu) r[e] = fmaxf(r[e], 0.0f);
+                            }
+                            if (!OUT_SD) {
+                                eo[(size_t)((c0 + c) >> 2) * 140] = make_float4(r[0], r[1], r[2], r[3]);
+                                eo[(size_t)((c0 + c + 4) >> 2) * 140] = make_float4(r[4], r[5], r[6], r[7]);
+                            } else {
+                                uint32_t hi[4], lo[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float a = valid ? r[2 * e] : 0.0f, b = valid ? r[2 * e + 1] : 0.0f;
+                                    const __half2 hh = __floats2half2_rn(a, b);
+                                    const float2 hf = __half22float2(hh);
+                                    const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                                    hi[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                                    lo[e] = *reinterpret_cast<const uint32_t *>(&ll);
+                                    omax = fmaxf(omax, fmaxf(fabsf(a), fabsf(b)));
+                                }
+                                // image (chunk = co / 16, kcore = (co / 8) & 1): [chunk][split][kcore][row][8]
+                                uint4 *img = reinterpret_cast<uint4 *>(p.out_sd) + (size_t)((co >> 4) * 4 + ((co >> 3) & 1)) * p.rows_out;
+                                const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                if (valid || wz) { img[pmain] = vh; img[2 * p.rows_out + pmain] = vl; }
+                                if (valid && pdup >= 0) { img[pdup] = vh; img[2 * p.rows_out + pdup] = vl; }
+                                if (R < 22) { const uint4 z = make_uint4(0u, 0u, 0u, 0u); img[R] = z; img[2 * p.rows_out + R] = z; }   // zero row of sample 0
+                            }
+                        }
+                    }
+                }
+            }
+            if (OUT_SD && !(omax < 65000.0f) && p.flag) atomicOr(p.flag, 1);
+        }
+    } else if (warp < NE + SD_NL) {
+        if (IN_SD) {
+            // =========================== A producer: presplit images by bulk copy =================================
+            // A chunk's four (split, kcore) images are four contiguous 2816-byte runs of the previous layer's output: one
+            // thread keeps NA chunks in flight; no register staging, no conversion.
+            if (warp == NE && lane == 0) {
+                uint32_t slot = 0, par = 0, round = 0;
+                for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+                    for (int c = 0; c < nchunks; ++c) {
+                        if (round) mbar_wait(bar_base + 8u * (BAR_AEMPTY + slot), par ^ 1u);
+                        mbar_arrive_expect_tx(bar_base + 8u * (BAR_AFULL + slot), (uint32_t)SD_CHUNK);
+                        const unsigned char *src = reinterpret_cast<const unsigned char *>(p.in_sd) + ((size_t)(c * 4) * p.rows_in + (size_t)t * SD_BM) * 16;
+#pragma unroll
+                        for (int im = 0; im < 4; ++im)
+                            bulk_g2s(a_base + slot * (uint32_t)SD_CHUNK + (uint32_t)im * SD_KCORE, src + (size_t)im * p.rows_in * 16, (uint32_t)SD_KCORE,
+                                     bar_base + 8u * (BAR_AFULL + slot));
+                        if (++slot == (uint32_t)NA) { slot = 0; par ^= 1u; round = 1; }
+                    }
+            }
+            __syncwarp();
+        } else {
+        // =========================== loaders: fp32 activations -> fp16 hi/lo chunk images ====================
+            // A chunk image is 2 x 176 items of (row, 8 channels) = two 16-byte loads each; thread `ltid` owns the items ltid,
+            // ltid + 128, ltid + 256 of EVERY chunk.  The activations come from HBM (~1400 cycles): all six loads of a chunk are
+            // issued at once and the loads of chunk j + 1 are in flight while chunk j is converted -- a chunk per thread group
+            // with one exposed round trip each was 3.4x slower than the tensor core needs (measured).
+            constexpr int ITEMS = (2 * SD_AROWS + SD_NL * 32 - 1) / (SD_NL * 32);      // 3
+            const int ltid = tid - NE * 32;
+            const float4 *in4 = reinterpret_cast<const float4 *>(p.in);
+            float amax = 0.0f;
+            float4 cur[ITEMS][2], nxt[ITEMS][2];
+            auto issue = [&](int t, int c, float4 (&v)[ITEMS][2]) {
+                const long long p0 = (long long)t * SD_BM;
+#pragma unroll
+                for (int m = 0; m < ITEMS; ++m) {
+                    const int idx = ltid + m * SD_NL * 32;
+                    v[m][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[m][1] = v[m][0];
+                    if (idx < 2 * SD_AROWS) {
+                        const int h = idx >= SD_AROWS ? 1 : 0, r = idx - h * SD_AROWS;
+                        const long long pr = p0 + r;
+                        const int s = (int)(pr / SD_SROWS), q = (int)(pr - (long long)s * SD_SROWS);
+                        const int yp = q / 22, xp = q - yp * 22;
+                        if (s < p.n && yp != 0 && !p.dbg) {
+                            const int xx = xp == 0 ? 19 : (xp == 21 ? 0 : xp - 1);
+                            int pos = (yp - 1) * 20 + xx, g0;
+                            if (p.is3d) { pos += c * 140; g0 = h * 2; } else { g0 = c * 4 + h * 2; }
+                            const float4 *src = in4 + ((size_t)s * p.G_in + g0) * p.S_in + pos;
+                            v[m][0] = __ldg(src);
+                            v[m][1] = __ldg(src + p.S_in);
+                        }
+                    }
+                }
+            };
+            int j = 0;
+            int t = blockIdx.x, c = 0;
+            if (t < p.n_tiles) issue(t, 0, cur);
+            while (t < p.n_tiles) {
+                // position of the chunk after this one
+                int tn = t, cn = c + 1;
+                if (cn == nchunks) { cn = 0; tn = t + gridDim.x; }
+                if (tn < p.n_tiles) issue(tn, cn, nxt);
+                const int slot = j % NA;
+                if (j >= NA) mbar_wait(bar_base + 8u * (BAR_AEMPTY + slot), (uint32_t)(((j / NA) - 1) & 1));
+                unsigned char *dst = smem + (size_t)slot * SD_CHUNK;
+#pragma unroll
+                for (int m = 0; m < ITEMS; ++m) {
+                    const int idx = ltid + m * SD_NL * 32;
+                    if (idx < 2 * SD_AROWS) {
+                        const int h = idx >= SD_AROWS ? 1 : 0, r = idx - h * SD_AROWS;
+                        const float xs[8] = {cur[m][0].x, cur[m][0].y, cur[m][0].z, cur[m][0].w, cur[m][1].x, cur[m][1].y, cur[m][1].z, cur[m][1].w};
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __half2 hh = __floats2half2_rn(xs[2 * e], xs[2 * e + 1]);
+                            const float2 hf = __half22float2(hh);
+                            const __half2 ll = __floats2half2_rn((xs[2 * e] - hf.x) * 2048.0f, (xs[2 * e + 1] - hf.y) * 2048.0f);
+                            hi[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                            lo[e] = *reinterpret_cast<const uint32_t *>(&ll);
+                            amax = fmaxf(amax, fmaxf(fabsf(xs[2 * e]), fabsf(xs[2 * e + 1])));
+                        }
+                        *reinterpret_cast<uint4 *>(dst + (size_t)h * SD_KCORE + (size_t)r * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(dst + (size_t)(2 + h) * SD_KCORE + (size_t)r * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> tensor-core (async proxy) reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_AFULL + slot));
+#pragma unroll
+                for (int m = 0; m < ITEMS; ++m) { cur[m][0] = nxt[m][0]; cur[m][1] = nxt[m][1]; }
+                t = tn; c = cn; ++j;
+            }
+            if (!(amax < 65000.0f) && p.flag) atomicOr(p.flag, 1);   // also true for NaN
+        }
+    } else if (warp == WGT_WARP) {
+        // =========================== weight producer ========================================================
+        if (lane == 0) {
+            const int n_super = n_stages / SB;
+            int q = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+                for (int ss = 0; ss < n_super; ++ss, ++q) {
+                    const int sb = q % NBS;
+                    const uint32_t useb = (uint32_t)(q / NBS);
+                    if (useb > 0) mbar_wait(bar_base + 8u * (BAR_BEMPTY + sb), (useb - 1) & 1);
+                    constexpr uint32_t bytes = (uint32_t)SB * (uint32_t)B_STAGE;
+                    mbar_arrive_expect_tx(bar_base + 8u * (BAR_BFULL + sb), bytes);
+                    bulk_g2s(b_base + (uint32_t)sb * bytes, reinterpret_cast<const unsigned char *>(p.w) + (size_t)ss * bytes, bytes,
+                             bar_base + 8u * (BAR_BFULL + sb));
+                }
+        }
+        __syncwarp();
+    } else {
+        // =========================== MMA issuer =============================================================
+        // The issue loop is the critical resource of the kernel: everything is compile-time or a running counter (no
+        // divisions / modulo per stage -- a generic loop of ~100 uniform-datapath instructions per stage issued one stage per
+        // ~320 cycles, measured), the nine taps are unrolled with constant descriptor offsets, one weight barrier per
+        // three taps, one segment (= one 16-channel chunk, nine main MMAs) per accumulator set.
+        // instruction descriptor: D = F32, A = B = F16, both K-major, N = NT, M = 128
+        constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);            // SBO = 128 B (8 rows x 16 B), descriptor version 1
+        constexpr uint32_t A_LBO = ((uint32_t)SD_KCORE >> 4) << 16;       // K-adjacent core matrices: one kcore image apart
+        constexpr uint32_t B_LBO = ((uint32_t)(NT * 16) >> 4) << 16;
+        constexpr uint32_t A_SPLIT = (2u * SD_KCORE) >> 4, B_SPLIT = (2u * NT * 16) >> 4;   // hi -> lo image, 16-byte units
+        constexpr uint32_t B_STAGE16 = (uint32_t)B_STAGE >> 4, A_CHUNK16 = (uint32_t)SD_CHUNK >> 4;
+        const uint32_t leader = elect_leader();
+        const uint32_t a0 = (a_base >> 4) | A_LBO, b0 = (b_base >> 4) | B_LBO;
+        uint32_t slot = 0, a_par = 0, sbq = 0, b_par = 0, seg = 0, k = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++k) {
+            const uint32_t xset = k & 1;
+            if (k >= 2) {
+                mbar_wait(bar_base + 8u * (BAR_XFREE + xset), ((k >> 1) - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const uint32_t d_cross = tmem_base + (2u * NT + xset * NT);
+            for (int c = 0; c < nchunks; ++c) {
+                const uint32_t set = seg & 1;
+                mbar_wait(bar_base + 8u * (BAR_AFULL + slot), a_par);
+                if (seg >= 2) mbar_wait(bar_base + 8u * (BAR_ACCFREE + set), ((seg >> 1) - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ac = a0 + slot * A_CHUNK16;
+                const uint32_t d_main = tmem_base + set * NT;
+                const uint32_t first = c == 0 ? 0u : 1u;
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    mbar_wait(bar_base + 8u * (BAR_BFULL + sbq), b_par);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t bg = b0 + sbq * (3u * B_STAGE16);
+#pragma unroll
+                    for (int tt = 0; tt < 3; ++tt) {
+                        const uint32_t ah = ac + (uint32_t)(g * 22 + tt), al = ah + A_SPLIT;      // one row = 16 B = one address unit
+                        const uint32_t bh = bg + (uint32_t)tt * B_STAGE16, bl = bh + B_SPLIT;
+                        mma_f16_ss(leader, d_cross, al, bh, DESC_HI, IDESC, (g == 0 && tt == 0) ? first : 1u);
+                        mma_f16_ss(leader, d_cross, ah, bl, DESC_HI, IDESC, 1u);
+                        mma_f16_ss(leader, d_main, ah, bh, DESC_HI, IDESC, (g == 0 && tt == 0) ? 0u : 1u);
+                    }
+                    mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sbq));
+                    if (++sbq == NBS) { sbq = 0; b_par ^= 1u; }
+                }
+                mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + set));
+                mma_commit(leader, bar_base + 8u * (BAR_AEMPTY + slot));     // the chunk's MMAs have read the slot
+                ++seg;
+                if (++slot == (uint32_t)NA) { slot = 0; a_par ^= 1u; }
+            }
+            mma_commit(leader, bar_base + 8u * (BAR_XDONE + xset));
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int NT, int ECS, int IN_SD, int OUT_SD>
+int launch_sd(ConvSdParams p, cudaStream_t st) {
+    constexpr int B_RING = SdRing<NT>::SB * SdRing<NT>::NBS * 64 * NT;
+    int na = 2 * p.nchunks;
+    const int na_max = (227 * 1024 - 1024 - B_RING) / SD_CHUNK;
+    if (na > na_max) na = na_max;
+    if (na > 12) na = 12;
+    p.NA = na;
+    const int smem = na * SD_CHUNK + B_RING;
+    static BxPerDevice attr = {};
+    if (bx_needs_attr(attr, (size_t)smem))
+        BX_CUDA(cudaFuncSetAttribute(conv_sd_kernel<NT, ECS, IN_SD, OUT_SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int sms = bx_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    conv_sd_kernel<NT, ECS, IN_SD, OUT_SD><<<grid, (4 * ECS + SD_NL + 2) * 32, smem, st>>>(p);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
+template <int NT, int ECS>
+int dispatch_sd(const ConvSdParams &p, int in_sd, int out_sd, cudaStream_t st) {
+    if (in_sd) return out_sd ? launch_sd<NT, ECS, 1, 1>(p, st) : launch_sd<NT, ECS, 1, 0>(p, st);
+    return out_sd ? launch_sd<NT, ECS, 0, 1>(p, st) : launch_sd<NT, ECS, 0, 0>(p, st);
+}
+
+}  // namespace
+
+// rows of a presplit padded activation image for n samples: whole 128-row tiles of the 176-row-per-sample raster + halo
+BX_API long long bx_conv_sd_rows(int n) {
+    const long long rows = (long long)n * SD_SROWS;
+    return (rows + SD_BM - 1) / SD_BM * SD_BM + (SD_AROWS - SD_BM);
+}
+
+BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const void *w_sd, const float *bias, void *out, int out_presplit,
+                            int n, int Cin, int Cout, int relu, int32_t *d_flag, void *stream) {
+    BX_REQUIRE(in && w_sd && bias && out, "bx_conv_layer_sd: null pointer");
+    BX_REQUIRE(geom == BX_GEOM_CYL3D || geom == BX_GEOM_CYL2D, "bx_conv_layer_sd: only the cylindrical geometries (CYL3D / CYL2D)");
+    BX_REQUIRE(n >= 0 && Cin >= 16 && Cin % 16 == 0 && Cout >= 4 && Cout % 4 == 0 && Cout <= 128, "bx_conv_layer_sd: bad channels Cin=%d Cout=%d", Cin, Cout);
+    BX_REQUIRE(geom != BX_GEOM_CYL3D || (Cin == 16 && !in_presplit), "bx_conv_layer_sd: CYL3D expects 16 fp32 input channels x 3 radial slices");
+    BX_REQUIRE(!out_presplit || Cout % 16 == 0, "bx_conv_layer_sd: presplit output needs Cout %% 16 == 0");
+    BX_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(w_sd)) & 15) == 0,
+               "bx_conv_layer_sd: activations, weights and bias must be 16-byte aligned");
+    if (n == 0) return BX_OK;
+    ConvSdParams p = {};
+    p.w = reinterpret_cast<const __half *>(w_sd); p.bias = bias; p.flag = d_flag;
+    p.in = in_presplit ? nullptr : reinterpret_cast<const float *>(in);
+    p.in_sd = in_presplit ? reinterpret_cast<const __half *>(in) : nullptr;
+    p.out = out_presplit ? nullptr : reinterpret_cast<float *>(out);
+    p.out_sd = out_presplit ? reinterpret_cast<__half *>(out) : nullptr;
+    p.n = n; p.Cout = Cout; p.relu = relu;
+    p.is3d = geom == BX_GEOM_CYL3D;
+    p.nchunks = p.is3d ? 3 : Cin / 16;
+    p.S_in = p.is3d ? 420 : 140;
+    p.G_in = Cin / 4;
+    { static int dbg = -1; if (dbg < 0) { const char *e = getenv("BX_SD_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+    const long long rows = (long long)n * SD_SROWS;
+    BX_REQUIRE(rows / SD_BM < 0x7fffffffLL, "bx_conv_layer_sd: too many samples");
+    p.n_tiles = (int)((rows + SD_BM - 1) / SD_BM);
+    p.rows_in = p.rows_out = bx_conv_sd_rows(n);
+    cudaStream_t st = bx_stream(stream);
+    if (Cout > 64) return dispatch_sd<128, 2>(p, in_presplit, out_presplit, st);
+    if (Cout > 32) return dispatch_sd<64, 2>(p, in_presplit, out_presplit, st);
+    return dispatch_sd<32, 1>(p, in_presplit, out_presplit, st);
+}

@@ -115,7 +115,7 @@ class _PairSlot:
             with torch.cuda.device(dev), torch.cuda.graph(self.graph, stream=self.stream):
                 self.tail = self._enqueue()
         # pinned landing buffer for the result block
-        n_tail = 18 + (S + 1) + 1 + 1 + 16   # RANSAC block, scale offsets, consensus count, scales used, refined pose
+        n_tail = 18 + (S + 1) + 1 + 1 + 16 + 1   # RANSAC block, scale offsets, consensus count, scales used, refined pose, fp16-range flag
         self.h_tail = torch.empty(n_tail, dtype=torch.float64).pin_memory()
 
     def _enqueue(self):
@@ -168,7 +168,11 @@ class _PairSlot:
     def result(self):
         self.done.synchronize()
         self.busy = False
-        return self.model._decode(self.h_tail.clone(), [0.0, 0.0, 0.0])
+        out = self.model._decode(self.h_tail.clone(), [0.0, 0.0, 0.0])
+        if self.model._overflow:            # an activation left fp16 range: this pair is recomputed on the TF32 kernel
+            return self.model._rerun_tf32(dict(src_fds_pcd=self.src.clone(), tgt_fds_pcd=self.tgt.clone(), is_aligned_to_global_z=self.aligned),
+                                          [(self.perm_s[i].clone(), self.perm_t[i].clone()) for i in range(self.perm_s.shape[0])], None)
+        return out
 
 
 class BufferX(nn.Module):
@@ -416,7 +420,8 @@ class BufferX(nn.Module):
             refined = torch.zeros(16, dtype=torch.float64, device=dev)
         # ---- one small block holds everything the caller needs ---------------------------------------
         su = torch.full((1,), float(scales_used), dtype=torch.float64, device=dev)
-        tail = torch.cat([res_block, offs.double(), dI.double(), su, refined])
+        # last element: the sticky fp16-range flag of the shifted-descriptor conv kernel (0 unless an activation overflowed)
+        tail = torch.cat([res_block, offs.double(), dI.double(), su, refined, self.Desc.conv_net.overflow_flag(dev).double()])
         if debug:
             dbg.update(fps_idx=fidx, kpts=fk, des_r=r_dev, des_m=m_dev, ss=ss_acc, tt=tt_acc, R=R_acc, t=t_acc)
         return tail, dbg
@@ -429,12 +434,25 @@ class BufferX(nn.Module):
         num_inlier_ind = int(tail[18 + S + 1].item())
         scales_used = int(tail[18 + S + 2].item())
         num_mutual_inliers = int(offs_h[scales_used])
+        self._overflow = bool(tail[-1].item() != 0)
         if cfg.test.pose_refine is True:
-            pose = tail[18 + S + 3:].numpy().astype(np.float32).reshape(4, 4)
+            pose = tail[18 + S + 3:18 + S + 3 + 16].numpy().astype(np.float32).reshape(4, 4)
         else:
             pose = init_pose
         self._last_ransac = dict(init_pose=init_pose, best_itr=best_itr, iters=iters, offs=offs_h)
         return pose, times, num_inliers, num_mutual_inliers, num_inlier_ind, scales_used
+
+    def _rerun_tf32(self, data_source, perms, ransac_seed, debug=False):
+        """The shifted-descriptor kernel splits values into two fp16 operands; an activation >= 65000 (never seen with
+        BatchNorm-ed stacks, but possible in principle) raises its sticky flag.  From then on the descriptor stack of this
+        model runs on the TF32 kernel (bx_conv_tc.cu): drop the captured graphs, clear the flag, recompute this pair."""
+        net = self.Desc.conv_net
+        if not net.force_tf32:
+            print("bufferx_b200: activation outside fp16 range -- descriptor stack switched to the TF32 tensor-core kernel")
+        net.force_tf32 = True
+        self._drop_captured_state()
+        net.overflow_flag(next(self.parameters()).device).zero_()
+        return self.forward(data_source, perms=perms, ransac_seed=ransac_seed, debug=debug)
 
     def forward(self, data_source, perms=None, ransac_seed=None, debug=False):
         cfg = self.config
@@ -452,6 +470,7 @@ class BufferX(nn.Module):
 
         aligned = bool(data_source["is_aligned_to_global_z"])
         enable_timing = cfg.test.get("enable_timing", False)
+        rng_state = np.random.get_state() if perms is None else None     # replayed if the pair has to be recomputed
         with torch.cuda.device(dev):        # kernels launch on the model's device, whatever the caller's current device
             src, tgt = _cloud(data_source["src_fds_pcd"]), _cloud(data_source["tgt_fds_pcd"])
             timers = (_Timer(enable_timing), _Timer(enable_timing), _Timer(enable_timing))
@@ -459,6 +478,10 @@ class BufferX(nn.Module):
         tail_h = tail.cpu()                 # the one device->host read of the pair
         timers[2].toc()                     # pairs with the tic before RANSAC / refinement in _enqueue (pose_optim time)
         out = self._decode(tail_h, [timers[0].total, timers[1].total, timers[2].total])
+        if self._overflow:
+            if rng_state is not None:
+                np.random.set_state(rng_state)
+            return self._rerun_tf32(data_source, perms, ransac_seed, debug)
         if debug:
             dbg.update(self._last_ransac)
             self.last_debug = dbg

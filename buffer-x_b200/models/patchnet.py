@@ -15,7 +15,10 @@ from bufferx_b200 import ops
 
 # Debug switch only: BX_CONV=ffma routes the conv stacks through the fp32 CUDA-core kernel (bx_conv.cu)
 # instead of the tcgen05 kernel (bx_conv_tc.cu).  Both are sm_100a kernels of this library.
-USE_FFMA = os.environ.get("BX_CONV", "tc").lower() == "ffma"
+USE_FFMA = os.environ.get("BX_CONV", "sd").lower() == "ffma"
+# BX_CONV=tc: the descriptor stack on the round-1 TF32 kernel (bx_conv_tc.cu) instead of the shifted-descriptor fp16-split
+# kernel (bx_conv_sd.cu, the default).  The TF32 kernel is also the automatic fall-back when an activation leaves fp16 range.
+USE_TF32_DESC = os.environ.get("BX_CONV", "sd").lower() == "tc"
 # Debug switch only: BX_COSTVOL=direct runs the first CostNet layer as a convolution over the on-the-fly cost volume
 # (GEOM_COSTVOL) instead of its factorised form (bx_costvol_ab + GEOM_COSTAB).
 DIRECT_COSTVOL = os.environ.get("BX_COSTVOL", "factored").lower() == "direct"
@@ -60,6 +63,7 @@ class _ConvStack(nn.Module):
                 self.ops.append(nn.ReLU(inplace=True))
             self.layers.append((ci, bi, relu))
         self._folded = None
+        self.use_sd = False          # Cylindrical_Net: also build the fp16-split images of bx_conv_layer_sd
 
     def invalidate(self):
         self._folded = None
@@ -84,8 +88,10 @@ class _ConvStack(nn.Module):
                                      None if bn is None or not bn.affine else bn.bias,
                                      eps=1e-5 if bn is None else bn.eps)
                 ks = tuple(conv.kernel_size)
-                out.append(dict(w=Wt, w_tc=ops.conv_tc_weights(Wt) if Wt.is_cuda else None, b=b, cin=conv.in_channels,
-                                cout=conv.out_channels, k=ks if len(ks) == 3 else (1,) + ks, relu=relu))
+                kk = ks if len(ks) == 3 else (1,) + ks
+                sd_ok = Wt.is_cuda and self.use_sd and kk in ((1, 3, 3), (3, 3, 3)) and conv.in_channels % 16 == 0
+                out.append(dict(w=Wt, w_tc=ops.conv_tc_weights(Wt) if Wt.is_cuda else None, w_sd=ops.conv_sd_weights(Wt) if sd_ok else None,
+                                b=b, cin=conv.in_channels, cout=conv.out_channels, k=kk, relu=relu))
             self._folded = out
         return self._folded
 
@@ -99,6 +105,15 @@ class Cylindrical_Net(_ConvStack):
                 (64, 32, (3, 3), True, True), (32, dim, (3, 3), False, False)]
         super().__init__(spec)
         self.out_dim = dim
+        self.use_sd = True
+        self.force_tf32 = USE_TF32_DESC      # set (sticky) by BufferX when the fp16-range flag fired once
+        self._flag = None
+
+    def overflow_flag(self, dev):
+        """int32[1] on `dev`, OR-ed by bx_conv_layer_sd when an activation is outside fp16 range (sticky until cleared)."""
+        if self._flag is None or self._flag.device != dev:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self._flag
 
     def forward(self, x):
         """Tensor-core path (default): x [K,4,420,4] channel-blocked -> x_out [K,8,140,4] channel-blocked.
@@ -107,8 +122,15 @@ class Cylindrical_Net(_ConvStack):
         dev = x.device
         L = self.folded()
         cur = x.contiguous()
+        use_sd = not USE_FFMA and not self.force_tf32
+        flag = self.overflow_flag(dev) if use_sd else None
         for i, l in enumerate(L):
             out = torch.empty((K, l["cout"], 140) if USE_FFMA else (K, l["cout"] // 4, 140, 4), dtype=torch.float32, device=dev)
+            if use_sd:       # layer-to-layer activations in the presplit padded fp16 format; fp32 in at the first, fp32 out at the last layer
+                out = out if i == len(L) - 1 else ops.conv_sd_buffer(K, l["cout"], dev)
+                ops.conv_layer_sd(ops.GEOM_CYL3D if i == 0 else ops.GEOM_CYL2D, cur, l["w_sd"], l["b"], out, K, l["cin"], l["cout"], l["relu"], flag)
+                cur = out
+                continue
             conv, w = (ops.conv_layer, l["w"]) if USE_FFMA else (ops.conv_layer_tc, l["w_tc"])
             if i == 0:
                 conv(ops.GEOM_CYL3D, cur, w, l["b"], out, K, l["cin"], l["cout"], 3, 7, 20, 3, 3, 3, l["relu"])

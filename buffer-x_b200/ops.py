@@ -23,7 +23,7 @@ SYMBOLS = [
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
     "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab", "bx_concat_matches",
-    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample",
+    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
@@ -64,6 +64,9 @@ def load_library():
     lib.bx_conv_layer.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_layer_tc.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_tc_ntile.argtypes = [c_int]
+    lib.bx_conv_layer_sd.argtypes = [c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]
+    lib.bx_conv_sd_rows.argtypes = [c_int]
+    lib.bx_conv_sd_rows.restype = c_int64
     lib.bx_costvol_ab.argtypes = [P, P, P, P, P, c_int, P, P, P, P, P, P]
     lib.bx_concat_matches.argtypes = [P, P, P, c_int, c_int, P, P, P, P, P, P]
     lib.bx_pca_analysis.argtypes = [P, c_int, P, c_int, P, P, P]
@@ -333,6 +336,81 @@ def conv_layer_tc(geom, x, w_tc, bias, out, n, Cin, Cout, D, H, W, kd, kh, kw, r
     if ev:
         ev[1].record()
     return out
+
+
+def conv_sd_weights(Wt: torch.Tensor) -> torch.Tensor:
+    """[T, Cin, Cout] folded fp32 weights (T = 9: 3x3, or 27: 3x3x3 with Cin = 16) -> the fp16 operand image of
+    ``bx_conv_layer_sd``: [chunk][tap(9)][split(hi,lo)][kcore(2)][n(NT)][8], w = hi + lo * 2^-11."""
+    T, Cin, Cout = Wt.shape
+    assert T in (9, 27) and Cin % 16 == 0 and Cout <= 128 and (T == 9 or Cin == 16)
+    NT = 128 if Cout > 64 else (64 if Cout > 32 else 32)
+    W = torch.zeros((T, Cin, NT), dtype=torch.float32, device=Wt.device)
+    W[:, :, :Cout] = Wt
+    if T == 27:
+        W = W.view(3, 9, 16, NT)                                   # chunk = radial slice dz
+    else:
+        W = W.view(9, Cin // 16, 16, NT).permute(1, 0, 2, 3)          # [chunk, tap, 16, NT]
+    hi = W.half()
+    lo = ((W - hi.float()) * 2048.0).half()
+    both = torch.stack([hi, lo], dim=2)                               # [chunk, tap, split, 16, NT]
+    nch = both.shape[0]
+    both = both.reshape(nch, 9, 2, 2, 8, NT).permute(0, 1, 2, 3, 5, 4).contiguous()   # [chunk, tap, split, kcore, NT, 8]
+    return both.view(-1)
+
+
+def conv_sd_rows(n: int) -> int:
+    """Rows of a presplit padded activation image for n samples (176 per sample, whole 128-row tiles + 48 halo rows)."""
+    return int(load_library().bx_conv_sd_rows(int(n)))
+
+
+def conv_sd_buffer(n: int, C: int, device):
+    """Uninitialised presplit activation image [C/16, 4, rows, 8] fp16 (the producing kernel writes every row that is read
+    into a kept result)."""
+    return torch.empty((C // 16, 4, conv_sd_rows(n), 8), dtype=torch.float16, device=device)
+
+
+def conv_layer_sd(geom, x, w_sd, bias, out, n, Cin, Cout, relu, flag=None):
+    """x: fp32 channel-blocked [n, Cin/4, S_in, 4] or presplit fp16 [Cin/16, 4, rows, 8]; out likewise (dtype decides);
+    ``flag``: int32[1] fp16-range flag (sticky)."""
+    ev = None
+    if profiler is not None:
+        taps = 27 if geom == GEOM_CYL3D else 9
+        ev = profiler.span("conv_desc", 2.0 * n * 140 * Cout * Cin * taps)
+        ev[0].record()
+    in_sd, out_sd = x.dtype == torch.float16, out.dtype == torch.float16
+    _check(load_library().bx_conv_layer_sd(geom, _dp(x, None, "x"), int(in_sd), _dp(w_sd, torch.float16, "w_sd"), _dp(bias, F32, "bias"),
+                                           _dp(out, None, "out"), int(out_sd), int(n), Cin, Cout, int(bool(relu)), _dp(flag, I32, "flag"), _stream()),
+           "bx_conv_layer_sd")
+    if ev:
+        ev[1].record()
+    return out
+
+
+def sd_pack(x: torch.Tensor) -> torch.Tensor:
+    """Test helper (torch ops): channel-first [n, C, 7, 20] fp32 -> the presplit padded image [C/16, 4, rows, 8] fp16."""
+    n, C = x.shape[0], x.shape[1]
+    rows = conv_sd_rows(n)
+    xp = torch.zeros((n, C, 8, 22), dtype=torch.float32, device=x.device)
+    xp[:, :, 1:, 1:21] = x
+    xp[:, :, 1:, 0] = x[:, :, :, 19]
+    xp[:, :, 1:, 21] = x[:, :, :, 0]
+    flat = torch.zeros((rows, C), dtype=torch.float32, device=x.device)
+    flat[: n * 176] = xp.permute(0, 2, 3, 1).reshape(n * 176, C)
+    hi = flat.half()
+    lo = ((flat - hi.float()) * 2048.0).half()
+    img = torch.stack([hi, lo], dim=0).view(2, rows, C // 16, 2, 8).permute(2, 0, 3, 1, 4).contiguous()   # [chunk, split, kcore, rows, 8]
+    return img.view(C // 16, 4, rows, 8)
+
+
+def sd_unpack(img: torch.Tensor, n: int) -> torch.Tensor:
+    """Test helper: presplit padded image -> channel-first [n, C, 7, 20] fp32 (hi + lo * 2^-11), plus the padded raster
+    [n, C, 8, 22] for checking the zero rows / wrap columns."""
+    nch, _, rows, _ = img.shape
+    v = img.view(nch, 2, 2, rows, 8).float()
+    val = v[:, 0] + v[:, 1] / 2048.0                                  # [chunk, kcore, rows, 8]
+    flat = val.permute(2, 0, 1, 3).reshape(rows, nch * 16)
+    xp = flat[: n * 176].view(n, 8, 22, nch * 16).permute(0, 3, 1, 2)
+    return xp[:, :, 1:, 1:21].contiguous(), xp
 
 
 def costvol_factor_weights(Wt: torch.Tensor):

@@ -335,16 +335,19 @@ def _compare_pair(model, sd, cfg, data, perms, oracle, name):
             # north_star: descriptors within 1e-4 relative.  The fp32 oracle is itself only an approximation of the
             # network: a few descriptors are ill-conditioned (attention pooling with a near-zero pooled vector before the
             # L2 normalisation).  So (1) 99.9 % within 1e-4 and nothing beyond 5e-4 against the oracle, and (2) against the
-            # float64 evaluation of the same network on the same inputs (oracle.desc_fp64) the GPU path is never further
-            # from the truth than 1.5x the fp32 oracle plus 3e-5 -- checked on the worst rows and on a strided sample.
+            # float64 evaluation of the same network on the same inputs (oracle.desc_fp64), on the worst rows and a strided
+            # sample: every offender is a descriptor where the fp32 ORACLE is as far from the truth as the GPU path (GPU error
+            # <= 1.5x oracle error + 2e-5), and every other row is within 1e-4 of the fp64 descriptor.
             assert (rel < 1e-4).mean() >= 0.999 and rel.max() < 5e-4, \
                 f"{name} scale {i} {key}: descriptor rel err max {rel.max()}, within 1e-4: {(rel < 1e-4).mean()}"
             sel = np.unique(np.concatenate([np.argsort(rel)[-8:], np.arange(0, len(rel), max(1, len(rel) // 24))]))
             t64 = oracle.desc_fp64(osc[key]["feat"][torch.from_numpy(sel)], sd).numpy()
             e_gpu, e_orc = _rel_rows(d[sel].astype(np.float64), t64), _rel_rows(od[sel].astype(np.float64), t64)
-            bad = e_gpu > 1.5 * e_orc + 3e-5
+            off = rel[sel] >= 1e-4                       # the offenders: wherever GPU and oracle disagree beyond 1e-4 ...
+            bad = off & (e_gpu > 1.5 * e_orc + 2e-5)     # ... the fp32 oracle itself is that far from the truth
             assert not bad.any(), f"{name} scale {i} {key}: GPU vs fp64 {e_gpu[bad]} against oracle vs fp64 {e_orc[bad]}"
-            assert np.median(e_gpu) < 2e-5
+            # and everywhere else the GPU is within north_star's 1e-4 of the TRUE (fp64) descriptor, typically 100x closer
+            assert (e_gpu[~off] < 1e-4).all() and np.median(e_gpu) < 2e-5, f"{name} scale {i} {key}: GPU vs fp64 max {e_gpu[~off].max()}"
         M, oM = int(sc["dM"].item()), len(osc["s_mids"])
         gs = set(zip(sc["s_mids"][:M].cpu().numpy().tolist(), sc["t_mids"][:M].cpu().numpy().tolist()))
         es = set(zip(osc["s_mids"].tolist(), osc["t_mids"].tolist()))
@@ -614,7 +617,7 @@ def _torch_layer(geom, x, W, b, relu, kd, kh, kw):
     return F.relu(y) if relu else y
 
 
-@pytest.mark.parametrize("impl", ["tc", "ffma"])
+@pytest.mark.parametrize("impl", ["sd", "tc", "ffma"])
 @pytest.mark.parametrize("geom,Cin,Cout,dims,k,n", [
     ("cyl3d", 16, 64, (3, 7, 20), (3, 3, 3), 37), ("cyl2d", 64, 128, (1, 7, 20), (1, 3, 3), 41),
     ("cyl2d", 128, 128, (1, 7, 20), (1, 3, 3), 19), ("cyl2d", 64, 32, (1, 7, 20), (1, 3, 3), 300),
@@ -623,6 +626,8 @@ def _torch_layer(geom, x, W, b, relu, kd, kh, kw):
 def test_conv_layer_kernels(dev, geom, Cin, Cout, dims, k, n, impl):
     from bufferx_b200 import ops
     from bufferx_b200.models.patchnet import fold_conv_bn
+    if impl == "sd" and geom == "valid3d":
+        pytest.skip("the shifted-descriptor kernel serves the cylindrical (descriptor) layers only")
     g = torch.Generator().manual_seed(Cin * 1000 + Cout + n)
     D, H, W_ = dims
     kd, kh, kw = k
@@ -641,7 +646,13 @@ def test_conv_layer_kernels(dev, geom, Cin, Cout, dims, k, n, impl):
     OD, OH, OW = (1, 7, 20) if geom != "valid3d" else (D - kd + 1, H - kh + 1, W_ - kw + 1)
     out = torch.full((n, Cout, OD * OH * OW), float("nan"), device=dev)
     xin = x.to(dev).reshape(n, Cin, -1).contiguous()
-    if impl == "tc":                                                  # tensor-core kernel: channel-blocked activations
+    if impl == "sd":                                                  # shifted-descriptor fp16-split kernel (production)
+        out_cb = torch.full((n, Cout // 4, OD * OH * OW, 4), float("nan"), device=dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        ops.conv_layer_sd(G, ops.to_blocked(xin), ops.conv_sd_weights(Wt.to(dev)), bf.to(dev), out_cb, n, Cin, Cout, relu, flag)
+        out = ops.from_blocked(out_cb)
+        assert int(flag.item()) == 0
+    elif impl == "tc":                                                # tensor-core kernel: channel-blocked activations
         out_cb = torch.full((n, Cout // 4, OD * OH * OW, 4), float("nan"), device=dev)
         ops.conv_layer_tc(G, ops.to_blocked(xin), ops.conv_tc_weights(Wt.to(dev)), bf.to(dev), out_cb, n, Cin, Cout, D, H, W_,
                           kd, kh, kw, relu)
@@ -651,6 +662,90 @@ def test_conv_layer_kernels(dev, geom, Cin, Cout, dims, k, n, impl):
     got = out.cpu().numpy().reshape(ref.shape)
     err = np.abs(got - ref.numpy()).max() / np.abs(ref.numpy()).max()
     assert err < 2e-5, f"{impl} {geom} Cin={Cin} Cout={Cout}: rel err {err}"     # fp32-grade (3xTF32 / FFMA) vs torch fp32
+
+
+@pytest.mark.parametrize("tap", list(range(9)))
+def test_conv_sd_single_tap_shifts(dev, tap):
+    """One non-zero 3x3 tap at a time: every tap is a shifted VIEW (descriptor start address + (22 dy + dx) * 16 B) of the same
+    shared-memory image, including the wrap columns and the zero rows -- the output must be the input moved by that tap."""
+    from bufferx_b200 import ops
+    import torch.nn.functional as F
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(tap)
+    n, Cin, Cout = 11, 32, 32
+    x = torch.randn((n, Cin, 7, 20), generator=g)
+    Wc = torch.zeros((Cout, Cin, 3, 3))
+    Wc[:, :, tap // 3, tap % 3] = torch.randn((Cout, Cin), generator=g) / Cin ** 0.5
+    b = torch.zeros(Cout)
+    ref = F.conv2d(O._pad_cyl(x), Wc, b)
+    Wt = Wc.reshape(Cout, Cin, 9).permute(2, 1, 0).contiguous()
+    out_cb = torch.full((n, Cout // 4, 140, 4), float("nan"), device=dev)
+    ops.conv_layer_sd(ops.GEOM_CYL2D, ops.to_blocked(x.to(dev).reshape(n, Cin, -1).contiguous()), ops.conv_sd_weights(Wt.to(dev)), b.to(dev),
+                      out_cb, n, Cin, Cout, False, None)
+    got = ops.from_blocked(out_cb).cpu().numpy().reshape(ref.shape)
+    err = np.abs(got - ref.numpy()).max() / np.abs(ref.numpy()).max()
+    assert err < 2e-5, f"tap {tap} (dy {tap // 3}, dx {tap % 3}): rel err {err}"
+
+
+@pytest.mark.parametrize("Cin,Cout,n", [(64, 128, 23), (128, 64, 9), (32, 32, 301), (64, 64, 1)])
+def test_conv_sd_presplit_formats(dev, Cin, Cout, n):
+    """The layer-to-layer format (fp16 hi/lo images over the padded 8 x 22 raster, written by the producing layer's epilogue
+    and read back with bulk copies): presplit-in -> fp32-out, fp32-in -> presplit-out (values, zero rows, wrap columns) and a
+    presplit -> presplit -> fp32 chain against torch fp32."""
+    from bufferx_b200 import ops
+    import torch.nn.functional as F
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(Cin + Cout + n)
+    x = torch.randn((n, Cin, 7, 20), generator=g)
+    W1 = torch.randn((Cout, Cin, 3, 3), generator=g) / (Cin * 9) ** 0.5
+    b1 = torch.randn(Cout, generator=g) * 0.1
+    W2 = torch.randn((Cin, Cout, 3, 3), generator=g) / (Cout * 9) ** 0.5
+    b2 = torch.randn(Cin, generator=g) * 0.1
+    y1 = F.relu(F.conv2d(O._pad_cyl(x), W1, b1))
+    y2 = F.conv2d(O._pad_cyl(y1), W2, b2)
+    wt = lambda W: ops.conv_sd_weights(W.reshape(W.shape[0], W.shape[1], 9).permute(2, 1, 0).contiguous().to(dev))
+    xd = x.to(dev)
+    rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max())
+    # (a) presplit in -> fp32 out
+    o = torch.full((n, Cout // 4, 140, 4), float("nan"), device=dev)
+    ops.conv_layer_sd(ops.GEOM_CYL2D, ops.sd_pack(xd), wt(W1), b1.to(dev), o, n, Cin, Cout, True)
+    assert rel(ops.from_blocked(o).view(n, Cout, 7, 20), y1) < 2e-5
+    # (b) fp32 in -> presplit out: values + padding structure
+    img = ops.conv_sd_buffer(n, Cout, dev)
+    img.fill_(float("nan"))
+    ops.conv_layer_sd(ops.GEOM_CYL2D, ops.to_blocked(xd.reshape(n, Cin, 140)), wt(W1), b1.to(dev), img, n, Cin, Cout, True)
+    val, xp = ops.sd_unpack(img, n)
+    assert rel(val, y1) < 2e-5
+    assert (xp[:, :, 0] == 0).all(), "zero rows"
+    assert (xp[:, :, 1:, 0] == xp[:, :, 1:, 20]).all() and (xp[:, :, 1:, 21] == xp[:, :, 1:, 1]).all(), "wrap columns"
+    tail = img.view(Cout // 16, 2, 2, -1, 8)[:, :, :, n * 176:n * 176 + 22].float()
+    assert (tail == 0).all(), "zero row after the last sample"
+    # (c) presplit -> presplit -> fp32
+    o2 = torch.full((n, Cin // 4, 140, 4), float("nan"), device=dev)
+    ops.conv_layer_sd(ops.GEOM_CYL2D, img, wt(W2), b2.to(dev), o2, n, Cout, Cin, False)
+    assert rel(ops.from_blocked(o2).view(n, Cin, 7, 20), y2) < 3e-5
+
+
+def test_conv_sd_fp16_range_flag_and_fallback(dev):
+    """An activation beyond fp16 range cannot be split into fp16 operands: the kernel raises the sticky flag (and the model
+    then re-runs on the TF32 kernel, BufferX._decode)."""
+    from bufferx_b200 import ops
+    n, Cin, Cout = 3, 16, 32
+    x = torch.ones((n, Cin, 140), device=dev)
+    x[1, 3, 17] = 1.0e5
+    Wt = torch.full((9, Cin, Cout), 0.01, device=dev)
+    out = torch.empty((n, Cout // 4, 140, 4), device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.conv_layer_sd(ops.GEOM_CYL2D, ops.to_blocked(x), ops.conv_sd_weights(Wt), torch.zeros(Cout, device=dev), out, n, Cin, Cout, True, flag)
+    assert int(flag.item()) == 1
+    x[1, 3, 17] = 2.0
+    flag.zero_()
+    ops.conv_layer_sd(ops.GEOM_CYL2D, ops.to_blocked(x), ops.conv_sd_weights(Wt), torch.zeros(Cout, device=dev), out, n, Cin, Cout, True, flag)
+    assert int(flag.item()) == 0
+    # an OUTPUT beyond fp16 range cannot be written in the presplit format either
+    big = torch.full((9, Cin, Cout), 500.0, device=dev)
+    ops.conv_layer_sd(ops.GEOM_CYL2D, ops.to_blocked(x), ops.conv_sd_weights(big), torch.zeros(Cout, device=dev), ops.conv_sd_buffer(n, Cout, dev), n, Cin, Cout, True, flag)
+    assert int(flag.item()) == 1
 
 
 def test_cost_volume_first_layer_tc_vs_ffma(dev, oracle, c1):

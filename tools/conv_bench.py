@@ -8,6 +8,7 @@ import bufferx_b200 as bx
 from bufferx_b200 import ops
 from bufferx_b200.synth import init_synthetic_weights, workload_cfg
 
+MODE = os.environ.get("BX_CONV", "sd").lower()          # sd (shifted-descriptor fp16-split kernel) | tc (round-1 TF32 kernel)
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 cfg = workload_cfg("C2")
@@ -18,7 +19,10 @@ dev = torch.device("cuda")
 torch.manual_seed(0)
 x = torch.relu(torch.randn(K, 4, 420, 4, device=dev))            # channel-blocked
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-bufs = [torch.empty((K, l["cout"] // 4, 140, 4), device=dev) for l in L]
+if MODE == "sd":     # layer-to-layer activations in the presplit padded fp16 format, fp32 out of the last layer
+    bufs = [ops.conv_sd_buffer(K, l["cout"], dev) if i < len(L) - 1 else torch.empty((K, l["cout"] // 4, 140, 4), device=dev) for i, l in enumerate(L)]
+else:
+    bufs = [torch.empty((K, l["cout"] // 4, 140, 4), device=dev) for l in L]
 times = [[] for _ in L]
 for r in range(reps + 2):
     flush.zero_()
@@ -26,7 +30,9 @@ for r in range(reps + 2):
     for i, l in enumerate(L):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        if i == 0:
+        if MODE == "sd":
+            ops.conv_layer_sd(ops.GEOM_CYL3D if i == 0 else ops.GEOM_CYL2D, cur, l["w_sd"], l["b"], bufs[i], K, l["cin"], l["cout"], l["relu"], None)
+        elif i == 0:
             ops.conv_layer_tc(ops.GEOM_CYL3D, cur, l["w_tc"], l["b"], bufs[i], K, l["cin"], l["cout"], 3, 7, 20, 3, 3, 3, l["relu"])
         else:
             ops.conv_layer_tc(ops.GEOM_CYL2D, cur, l["w_tc"], l["b"], bufs[i], K, l["cin"], l["cout"], 1, 7, 20, 1, 3, 3, l["relu"])
@@ -43,9 +49,13 @@ for i, l in enumerate(L):
     stages = l["cin"] // 16 * taps
     nt = 128 if l["cout"] > 64 else (64 if l["cout"] > 32 else 32)
     tiles = (K * 140 + 127) // 128
-    tensor_min_us = stages * 6 * (nt / 2) * ((tiles + 147) // 148) / 1965.0     # 6 MMAs/stage, N/2 cycles each at 1.965 GHz
+    if MODE == "sd":        # 3 fp16 MMAs (K = 16) per stage, N/2 cycles each; tiles of 128 padded rows (176 per sample)
+        tiles = (K * 176 + 127) // 128
+        tensor_min_us = stages * 3 * (nt / 2) * ((tiles + 147) // 148) / 1965.0
+    else:
+        tensor_min_us = stages * 6 * (nt / 2) * ((tiles + 147) // 148) / 1965.0     # 6 MMAs/stage, N/2 cycles each at 1.965 GHz
     tot_ms += ms
     tot_fl += fl
     print(f"L{i}: {l['cin']:3d}->{l['cout']:3d} taps {taps:2d} stages {stages:3d}  {ms * 1e3:7.1f} us  {fl / ms / 1e9:6.1f} TFLOP/s  "
           f"tensor-min {tensor_min_us:6.1f} us ({100 * tensor_min_us / (ms * 1e3):4.1f} %)")
-print(f"stack: {tot_ms * 1e3:.1f} us  {tot_fl / tot_ms / 1e9:.1f} TFLOP/s fp32-equivalent")
+print(f"[{MODE}] stack: {tot_ms * 1e3:.1f} us  {tot_fl / tot_ms / 1e9:.1f} TFLOP/s fp32-equivalent")
