@@ -55,3 +55,49 @@ def gather_records(local: np.ndarray, n_pairs: int, device=None):
         out = out[~np.isnan(out[:, 26])]
     order = np.argsort(out[:, 26], kind="stable")
     return out[order]
+
+
+def evaluate_sharded(forward_fn, pairs, cfg, out_dir=None, experiment_id="bufferx_b200", timestr="run", dataset="synthetic", device=None,
+                     write_logs=False):
+    """The reference's test loop (test.py:132-338) over a LIST of pairs, sharded round-robin over the ranks of the default
+    process group: rank r calls ``forward_fn(data_source)`` (``BufferX.forward`` signature and return tuple) for the pairs
+    r, r + world, ..., evaluates each against ``data_source["relt_pose"]`` (test.py:168-172), packs one record per pair, ONE
+    all-gather collects them, and rank 0 writes the reference's artefacts from the gathered records: the per-sample CSV
+    (utils/result_io.py:7-49), the summary CSV (:80-124) and -- ``write_logs`` -- the 3DMatch ``.log`` entries
+    (test.py:151-166).  Returns (summary dict, states [n_pairs, 12]) on every rank."""
+    import os
+    import time
+    from . import evaluation as E
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    rte_th, rre_th = cfg.test.rte_thresh, cfg.test.rre_thresh
+    recs = []
+    for i in shard_indices(len(pairs), rank, world):
+        d = pairs[i]
+        t0 = time.perf_counter()
+        pose, times, ninl, nmut, nind, su = forward_fn(d)
+        wall = time.perf_counter() - t0
+        gt = np.asarray(d["relt_pose"].cpu() if isinstance(d["relt_pose"], torch.Tensor) else d["relt_pose"])
+        st = E.pair_state(pose, gt, ninl, nmut, nind, su, times if any(times) else [wall, 0.0, 0.0], rte_th, rre_th)
+        recs.append(pack_record(i, pose if pose is not None else np.eye(4), st[9:12], ninl, nmut, nind, su, rte=st[1], rre=st[2], success=float(st[0])))
+    local = np.stack(recs) if recs else np.zeros((0, RECORD), np.float32)
+    allrec = gather_records(local, len(pairs), device=device)
+    states = E.states_from_records(allrec)
+    summary = E.summarize_states(states, dataset)
+    if rank == 0 and out_dir is not None:
+        exp = experiment_id.rsplit("/", 1)[-1]
+        pose_method = str(cfg.match.pose_estimator).upper()
+        early = "ON" if cfg.match.get("enable_early_exit", True) else "OFF"
+        E.save_per_sample_results(states, os.path.join(out_dir, "per_sample_results", exp,
+                                                       f"{exp}_{dataset}_{cfg.patch.num_points_per_patch}_{cfg.patch.num_scales}_{cfg.patch.num_fps}_{timestr}.csv"),
+                                  pose_method, early)
+        E.save_full_results_csv([summary], experiment_id, timestr, cfg.patch.num_points_per_patch, cfg.patch.num_scales, cfg.patch.num_fps,
+                                full_results_dir=os.path.join(out_dir, "full_results"))
+        if write_logs:
+            for r in allrec:
+                u = unpack_record(r)
+                d = pairs[u["pair_id"]]
+                scene = str(d.get("scene_name", "scene"))
+                E.append_trajectory_entry(os.path.join(out_dir, "logs", scene, f"{timestr}.log"), str(d.get("src_id", u["pair_id"])).split("_")[-1],
+                                          str(d.get("tgt_id", u["pair_id"])).split("_")[-1], u["pose"])
+    return summary, states
