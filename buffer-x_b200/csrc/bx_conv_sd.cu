@@ -433,7 +433,7 @@ BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const voi
     BX_REQUIRE(in && w_sd && bias && out, "bx_conv_layer_sd: null pointer");
     BX_REQUIRE(geom == BX_GEOM_CYL3D || geom == BX_GEOM_CYL2D, "bx_conv_layer_sd: only the cylindrical geometries (CYL3D / CYL2D)");
     BX_REQUIRE(n >= 0 && Cin >= 16 && Cin % 16 == 0 && Cout >= 4 && Cout % 4 == 0 && Cout <= 128, "bx_conv_layer_sd: bad channels Cin=%d Cout=%d", Cin, Cout);
-    BX_REQUIRE(geom != BX_GEOM_CYL3D || (Cin == 16 && !in_presplit), "bx_conv_layer_sd: CYL3D expects 16 fp32 input channels x 3 radial slices");
+    BX_REQUIRE(geom != BX_GEOM_CYL3D || Cin == 16, "bx_conv_layer_sd: CYL3D expects 16 input channels x 3 radial slices");
     BX_REQUIRE(!out_presplit || Cout % 16 == 0, "bx_conv_layer_sd: presplit output needs Cout %% 16 == 0");
     BX_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(w_sd)) & 15) == 0,
                "bx_conv_layer_sd: activations, weights and bias must be 16-byte aligned");

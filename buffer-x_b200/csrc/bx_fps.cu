@@ -81,7 +81,7 @@ __device__ __forceinline__ void fps_wait_cluster(uint32_t bar, uint32_t parity) 
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, int npoint,
-                   int *__restrict__ idx_out, float *__restrict__ kpts_out) {
+                   int *__restrict__ idx_out, float *__restrict__ kpts_out, int sync_mode) {
     constexpr int NW = THREADS / 32;
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int)cluster.num_blocks();
@@ -174,11 +174,14 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
                 fps_st_cluster_v4(fps_mapa(fps_smem_u32(&c_a[par][rank]), (uint32_t)lane),
                                   make_uint4(cb.hi, cb.lo, __float_as_uint(cb.x), __float_as_uint(cb.y)));
                 fps_st_cluster_f32(fps_mapa(fps_smem_u32(&c_z[par][rank]), (uint32_t)lane), cb.z);
-                fps_arrive_cluster(fps_mapa(fps_smem_u32(&cbar[par]), (uint32_t)lane));
+                if (!sync_mode) fps_arrive_cluster(fps_mapa(fps_smem_u32(&cbar[par]), (uint32_t)lane));
             }
             // Buffers and barriers are double-buffered by parity: a peer can only be one iteration ahead (its next
             // wait needs our next arrive), so slot [par] is not rewritten before everybody has read it.
-            fps_wait_cluster(fps_smem_u32(&cbar[par]), (uint32_t)(((j >> 1) - (par ? 0 : 1)) & 1));
+            // sync_mode (BX_FPS_SYNC=1, verification only): the same exchange ordered by a plain cluster.sync() -- the form
+            // compute-sanitizer's racecheck models; results are bit-identical (tests/test_gpu_parity.py).
+            if (sync_mode) cluster.sync();
+            else fps_wait_cluster(fps_smem_u32(&cbar[par]), (uint32_t)(((j >> 1) - (par ? 0 : 1)) & 1));
             Cand g;
             g.hi = 0u; g.lo = 0u; g.x = p0x; g.y = p0y; g.z = p0z;
             if (lane < CL) {
@@ -203,6 +206,8 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
     cluster.sync();  // nobody exits while a peer may still write into its shared memory
 }
 
+int g_fps_sync_override = -1;
+
 template <int THREADS, int PPT>
 int launch_fps(const float *xyz, const FpsOffsets off, int B, int CL, int npoint, int *idx, float *kpts, cudaStream_t st) {
     auto kern = fps_cluster_kernel<THREADS, PPT>;
@@ -219,12 +224,24 @@ int launch_fps(const float *xyz, const FpsOffsets off, int B, int CL, int npoint
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    BX_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, off, npoint, idx, kpts));
+    static int sync_mode = -1;     // BX_FPS_SYNC=1: cluster.sync() exchange (racecheck-clean reference form of the mbarrier exchange)
+    if (sync_mode < 0) { const char *e = getenv("BX_FPS_SYNC"); sync_mode = (e && atoi(e)) ? 1 : 0; }
+    if (g_fps_sync_override >= 0) sync_mode = g_fps_sync_override;
+    BX_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, off, npoint, idx, kpts, sync_mode));
     ++g_bx_launches;
     return BX_OK;
 }
 
 }  // namespace
+
+// Verification switch: 1 = order the per-iteration cluster exchange with cluster.sync() instead of the remote-mbarrier
+// arrive / acquire-wait pair (same data path, same results; the form compute-sanitizer racecheck models), 0 = production,
+// -1 = follow the BX_FPS_SYNC environment variable.  Returns the previous value.
+BX_API int bx_fps_set_sync_mode(int mode) {
+    const int old = g_fps_sync_override;
+    g_fps_sync_override = mode;
+    return old;
+}
 
 BX_API int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint, int32_t *idx, float *kpts,
                   void *stream) {

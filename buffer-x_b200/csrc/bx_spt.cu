@@ -24,6 +24,8 @@
 // The candidate enumeration is conservative (slack 1e-3 on the bands, +1 azimuth bin), membership itself is
 // the bit-exact test of oracle bxo_spt: d2 = ((qx-x)^2+(qy-y)^2)+(qz-z)^2 < r*r; slot 0 zeroed when its index
 // is 0 (utils/common.py:447-449), padding slots zeroed; x' = x*c + y*(-s), y' = x*s + y*c.  -fmad=false.
+#include <cuda_fp16.h>
+
 #include "bx_common.cuh"
 
 namespace {
@@ -32,11 +34,14 @@ constexpr int SPT_THREADS = 256;
 constexpr int MAX_NV = 16;
 constexpr int MAX_RE = 64;   // rad_n * ele_n rows of the voxel table
 
+// SD = 1: the features leave the kernel in the presplit padded fp16 format of bx_conv_layer_sd (three radial slices = three
+// 16-channel chunks over the 8 x 22 raster, zero rows and wrap columns included) instead of fp32 channel-blocked.
+template <int SD>
 __global__ void __launch_bounds__(SPT_THREADS)
 spt_pnt_kernel(const float *__restrict__ delta, int K, int P, const float *__restrict__ voxels, int V, int azi_n,
                const float *__restrict__ rot, float voxel_r, int nv, const float *__restrict__ w,
                const float *__restrict__ b, float *__restrict__ feat, int *__restrict__ dbg_vidx,
-               float *__restrict__ dbg_inv) {
+               float *__restrict__ dbg_inv, long long sd_rows, int *__restrict__ sd_flag) {
     extern __shared__ float smem[];
     const int NW = (P + 31) >> 5;
     float *px = smem;                                   // P
@@ -215,6 +220,66 @@ spt_pnt_kernel(const float *__restrict__ delta, int K, int P, const float *__res
     __syncthreads();
     // ---- 4. features in the channel-blocked layout [K][16/4][V][4] the tensor-core convolution reads: thread = (group
     //         of 4 channels, voxel); the selected non-zero points are de-rotated once per thread; one 16-byte store ----
+    if (SD) {
+        // thread = (kcore of 8 channels, voxel): one 16-byte hi and one 16-byte lo store (x = hi + lo * 2^-11, the split the
+        // convolution's own loader would apply to the fp32 features -- bit-identical operands)
+        uint4 *img = reinterpret_cast<uint4 *>(feat);
+        float omax = 0.0f;
+        for (int t = tid; t < 2 * V; t += SPT_THREADS) {
+            const int h = t / V, v = t - h * V;
+            float w0[8], w1[8], w2[8], bb[8], best[8];
+            const int c = scnt[v];
+            unsigned nzm = snz[v];
+            const bool any_zero = (c < nv) || (__popc(nzm) < c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int ch = h * 8 + q;
+                w0[q] = sw[3 * ch]; w1[q] = sw[3 * ch + 1]; w2[q] = sw[3 * ch + 2]; bb[q] = sw[48 + ch];
+                best[q] = any_zero ? fmaxf(bb[q], 0.0f) : -INFINITY;
+            }
+            const int a = v % azi_n;
+            const float cs = srot[2 * a], sn = srot[2 * a + 1];
+            while (nzm) {
+                const int l = __ffs(nzm) - 1;
+                nzm &= nzm - 1;
+                const int i = sel[(size_t)v * MAX_NV + l];
+                const float x = px[i], y = py[i], z = pz[i];
+                const float xr = (x * cs) + (y * (-sn));
+                const float yr = (x * sn) + (y * cs);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float val = (((w0[q] * xr) + (w1[q] * yr)) + (w2[q] * z)) + bb[q];
+                    best[q] = fmaxf(best[q], fmaxf(val, 0.0f));
+                }
+            }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __half2 hh = __floats2half2_rn(best[2 * e], best[2 * e + 1]);
+                const float2 hf = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn((best[2 * e] - hf.x) * 2048.0f, (best[2 * e + 1] - hf.y) * 2048.0f);
+                hi[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                lo[e] = *reinterpret_cast<const uint32_t *>(&ll);
+                omax = fmaxf(omax, fmaxf(fabsf(best[2 * e]), fabsf(best[2 * e + 1])));
+            }
+            const int r = v / (7 * 20), rem = v - r * 140, ey = rem / 20, ax = rem - ey * 20;
+            uint4 *im = img + (size_t)(r * 4 + h) * sd_rows + (size_t)k * 176 + (ey + 1) * 22;
+            const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            im[ax + 1] = vh;
+            im[2 * sd_rows + ax + 1] = vl;
+            if (ax == 19) { im[0] = vh; im[2 * sd_rows] = vl; }          // wrap column x' = 0
+            if (ax == 0) { im[21] = vh; im[2 * sd_rows + 21] = vl; }     // wrap column x' = 21
+        }
+        // the zero row above this sample's first elevation (and, from the last sample, the one below its last)
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int t = tid; t < 12 * 22; t += SPT_THREADS) {
+            const int im = t / 22, xp = t - im * 22;
+            img[(size_t)im * sd_rows + (size_t)k * 176 + xp] = z4;
+            if (k == K - 1) img[(size_t)im * sd_rows + (size_t)K * 176 + xp] = z4;
+        }
+        if (!(omax < 65000.0f) && sd_flag) atomicOr(sd_flag, 1);
+        return;
+    }
     float4 *out4 = reinterpret_cast<float4 *>(feat + (size_t)k * 16 * V);
     for (int t = tid; t < 4 * V; t += SPT_THREADS) {
         const int cg = t / V, v = t - cg * V;
@@ -270,9 +335,28 @@ BX_API int bx_spt_pnt(const float *delta, int K, int P, const float *voxels, int
     BX_REQUIRE(smem <= 200 * 1024, "bx_spt_pnt: P=%d V=%d needs %zu bytes of shared memory", P, V, smem);
     static BxPerDevice attr = {};
     if (bx_needs_attr(attr, smem))
-        BX_CUDA(cudaFuncSetAttribute(spt_pnt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spt_pnt_kernel<<<K, SPT_THREADS, smem, bx_stream(stream)>>>(delta, K, P, voxels, V, azi_n, rot, voxel_r, nv, w, b,
-                                                             feat, dbg_vidx, dbg_inv);
+        BX_CUDA(cudaFuncSetAttribute(spt_pnt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spt_pnt_kernel<0><<<K, SPT_THREADS, smem, bx_stream(stream)>>>(delta, K, P, voxels, V, azi_n, rot, voxel_r, nv, w, b,
+                                                                feat, dbg_vidx, dbg_inv, 0, nullptr);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
+BX_API int bx_spt_pnt_sd(const float *delta, int K, int P, const float *voxels, int V, int azi_n, const float *rot,
+                         float voxel_r, int nv, const float *w, const float *b, void *feat_sd, long long rows, int32_t *d_flag,
+                         void *stream) {
+    BX_REQUIRE(delta && voxels && rot && w && b && feat_sd, "bx_spt_pnt_sd: null pointer");
+    BX_REQUIRE(K >= 0 && P >= 1 && P <= 65535 && nv >= 1 && nv <= MAX_NV, "bx_spt_pnt_sd: bad sizes");
+    BX_REQUIRE(V == 420 && azi_n == 20, "bx_spt_pnt_sd: the presplit raster is 3 radial x 7 elevation x 20 azimuth voxels");
+    BX_REQUIRE(rows >= (long long)K * 176 + 22 && (reinterpret_cast<uintptr_t>(feat_sd) & 15) == 0, "bx_spt_pnt_sd: image too small or misaligned");
+    if (K == 0) return BX_OK;
+    const size_t smem = spt_smem_bytes(P, V, azi_n);
+    BX_REQUIRE(smem <= 200 * 1024, "bx_spt_pnt_sd: P=%d V=%d needs %zu bytes of shared memory", P, V, smem);
+    static BxPerDevice attr = {};
+    if (bx_needs_attr(attr, smem))
+        BX_CUDA(cudaFuncSetAttribute(spt_pnt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spt_pnt_kernel<1><<<K, SPT_THREADS, smem, bx_stream(stream)>>>(delta, K, P, voxels, V, azi_n, rot, voxel_r, nv, w, b,
+                                                                reinterpret_cast<float *>(feat_sd), nullptr, nullptr, rows, d_flag);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

@@ -137,13 +137,19 @@ class MiniSpinNet(nn.Module):
             Rs.append(R)
             axes.append(ra)
             o += K
-        feat = ops.spt_pnt(delta, prep["voxels"], prep["rot"], self.delta / self.rad_n, self.voxel_sample, prep["w_pnt"],
-                           prep["b_pnt"], self.azi_n)
+        net = self.conv_net
+        if not pn.USE_FFMA and not net.force_tf32 and self.rad_n * self.ele_n * self.azi_n == 420 and self.azi_n == 20:
+            # production: features straight into the presplit fp16 format the first conv layer fetches with bulk copies
+            feat = ops.spt_pnt_sd(delta, prep["voxels"], prep["rot"], self.delta / self.rad_n, self.voxel_sample, prep["w_pnt"],
+                                  prep["b_pnt"], self.azi_n, net.overflow_flag(dev))
+        else:
+            feat = ops.spt_pnt(delta, prep["voxels"], prep["rot"], self.delta / self.rad_n, self.voxel_sample, prep["w_pnt"],
+                               prep["b_pnt"], self.azi_n)
         if pn.USE_FFMA:
             x, _ = self.conv_net(ops.from_blocked(feat).view(Kt, 16, self.rad_n, self.ele_n, self.azi_n))
             desc, equi = ops.pool_desc(x, prep["w1"], prep["b1"], prep["w2"], prep["b2"])
         else:
-            x, _ = self.conv_net(feat)
+            x, _ = self.conv_net(feat, K=Kt)
             desc, equi = ops.pool_desc(x, prep["w1"], prep["b1"], prep["w2"], prep["b2"], channels_last=True)
         outs, o = [], 0
         for K, R, ra in zip(Ks, Rs, axes):

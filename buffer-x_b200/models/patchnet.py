@@ -115,14 +115,16 @@ class Cylindrical_Net(_ConvStack):
             self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         return self._flag
 
-    def forward(self, x):
-        """Tensor-core path (default): x [K,4,420,4] channel-blocked -> x_out [K,8,140,4] channel-blocked.
+    def forward(self, x, K=None):
+        """Tensor-core path (default): x [K,4,420,4] channel-blocked (or the presplit image of K patches) -> x_out [K,8,140,4].
         CUDA-core debug path (BX_CONV=ffma): x [K,16,3,7,20] -> [K,32,7,20].  Returns (x_out, None)."""
-        K = x.shape[0]
+        presplit_in = x.dtype == torch.float16             # [3, 4, rows, 8] from bx_spt_pnt_sd: K is passed separately
+        K = x.shape[0] if not presplit_in else int(K)
         dev = x.device
         L = self.folded()
         cur = x.contiguous()
         use_sd = not USE_FFMA and not self.force_tf32
+        assert use_sd or not presplit_in
         flag = self.overflow_flag(dev) if use_sd else None
         for i, l in enumerate(L):
             out = torch.empty((K, l["cout"], 140) if USE_FFMA else (K, l["cout"] // 4, 140, 4), dtype=torch.float32, device=dev)

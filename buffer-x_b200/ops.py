@@ -23,7 +23,7 @@ SYMBOLS = [
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
     "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab", "bx_concat_matches",
-    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows",
+    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
@@ -66,6 +66,8 @@ def load_library():
     lib.bx_conv_tc_ntile.argtypes = [c_int]
     lib.bx_conv_layer_sd.argtypes = [c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]
     lib.bx_conv_sd_rows.argtypes = [c_int]
+    lib.bx_fps_set_sync_mode.argtypes = [c_int]
+    lib.bx_spt_pnt_sd.argtypes = [P, c_int, c_int, P, c_int, c_int, P, c_float, c_int, P, P, P, c_int64, P, P]
     lib.bx_conv_sd_rows.restype = c_int64
     lib.bx_costvol_ab.argtypes = [P, P, P, P, P, c_int, P, P, P, P, P, P]
     lib.bx_concat_matches.argtypes = [P, P, P, c_int, c_int, P, P, P, P, P, P]
@@ -249,6 +251,17 @@ def lrf(patches: torch.Tensor, des_r, aligned: bool, delta=None, Rt=None, ra=Non
         flags = int(bool(aligned)) | (2 if os.environ.get("BX_LRF", "").lower() == "stable" else 0)
         _check(load_library().bx_lrf(_dp(patches, F32, "patches"), K, P, rv, rp, flags, _dp(delta), _dp(Rt), _dp(ra), _stream()), "bx_lrf")
     return delta, Rt, ra
+
+
+def spt_pnt_sd(delta, voxels, rot, voxel_r: float, nv: int, w, b, azi_n: int, flag=None):
+    """SPT + point layer with the features in the presplit padded fp16 format: [3, 4, conv_sd_rows(K), 8] fp16."""
+    K, P, _ = delta.shape
+    V = voxels.shape[0]
+    feat = conv_sd_buffer(K, 48, delta.device)
+    with _Span("spt", 12.0 * K * P + 64.0 * K * V):
+        _check(load_library().bx_spt_pnt_sd(_dp(delta, F32, "delta"), K, P, _dp(voxels, F32), V, azi_n, _dp(rot, F32), float(voxel_r), nv,
+                                            _dp(w, F32), _dp(b, F32), _dp(feat), feat.shape[2], _dp(flag, I32, "flag"), _stream()), "bx_spt_pnt_sd")
+    return feat
 
 
 def spt_pnt(delta, voxels, rot, voxel_r: float, nv: int, w, b, azi_n: int, debug=False, feat=None):

@@ -50,6 +50,9 @@ unsigned long long bx_launch_count(void); /* kernels launched by this library si
  * idx: [B,npoint] int32 (index inside the cloud); kpts: [B,npoint,3] (may be NULL).
  * Limit: N <= 131072 per cloud. */
 int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint, int32_t *idx, float *kpts, void *stream);
+/* Verification switch for the FPS cluster exchange: 1 = cluster.sync() per iteration (racecheck-clean reference form),
+ * 0 = remote mbarrier arrive + acquire wait (production), -1 = BX_FPS_SYNC environment variable.  Returns the old value. */
+int bx_fps_set_sync_mode(int mode);
 
 /* ---- a2: density-aware radius estimation ----------------------------------------------------
  * Replaces density_aware_radius_estimation + squared_cdist (models/BUFFERX.py:610-696) without
@@ -99,6 +102,12 @@ int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r
 int bx_spt_pnt(const float *delta, int K, int P, const float *voxels, int V, int azi_n, const float *rot,
                float voxel_r, int nv, const float *w, const float *b, float *feat, int32_t *dbg_vidx,
                float *dbg_inv, void *stream);
+/* Same computation; the features are written in the presplit padded fp16 format that bx_conv_layer_sd reads with bulk
+ * copies: feat_sd [3 (radial slice = 16-channel chunk)][4 (split, kcore)][rows][8 x fp16], rows = bx_conv_sd_rows(K),
+ * zero rows and wrap columns included; V must be 3*7*20.  *d_flag |= 1 if a feature is outside fp16 range. */
+int bx_spt_pnt_sd(const float *delta, int K, int P, const float *voxels, int V, int azi_n, const float *rot,
+                  float voxel_r, int nv, const float *w, const float *b, void *feat_sd, long long rows, int32_t *d_flag,
+                  void *stream);
 
 /* ---- a8/a11: convolution stacks -------------------------------------------------------------
  * One implicit-GEMM kernel serves every conv layer of Cylindrical_Net (models/patchnet.py:16-84,

@@ -51,6 +51,26 @@ def test_fps_bit_exact(dev, oracle, n, m, kind):
     assert (kp[0].cpu().numpy() == xyz[exp]).all()
 
 
+@pytest.mark.parametrize("n,m", [(20000, 1500), (120000, 300), (5000, 512)])
+def test_fps_mbarrier_exchange_equals_cluster_sync_exchange(dev, oracle, n, m):
+    """The production cluster exchange (remote st.shared::cluster + mbarrier.arrive.release.cluster, local acquire wait) and
+    the verification form (the same stores ordered by cluster.sync(), which racecheck models; profiles/r02_sanitizer_*)
+    give the same indices -- and both equal the oracle."""
+    from bufferx_b200 import ops
+    lib = ops.load_library()
+    rng = np.random.default_rng(n)
+    xyz = rng.normal(size=(n, 3)).astype(np.float32)
+    d = cu(xyz, dev)
+    old = lib.bx_fps_set_sync_mode(1)
+    try:
+        a, _ = ops.fps(d, [0, n], m)
+        lib.bx_fps_set_sync_mode(0)
+        b, _ = ops.fps(d, [0, n], m)
+    finally:
+        lib.bx_fps_set_sync_mode(old)
+    assert torch.equal(a, b) and (a[0].cpu().numpy() == oracle.fps(xyz, m)).all()
+
+
 def test_fps_two_clouds_one_launch(dev, oracle):
     from bufferx_b200 import ops
     rng = np.random.default_rng(0)
@@ -143,6 +163,23 @@ def test_spt_pnt(dev, oracle, c1):
 
 
 # ------------------------------------------------------------------------------------------- a8+a9
+def test_spt_presplit_output_is_the_split_of_the_fp32_features(dev, oracle, c1):
+    """bx_spt_pnt_sd writes the features directly in the presplit padded fp16 format of the conv kernel: bit-identical to
+    splitting bx_spt_pnt's fp32 features (hi = fp16(x), lo = fp16((x - hi) * 2^11)), zero rows and wrap columns included."""
+    from bufferx_b200 import ops
+    delta = c1["res"][5]["scales"][0]["src"]["delta"]
+    K = delta.shape[0]
+    prep = c1["model"].to(dev).Desc.prepared(dev)
+    d = cu(delta, dev)
+    feat = ops.spt_pnt(d, prep["voxels"], prep["rot"], 0.8 / 3, 10, prep["w_pnt"], prep["b_pnt"], 20)
+    img = ops.spt_pnt_sd(d, prep["voxels"], prep["rot"], 0.8 / 3, 10, prep["w_pnt"], prep["b_pnt"], 20)
+    x = ops.from_blocked(feat).view(K, 16, 3, 140).permute(0, 2, 1, 3).reshape(K, 48, 7, 20)      # chunk = radial slice
+    want = ops.sd_pack(x)
+    rows = K * 176 + 22
+    assert img.shape == want.shape and torch.equal(img[:, :, :rows].view(torch.int16), want[:, :, :rows].view(torch.int16))
+    c1["model"].cpu()
+
+
 def test_cylindrical_net_and_pooling(dev, oracle, c1):
     from bufferx_b200 import ops
     aux = c1["res"][5]
