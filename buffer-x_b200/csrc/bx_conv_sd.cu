@@ -19,17 +19,19 @@
 //   precision   fp32-grade results (descriptor parity 1e-4 rel) from fp16 tensor-core operands: x = hi + lo * 2^-11 with
 //               hi = fp16(x), lo = fp16((x - hi) * 2^11) (22 mantissa bits, the same as the 3xTF32 split, at twice the
 //               tensor rate and half the operand bytes):  a*b ~= ah*bh + (al*bh + ah*bl) * 2^-11.  The ah*bh products go to
-//               a ping-pong pair of TMEM accumulators cut after every 16-channel chunk (nine MMAs, K = 144) and are added with round-to-nearest into
-//               fp32 running sums in registers (the tensor core accumulates with truncation: bx_conv_tc.cu header); the
-//               cross terms keep one chain per tile in their own ping-pong accumulator and are scaled by 2^-11 at the end.
+//               a ping-pong pair of TMEM accumulator sets [main | cross] cut after every 16-channel chunk (K = 144); a finished
+//               segment's main + cross * 2^-11 is added with round-to-nearest into fp32 running sums in registers (the tensor
+//               core accumulates with truncation: bx_conv_tc.cu header).  Per tap TWO instructions: ah * [bh | bl] as one
+//               N = 2*NT MMA into [main | cross] (the hi activations are fetched from shared memory once for both products --
+//               the kernel is bound by the tensor core's shared-memory operand reads), then al * bh into the cross columns.
 //               |x| >= 65504 cannot be represented: the loader raises *flag and the host re-runs the layer on the TF32 kernel.
 //
 // Persistent warp-specialised CTA, one per SM:
 //   4 loader warps    fill the A ring (NA chunk slots): fp32 channel-blocked activations [n][C/4][pos][4] -> fp16 hi/lo,
 //                     padding rows / wrap columns materialised by index arithmetic; fence.proxy.async + mbarrier.
-//   1 weight warp     streams the host-arranged weight image [chunk][tap][split][kcore][n][8 x fp16] through the B ring with
+//   1 weight warp     streams the host-arranged weight image [chunk][tap][kcore][split][n][8 x fp16] through the B ring with
 //                     cp.async.bulk + mbarrier transaction counts (SB stages per copy).
-//   1 MMA warp        per (chunk, tap): 3 x tcgen05.mma.kind::f16 (SS form, M = 128, N = NT, K = 16); tcgen05.commit to the
+//   1 MMA warp        per (chunk, tap): 2 x tcgen05.mma.kind::f16 (SS form, M = 128, N = 2*NT and NT, K = 16); tcgen05.commit to the
 //                     slot / segment / tile barriers.  No thread ever touches an activation between shared memory and the MMA.
 //   4*ECS epilogue warps   drain finished segments (tcgen05.ld) into running sums, then bias (+ReLU) and 16-byte
 //                     channel-blocked stores of the valid rows -- while the tensor core already works on the next tile.
@@ -61,7 +63,7 @@ struct ConvSdParams {
 
 // B ring: one bulk copy / one mbarrier per SUPER-STAGE of three taps (the MMA warp's issue loop is the critical resource:
 // every barrier wait costs it ~90 cycles), NBS super-stages deep.
-template <int NT> struct SdRing { static constexpr int SB = 3, NBS = NT == 128 ? 3 : (NT == 64 ? 4 : 6); };
+template <int NT> struct SdRing { static constexpr int SB = 3, NBS = NT == 128 ? 3 : (NT == 64 ? 4 : 6); };   // deeper rings (5 / 8 / 12) measured: no gain
 
 __device__ __forceinline__ void mma_f16_ss(uint32_t leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -81,13 +83,17 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t leader, uint32_t tmem_d, uin
 
 // IN_SD = 0: fp32 channel-blocked input converted by the loader warps; 1: presplit padded fp16 images fetched with bulk copies.
 // OUT_SD = 0: fp32 channel-blocked output; 1: presplit padded fp16 images (zero rows and wrap columns written here).
+// MERGED (NT <= 64): per tap ah * [bh | bl] as ONE N = 2*NT instruction into [main | cross] + al * bh; both halves are cut
+// and drained per segment.  NT = 128 (N = 256 instructions and twice the drain traffic measured 5 % SLOWER there): three
+// N = 128 instructions per tap, main ping-pong per segment, cross accumulators one chain per tile (ping-pong by tile).
 template <int NT, int ECS, int IN_SD, int OUT_SD>
 __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(const ConvSdParams p) {
+    constexpr bool MERGED = NT <= 64;
     constexpr int NE = 4 * ECS, MMA_WARP = NE + SD_NL, WGT_WARP = NE + SD_NL + 1;
     constexpr int CW = NT / ECS;                  // accumulator columns of one epilogue warp
     constexpr int SB = SdRing<NT>::SB, NBS = SdRing<NT>::NBS;
-    constexpr int B_STAGE = 64 * NT;              // [split][kcore][n][16 B]
-    constexpr int TMEM_COLS = 4 * NT;             // main[2], cross[2]
+    constexpr int B_STAGE = 64 * NT;              // [kcore][split][n][16 B]
+    constexpr int TMEM_COLS = 4 * NT;             // MERGED: two sets of [main | cross]; else main[2], cross[2]
     constexpr int MAXNA = 12;
     // barriers
     constexpr int BAR_AFULL = 0, BAR_AEMPTY = MAXNA, BAR_BFULL = 2 * MAXNA, BAR_BEMPTY = BAR_BFULL + NBS;
@@ -148,18 +154,40 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
 #pragma unroll
                 for (int c0 = 0; c0 < CW; c0 += 32) {
                     uint32_t v[32];
-                    tmem_ld<32>(tmem_base + tm_lane + (uint32_t)(set * NT + ecs * CW + c0), v);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if constexpr (MERGED) {
+                        uint32_t u[32];
+                        tmem_ld<32>(tmem_base + tm_lane + (uint32_t)(set * 2 * NT + ecs * CW + c0), v);            // ah*bh
+                        tmem_ld<32>(tmem_base + tm_lane + (uint32_t)(set * 2 * NT + NT + ecs * CW + c0), u);       // (ah*bl + al*bh) * 2^11
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) run[c0 + c] += __uint_as_float(v[c]);
+                        for (int c = 0; c < 32; ++c) run[c0 + c] += fmaf(__uint_as_float(u[c]), 0.00048828125f, __uint_as_float(v[c]));
+                    } else {
+                        tmem_ld<32>(tmem_base + tm_lane + (uint32_t)(set * NT + ecs * CW + c0), v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) run[c0 + c] += __uint_as_float(v[c]);
+                    }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_ACCFREE + set));
             }
-            const int xset = k & 1;
-            mbar_wait(bar_base + 8u * (BAR_XDONE + xset), (uint32_t)((k >> 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if constexpr (!MERGED) {      // the tile's cross accumulator: one read, scaled by 2^-11
+                const int xset = k & 1;
+                mbar_wait(bar_base + 8u * (BAR_XDONE + xset), (uint32_t)((k >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c0 = 0; c0 < CW; c0 += 32) {
+                    uint32_t u[32];
+                    tmem_ld<32>(tmem_base + tm_lane + (uint32_t)(2 * NT + xset * NT + ecs * CW + c0), u);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) run[c0 + c] = fmaf(__uint_as_float(u[c]), 0.00048828125f, run[c0 + c]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_XFREE + xset));
+            }
             const long long R = (long long)t * SD_BM + quarter * 32 + lane;
             const int s = (int)(R / SD_SROWS), q = (int)(R - (long long)s * SD_SROWS);
             const int y = q / 22, x = q - y * 22;
@@ -173,14 +201,6 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
             float omax = 0.0f;
 #pragma unroll
             for (int c0 = 0; c0 < CW; c0 += 32) {
-                uint32_t u[32];
-                tmem_ld<32>(tmem_base + tm_lane + (uint32_t)(2 * NT + xset * NT + ecs * CW + c0), u);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 32 >= CW) {           // last piece read: the cross accumulator may be overwritten by tile k + 2
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_XFREE + xset));
-                }
                 if (OUT_SD ? live : valid) {
 #pragma unroll
                     for (int c = 0; c < 32; c += 8) {
@@ -189,7 +209,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                             float r[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                r[e] = fmaf(__uint_as_float(u[c + e]), 0.00048828125f, run[c0 + c + e]) + __ldg(p.bias + co + e);
+                                r[e] = run[c0 + c + e] + __ldg(p.bias + co + e);
                                 if (p.relu) r[e] = fmaxf(r[e], 0.0f);
                             }
                             if (!OUT_SD) {
@@ -339,17 +359,18 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
         // three taps, one segment (= one 16-channel chunk, nine main MMAs) per accumulator set.
         // instruction descriptor: D = F32, A = B = F16, both K-major, N = NT, M = 128
         constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // N = 2 * NT
         constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);            // SBO = 128 B (8 rows x 16 B), descriptor version 1
         constexpr uint32_t A_LBO = ((uint32_t)SD_KCORE >> 4) << 16;       // K-adjacent core matrices: one kcore image apart
-        constexpr uint32_t B_LBO = ((uint32_t)(NT * 16) >> 4) << 16;
-        constexpr uint32_t A_SPLIT = (2u * SD_KCORE) >> 4, B_SPLIT = (2u * NT * 16) >> 4;   // hi -> lo image, 16-byte units
+        constexpr uint32_t B_LBO = ((uint32_t)(2 * NT * 16) >> 4) << 16;   // weight image [kcore][split(hi,lo)][n][16 B]: K-adjacent core matrices 2*NT rows apart
+        constexpr uint32_t A_SPLIT = (2u * SD_KCORE) >> 4, B_LO16 = (uint32_t)(NT * 16) >> 4;   // hi -> lo image (A), hi -> lo rows (B), 16-byte units
         constexpr uint32_t B_STAGE16 = (uint32_t)B_STAGE >> 4, A_CHUNK16 = (uint32_t)SD_CHUNK >> 4;
         const uint32_t leader = elect_leader();
         const uint32_t a0 = (a_base >> 4) | A_LBO, b0 = (b_base >> 4) | B_LBO;
         uint32_t slot = 0, a_par = 0, sbq = 0, b_par = 0, seg = 0, k = 0;
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++k) {
             const uint32_t xset = k & 1;
-            if (k >= 2) {
+            if (!MERGED && k >= 2) {
                 mbar_wait(bar_base + 8u * (BAR_XFREE + xset), ((k >> 1) - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
@@ -360,8 +381,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                 if (seg >= 2) mbar_wait(bar_base + 8u * (BAR_ACCFREE + set), ((seg >> 1) - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ac = a0 + slot * A_CHUNK16;
-                const uint32_t d_main = tmem_base + set * NT;
-                const uint32_t first = c == 0 ? 0u : 1u;
+                const uint32_t d_set = tmem_base + set * (2u * NT);      // [main | cross]
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
                     mbar_wait(bar_base + 8u * (BAR_BFULL + sbq), b_par);
@@ -370,10 +390,18 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
 #pragma unroll
                     for (int tt = 0; tt < 3; ++tt) {
                         const uint32_t ah = ac + (uint32_t)(g * 22 + tt), al = ah + A_SPLIT;      // one row = 16 B = one address unit
-                        const uint32_t bh = bg + (uint32_t)tt * B_STAGE16, bl = bh + B_SPLIT;
-                        mma_f16_ss(leader, d_cross, al, bh, DESC_HI, IDESC, (g == 0 && tt == 0) ? first : 1u);
-                        mma_f16_ss(leader, d_cross, ah, bl, DESC_HI, IDESC, 1u);
-                        mma_f16_ss(leader, d_main, ah, bh, DESC_HI, IDESC, (g == 0 && tt == 0) ? 0u : 1u);
+                        const uint32_t bb = bg + (uint32_t)tt * B_STAGE16;                         // rows 0..NT-1 = bh, NT..2NT-1 = bl
+                        // ah * [bh | bl] -> [main | cross] in ONE N = 2*NT instruction (the hi activations are read once for
+                        // both products), then al * bh into the cross columns
+                        if constexpr (MERGED) {
+                            mma_f16_ss(leader, d_set, ah, bb, DESC_HI, IDESC2, (g == 0 && tt == 0) ? 0u : 1u);
+                            mma_f16_ss(leader, d_set + NT, al, bb, DESC_HI, IDESC, 1u);
+                        } else {
+                            const uint32_t first = c == 0 ? 0u : 1u;
+                            mma_f16_ss(leader, d_cross, al, bb, DESC_HI, IDESC, (g == 0 && tt == 0) ? first : 1u);
+                            mma_f16_ss(leader, d_cross, ah, bb + B_LO16, DESC_HI, IDESC, 1u);
+                            mma_f16_ss(leader, tmem_base + set * NT, ah, bb, DESC_HI, IDESC, (g == 0 && tt == 0) ? 0u : 1u);
+                        }
                     }
                     mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sbq));
                     if (++sbq == NBS) { sbq = 0; b_par ^= 1u; }
@@ -383,7 +411,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                 ++seg;
                 if (++slot == (uint32_t)NA) { slot = 0; a_par ^= 1u; }
             }
-            mma_commit(leader, bar_base + 8u * (BAR_XDONE + xset));
+            if (!MERGED) mma_commit(leader, bar_base + 8u * (BAR_XDONE + xset));
         }
         __syncwarp();
     }

@@ -353,7 +353,8 @@ def conv_layer_tc(geom, x, w_tc, bias, out, n, Cin, Cout, D, H, W, kd, kh, kw, r
 
 def conv_sd_weights(Wt: torch.Tensor) -> torch.Tensor:
     """[T, Cin, Cout] folded fp32 weights (T = 9: 3x3, or 27: 3x3x3 with Cin = 16) -> the fp16 operand image of
-    ``bx_conv_layer_sd``: [chunk][tap(9)][split(hi,lo)][kcore(2)][n(NT)][8], w = hi + lo * 2^-11."""
+    ``bx_conv_layer_sd``: [chunk][tap(9)][kcore(2)][split(hi,lo)][n(NT)][8], w = hi + lo * 2^-11 (hi and lo rows of a kcore are
+    adjacent, so [hi | lo] is one N = 2*NT operand)."""
     T, Cin, Cout = Wt.shape
     assert T in (9, 27) and Cin % 16 == 0 and Cout <= 128 and (T == 9 or Cin == 16)
     NT = 128 if Cout > 64 else (64 if Cout > 32 else 32)
@@ -367,7 +368,7 @@ def conv_sd_weights(Wt: torch.Tensor) -> torch.Tensor:
     lo = ((W - hi.float()) * 2048.0).half()
     both = torch.stack([hi, lo], dim=2)                               # [chunk, tap, split, 16, NT]
     nch = both.shape[0]
-    both = both.reshape(nch, 9, 2, 2, 8, NT).permute(0, 1, 2, 3, 5, 4).contiguous()   # [chunk, tap, split, kcore, NT, 8]
+    both = both.reshape(nch, 9, 2, 2, 8, NT).permute(0, 1, 3, 2, 5, 4).contiguous()   # [chunk, tap, kcore, split, NT, 8]
     return both.view(-1)
 
 

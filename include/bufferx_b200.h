@@ -135,7 +135,7 @@ int bx_conv_layer(int geom, const float *in, const float *w, const float *bias, 
  *                 176 rows per sample (8 x 22: one zero row + 7 elevations, 20 azimuths + 2 wrap columns),
  *                 rows = bx_conv_sd_rows(n), x = hi + lo * 2^-11.  The kernel that writes it also writes the zero rows and
  *                 wrap columns, so the next layer's operand tiles are plain cp.async.bulk copies.
- * w_sd: fp16 hi/lo weight image [chunk][tap][split][kcore][NT][8] (ops.conv_sd_weights; NT = bx_conv_tc_ntile(Cout));
+ * w_sd: fp16 hi/lo weight image [chunk][tap][kcore][split][NT][8] (ops.conv_sd_weights; NT = bx_conv_tc_ntile(Cout));
  * bias fp32 [Cout].  An activation with |x| >= 65000 cannot be split into fp16 operands -> *d_flag |= 1 (d_flag may be
  * NULL) and the caller re-runs the stack with bx_conv_layer_tc. */
 int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const void *w_sd, const float *bias, void *out, int out_presplit,

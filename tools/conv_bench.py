@@ -18,6 +18,8 @@ L = net.folded()
 dev = torch.device("cuda")
 torch.manual_seed(0)
 x = torch.relu(torch.randn(K, 4, 420, 4, device=dev))            # channel-blocked
+if MODE == "sd":     # production feeds the first layer the presplit image written by bx_spt_pnt_sd
+    x = ops.sd_pack(ops.from_blocked(x).view(K, 16, 3, 140).permute(0, 2, 1, 3).reshape(K, 48, 7, 20))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 if MODE == "sd":     # layer-to-layer activations in the presplit padded fp16 format, fp32 out of the last layer
     bufs = [ops.conv_sd_buffer(K, l["cout"], dev) if i < len(L) - 1 else torch.empty((K, l["cout"] // 4, 140, 4), device=dev) for i, l in enumerate(L)]
