@@ -56,6 +56,8 @@ struct ConvSdParams {
     float *out;
     int *flag;
     int n, Cout, nchunks, is3d, S_in, G_in, relu, n_tiles, NA, dbg;
+    const int *d_n;            // optional device-side sample count (<= n): the match lists of the cost-volume stack
+    int cyl, rs, W, OD, OW, S_out, rs_out;   // raster geometry: rows per sample, row stride, valid output extent, output rasters
     const __half *in_sd;       // IN_SD: presplit padded input  [nchunks][split,kcore (4)][rows_in][8 x fp16]
     __half *out_sd;            // OUT_SD: presplit padded output [Cout/16][4][rows_out][8 x fp16] = the next layer's in_sd
     long long rows_in, rows_out;
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NA = p.NA, nchunks = p.nchunks;
+    const int n_samples = p.d_n ? min(*p.d_n, p.n) : p.n;
+    const int n_tiles = (int)(((long long)n_samples * p.rs + SD_BM - 1) / SD_BM);   // <= the host's bound the grid was sized for
     const int n_stages = nchunks * 9;
     const int nseg = nchunks;                    // one accumulator segment per 16-channel chunk (nine main MMAs, K = 144)
 
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
         const uint32_t tm_lane = (uint32_t)(quarter * 32) << 16;
         float run[CW];
         int seg = 0, k = 0;
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++k) {
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
 #pragma unroll
             for (int c = 0; c < CW; ++c) run[c] = 0.0f;
             for (int jj = 0; jj < nseg; ++jj, ++seg) {
@@ -189,15 +193,18 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                 if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_XFREE + xset));
             }
             const long long R = (long long)t * SD_BM + quarter * 32 + lane;
-            const int s = (int)(R / SD_SROWS), q = (int)(R - (long long)s * SD_SROWS);
-            const int y = q / 22, x = q - y * 22;
-            const bool valid = s < p.n && y < 7 && x < 20;
-            float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)s * (p.Cout >> 2) + ((ecs * CW) >> 2)) * 140 + (y * 20 + x);
+            const int s = (int)(R / p.rs), q = (int)(R - (long long)s * p.rs);
+            const int y = q / p.W, x = q - y * p.W;
+            const bool valid = s < n_samples && y < p.OD && x < p.OW;
+            const int S_out = p.S_out;
+            float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)s * (p.Cout >> 2) + ((ecs * CW) >> 2)) * S_out + (y * p.OW + x);
             // OUT_SD: this row's value goes to padded row R + 23 (= (y + 1) * 22 + (x + 1)); azimuth 19 / 0 are duplicated into the
             // wrap columns x' = 0 / 21; the rows that land on a zero row write zeros; everything else is dropped.
-            const bool live = s < p.n;
-            const bool wz = live && ((y == 7 && x <= 20) || (y == 6 && x == 21));       // zero row of sample s + 1
-            const long long pmain = R + 23, pdup = x == 19 ? R + 3 : (x == 0 ? R + 43 : -1);
+            // (valid-convolution rasters of the cost-volume stack: compact output raster, no padding rows / columns)
+            const bool live = s < n_samples;
+            const bool wz = p.cyl && live && ((y == 7 && x <= 20) || (y == 6 && x == 21));       // zero row of sample s + 1
+            const long long pmain = p.cyl ? R + 23 : (long long)s * p.rs_out + y * p.OW + x;
+            const long long pdup = !p.cyl ? -1 : (x == 19 ? R + 3 : (x == 0 ? R + 43 : -1));
             float omax = 0.0f;
 #pragma unroll
             for (int c0 = 0; c0 < CW; c0 += 32) {
@@ -213,8 +220,8 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                                 if (p.relu) r[e] = fmaxf(r[e], 0.0f);
                             }
                             if (!OUT_SD) {
-                                eo[(size_t)((c0 + c) >> 2) * 140] = make_float4(r[0], r[1], r[2], r[3]);
-                                eo[(size_t)((c0 + c + 4) >> 2) * 140] = make_float4(r[4], r[5], r[6], r[7]);
+                                eo[(size_t)((c0 + c) >> 2) * S_out] = make_float4(r[0], r[1], r[2], r[3]);
+                                eo[(size_t)((c0 + c + 4) >> 2) * S_out] = make_float4(r[4], r[5], r[6], r[7]);
                             } else {
                                 uint32_t hi[4], lo[4];
 #pragma unroll
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                                 const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                                 if (valid || wz) { img[pmain] = vh; img[2 * p.rows_out + pmain] = vl; }
                                 if (valid && pdup >= 0) { img[pdup] = vh; img[2 * p.rows_out + pdup] = vl; }
-                                if (R < 22) { const uint4 z = make_uint4(0u, 0u, 0u, 0u); img[R] = z; img[2 * p.rows_out + R] = z; }   // zero row of sample 0
+                                if (p.cyl && R < 22) { const uint4 z = make_uint4(0u, 0u, 0u, 0u); img[R] = z; img[2 * p.rows_out + R] = z; }   // zero row of sample 0
                             }
                         }
                     }
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
             // thread keeps NA chunks in flight; no register staging, no conversion.
             if (warp == NE && lane == 0) {
                 uint32_t slot = 0, par = 0, round = 0;
-                for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+                for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
                     for (int c = 0; c < nchunks; ++c) {
                         if (round) mbar_wait(bar_base + 8u * (BAR_AEMPTY + slot), par ^ 1u);
                         mbar_arrive_expect_tx(bar_base + 8u * (BAR_AFULL + slot), (uint32_t)SD_CHUNK);
@@ -281,11 +288,11 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                     if (idx < 2 * SD_AROWS) {
                         const int h = idx >= SD_AROWS ? 1 : 0, r = idx - h * SD_AROWS;
                         const long long pr = p0 + r;
-                        const int s = (int)(pr / SD_SROWS), q = (int)(pr - (long long)s * SD_SROWS);
+                        const int s = (int)(pr / p.rs), q = (int)(pr - (long long)s * p.rs);
                         const int yp = q / 22, xp = q - yp * 22;
-                        if (s < p.n && yp != 0 && !p.dbg) {
+                        if (s < n_samples && (yp != 0 || !p.cyl) && !p.dbg) {
                             const int xx = xp == 0 ? 19 : (xp == 21 ? 0 : xp - 1);
-                            int pos = (yp - 1) * 20 + xx, g0;
+                            int pos = p.cyl ? (yp - 1) * 20 + xx : q, g0;       // valid rasters: the row IS the input position
                             if (p.is3d) { pos += c * 140; g0 = h * 2; } else { g0 = c * 4 + h * 2; }
                             const float4 *src = in4 + ((size_t)s * p.G_in + g0) * p.S_in + pos;
                             v[m][0] = __ldg(src);
@@ -296,12 +303,12 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
             };
             int j = 0;
             int t = blockIdx.x, c = 0;
-            if (t < p.n_tiles) issue(t, 0, cur);
-            while (t < p.n_tiles) {
+            if (t < n_tiles) issue(t, 0, cur);
+            while (t < n_tiles) {
                 // position of the chunk after this one
                 int tn = t, cn = c + 1;
                 if (cn == nchunks) { cn = 0; tn = t + gridDim.x; }
-                if (tn < p.n_tiles) issue(tn, cn, nxt);
+                if (tn < n_tiles) issue(tn, cn, nxt);
                 const int slot = j % NA;
                 if (j >= NA) mbar_wait(bar_base + 8u * (BAR_AEMPTY + slot), (uint32_t)(((j / NA) - 1) & 1));
                 unsigned char *dst = smem + (size_t)slot * SD_CHUNK;
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
         if (lane == 0) {
             const int n_super = n_stages / SB;
             int q = 0;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
                 for (int ss = 0; ss < n_super; ++ss, ++q) {
                     const int sb = q % NBS;
                     const uint32_t useb = (uint32_t)(q / NBS);
@@ -367,8 +374,9 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
         constexpr uint32_t B_STAGE16 = (uint32_t)B_STAGE >> 4, A_CHUNK16 = (uint32_t)SD_CHUNK >> 4;
         const uint32_t leader = elect_leader();
         const uint32_t a0 = (a_base >> 4) | A_LBO, b0 = (b_base >> 4) | B_LBO;
+        const int Wrow = p.W;                                              // tap (g, tt) reads rows R + g * W + tt
         uint32_t slot = 0, a_par = 0, sbq = 0, b_par = 0, seg = 0, k = 0;
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++k) {
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
             const uint32_t xset = k & 1;
             if (!MERGED && k >= 2) {
                 mbar_wait(bar_base + 8u * (BAR_XFREE + xset), ((k >> 1) - 1) & 1);
@@ -389,7 +397,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                     const uint32_t bg = b0 + sbq * (3u * B_STAGE16);
 #pragma unroll
                     for (int tt = 0; tt < 3; ++tt) {
-                        const uint32_t ah = ac + (uint32_t)(g * 22 + tt), al = ah + A_SPLIT;      // one row = 16 B = one address unit
+                        const uint32_t ah = ac + (uint32_t)(g * Wrow + tt), al = ah + A_SPLIT;    // one row = 16 B = one address unit
                         const uint32_t bb = bg + (uint32_t)tt * B_STAGE16;                         // rows 0..NT-1 = bh, NT..2NT-1 = bl
                         // ah * [bh | bl] -> [main | cross] in ONE N = 2*NT instruction (the hi activations are read once for
                         // both products), then al * bh into the cross columns
@@ -450,38 +458,48 @@ int dispatch_sd(const ConvSdParams &p, int in_sd, int out_sd, cudaStream_t st) {
 
 }  // namespace
 
-// rows of a presplit padded activation image for n samples: whole 128-row tiles of the 176-row-per-sample raster + halo
-BX_API long long bx_conv_sd_rows(int n) {
-    const long long rows = (long long)n * SD_SROWS;
+// rows of a presplit activation image: n samples of rows_per_sample raster rows (176 for the cylindrical layers: 8 x 22),
+// rounded to whole 128-row tiles, + the 48-row halo a tile's operand fetch reaches past its last row
+BX_API long long bx_conv_sd_rows(int n, int rows_per_sample) {
+    const long long rows = (long long)n * rows_per_sample;
     return (rows + SD_BM - 1) / SD_BM * SD_BM + (SD_AROWS - SD_BM);
 }
 
 BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const void *w_sd, const float *bias, void *out, int out_presplit,
-                            int n, int Cin, int Cout, int relu, int32_t *d_flag, void *stream) {
+                            int n, const int32_t *d_n, int Cin, int Cout, int D, int W, int relu, int32_t *d_flag, void *stream) {
     BX_REQUIRE(in && w_sd && bias && out, "bx_conv_layer_sd: null pointer");
-    BX_REQUIRE(geom == BX_GEOM_CYL3D || geom == BX_GEOM_CYL2D, "bx_conv_layer_sd: only the cylindrical geometries (CYL3D / CYL2D)");
+    BX_REQUIRE(geom == BX_GEOM_CYL3D || geom == BX_GEOM_CYL2D || geom == BX_GEOM_VALID3D, "bx_conv_layer_sd: geometry must be CYL3D, CYL2D or VALID3D (k = 3x1x3)");
     BX_REQUIRE(n >= 0 && Cin >= 16 && Cin % 16 == 0 && Cout >= 4 && Cout % 4 == 0 && Cout <= 128, "bx_conv_layer_sd: bad channels Cin=%d Cout=%d", Cin, Cout);
     BX_REQUIRE(geom != BX_GEOM_CYL3D || Cin == 16, "bx_conv_layer_sd: CYL3D expects 16 input channels x 3 radial slices");
+    BX_REQUIRE(geom != BX_GEOM_VALID3D || (D >= 3 && W >= 3 && 2 * W + 2 <= SD_AROWS - SD_BM), "bx_conv_layer_sd: VALID3D raster %d x %d out of range (W <= 23)", D, W);
     BX_REQUIRE(!out_presplit || Cout % 16 == 0, "bx_conv_layer_sd: presplit output needs Cout %% 16 == 0");
     BX_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(w_sd)) & 15) == 0,
                "bx_conv_layer_sd: activations, weights and bias must be 16-byte aligned");
     if (n == 0) return BX_OK;
     ConvSdParams p = {};
-    p.w = reinterpret_cast<const __half *>(w_sd); p.bias = bias; p.flag = d_flag;
+    p.w = reinterpret_cast<const __half *>(w_sd); p.bias = bias; p.flag = d_flag; p.d_n = d_n;
     p.in = in_presplit ? nullptr : reinterpret_cast<const float *>(in);
     p.in_sd = in_presplit ? reinterpret_cast<const __half *>(in) : nullptr;
     p.out = out_presplit ? nullptr : reinterpret_cast<float *>(out);
     p.out_sd = out_presplit ? reinterpret_cast<__half *>(out) : nullptr;
     p.n = n; p.Cout = Cout; p.relu = relu;
     p.is3d = geom == BX_GEOM_CYL3D;
+    p.cyl = geom != BX_GEOM_VALID3D;
     p.nchunks = p.is3d ? 3 : Cin / 16;
-    p.S_in = p.is3d ? 420 : 140;
     p.G_in = Cin / 4;
+    if (p.cyl) {
+        p.rs = SD_SROWS; p.W = 22; p.OD = 7; p.OW = 20; p.S_out = 140; p.rs_out = SD_SROWS;
+        p.S_in = p.is3d ? 420 : 140;
+    } else {        // valid k = (3,1,3) convolution over a D x W raster (CostNet layers, models/patchnet.py:151-210)
+        p.rs = D * W; p.W = W; p.OD = D - 2; p.OW = W - 2; p.S_out = p.OD * p.OW; p.rs_out = p.S_out;
+        p.S_in = D * W;
+    }
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("BX_SD_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
-    const long long rows = (long long)n * SD_SROWS;
+    const long long rows = (long long)n * p.rs;
     BX_REQUIRE(rows / SD_BM < 0x7fffffffLL, "bx_conv_layer_sd: too many samples");
     p.n_tiles = (int)((rows + SD_BM - 1) / SD_BM);
-    p.rows_in = p.rows_out = bx_conv_sd_rows(n);
+    p.rows_in = bx_conv_sd_rows(n, p.rs);
+    p.rows_out = bx_conv_sd_rows(n, p.rs_out);
     cudaStream_t st = bx_stream(stream);
     if (Cout > 64) return dispatch_sd<128, 2>(p, in_presplit, out_presplit, st);
     if (Cout > 32) return dispatch_sd<64, 2>(p, in_presplit, out_presplit, st);

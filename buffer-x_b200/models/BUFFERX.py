@@ -183,6 +183,7 @@ class BufferX(nn.Module):
         self.Desc = MiniSpinNet(config)
         self.Pose = CostVolume(config)
         self.equi_match = EquiMatch(config)
+        self.Pose.conv.flag_source = self.Desc.conv_net.overflow_flag      # one sticky fp16-range flag per model
         if config.stage == "test":
             self.pose_estimator = PoseEstimator(config)
         self._use_graphs = False
@@ -448,8 +449,9 @@ class BufferX(nn.Module):
         model runs on the TF32 kernel (bx_conv_tc.cu): drop the captured graphs, clear the flag, recompute this pair."""
         net = self.Desc.conv_net
         if not net.force_tf32:
-            print("bufferx_b200: activation outside fp16 range -- descriptor stack switched to the TF32 tensor-core kernel")
+            print("bufferx_b200: activation outside fp16 range -- convolution stacks switched to the TF32 tensor-core kernel")
         net.force_tf32 = True
+        self.Pose.conv.force_tf32 = True
         self._drop_captured_state()
         net.overflow_flag(next(self.parameters()).device).zero_()
         return self.forward(data_source, perms=perms, ransac_seed=ransac_seed, debug=debug)

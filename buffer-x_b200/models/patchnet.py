@@ -63,7 +63,7 @@ class _ConvStack(nn.Module):
                 self.ops.append(nn.ReLU(inplace=True))
             self.layers.append((ci, bi, relu))
         self._folded = None
-        self.use_sd = False          # Cylindrical_Net: also build the fp16-split images of bx_conv_layer_sd
+        self.sd_kernel_sizes = ()    # kernel sizes whose layers also get the fp16-split weight image of bx_conv_layer_sd
 
     def invalidate(self):
         self._folded = None
@@ -89,7 +89,7 @@ class _ConvStack(nn.Module):
                                      eps=1e-5 if bn is None else bn.eps)
                 ks = tuple(conv.kernel_size)
                 kk = ks if len(ks) == 3 else (1,) + ks
-                sd_ok = Wt.is_cuda and self.use_sd and kk in ((1, 3, 3), (3, 3, 3)) and conv.in_channels % 16 == 0
+                sd_ok = Wt.is_cuda and kk in self.sd_kernel_sizes and conv.in_channels % 16 == 0 and conv.out_channels % 16 == 0
                 out.append(dict(w=Wt, w_tc=ops.conv_tc_weights(Wt) if Wt.is_cuda else None, w_sd=ops.conv_sd_weights(Wt) if sd_ok else None,
                                 b=b, cin=conv.in_channels, cout=conv.out_channels, k=kk, relu=relu))
             self._folded = out
@@ -105,7 +105,7 @@ class Cylindrical_Net(_ConvStack):
                 (64, 32, (3, 3), True, True), (32, dim, (3, 3), False, False)]
         super().__init__(spec)
         self.out_dim = dim
-        self.use_sd = True
+        self.sd_kernel_sizes = ((1, 3, 3), (3, 3, 3))
         self.force_tf32 = USE_TF32_DESC      # set (sticky) by BufferX when the fp16-range flag fired once
         self._flag = None
 
@@ -152,17 +152,32 @@ class CostNet(_ConvStack):
                 (32, dim, (2, 1, 2), False, False)]
         super().__init__(spec)
         self.out_dim = dim
+        self.sd_kernel_sizes = ((3, 1, 3),)
+        self.force_tf32 = USE_TF32_DESC
+        self.flag_source = None          # set by BufferX: the descriptor stack's overflow_flag (one sticky flag per model)
 
     def forward_matches(self, equi_s, equi_t, s_mids, t_mids, d_M, maxM):
-        """equi_* [K,32,7,20]; match lists + device count -> logits [maxM, dim] (rows >= *d_M undefined)."""
+        """equi_* [K,32,7,20]; match lists + device count -> logits [maxM, dim] (rows >= *d_M undefined).
+        The k = (3,1,3) layers with Cout >= 32 run on the shifted-descriptor fp16-split kernel (bx_conv_layer_sd, valid
+        rasters, presplit activations between them); the factorised first layers and the 2x1x2 head on bx_conv_layer_tc."""
         dev = equi_s.device
         L = self.folded()
         D, H, W = 20, 5, 20
         cur = None
         factored = (not USE_FFMA) and not DIRECT_COSTVOL
+        use_sd = not USE_FFMA and not self.force_tf32
+        flag = self.flag_source(dev) if (use_sd and self.flag_source is not None) else None
         for i, l in enumerate(L):
             kd, kh, kw = l["k"]
             OD, OH, OW = D - kd + 1, H - kh + 1, W - kw + 1
+            if use_sd and l.get("w_sd") is not None and H == 1 and cur is not None:
+                nxt = L[i + 1] if i + 1 < len(L) else None
+                nxt_sd = nxt is not None and nxt.get("w_sd") is not None
+                out = (ops.conv_sd_buffer(maxM, l["cout"], dev, OD * OW) if nxt_sd
+                       else torch.empty((maxM, l["cout"] // 4, OD * OW, 4), dtype=torch.float32, device=dev))
+                ops.conv_layer_sd(ops.GEOM_VALID3D, cur, l["w_sd"], l["b"], out, maxM, l["cin"], l["cout"], l["relu"], flag, d_n=d_M, D=D, W=W)
+                cur, D, H, W = out, OD, OH, OW
+                continue
             conv, w = (ops.conv_layer, l["w"]) if USE_FFMA else (ops.conv_layer_tc, l["w_tc"])
             if factored and i == 0:
                 # first layer is linear in the cost volume before its ReLU: two small convolutions of the equivariant

@@ -64,8 +64,8 @@ def load_library():
     lib.bx_conv_layer.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_layer_tc.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_tc_ntile.argtypes = [c_int]
-    lib.bx_conv_layer_sd.argtypes = [c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]
-    lib.bx_conv_sd_rows.argtypes = [c_int]
+    lib.bx_conv_layer_sd.argtypes = [c_int, P, c_int, P, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P]
+    lib.bx_conv_sd_rows.argtypes = [c_int, c_int]
     lib.bx_fps_set_sync_mode.argtypes = [c_int]
     lib.bx_spt_pnt_sd.argtypes = [P, c_int, c_int, P, c_int, c_int, P, c_float, c_int, P, P, P, c_int64, P, P]
     lib.bx_conv_sd_rows.restype = c_int64
@@ -372,29 +372,31 @@ def conv_sd_weights(Wt: torch.Tensor) -> torch.Tensor:
     return both.view(-1)
 
 
-def conv_sd_rows(n: int) -> int:
-    """Rows of a presplit padded activation image for n samples (176 per sample, whole 128-row tiles + 48 halo rows)."""
-    return int(load_library().bx_conv_sd_rows(int(n)))
+def conv_sd_rows(n: int, rows_per_sample: int = 176) -> int:
+    """Rows of a presplit activation image for n samples (cylindrical layers: 176 per sample; whole 128-row tiles + 48 halo rows)."""
+    return int(load_library().bx_conv_sd_rows(int(n), int(rows_per_sample)))
 
 
-def conv_sd_buffer(n: int, C: int, device):
+def conv_sd_buffer(n: int, C: int, device, rows_per_sample: int = 176):
     """Uninitialised presplit activation image [C/16, 4, rows, 8] fp16 (the producing kernel writes every row that is read
     into a kept result)."""
-    return torch.empty((C // 16, 4, conv_sd_rows(n), 8), dtype=torch.float16, device=device)
+    return torch.empty((C // 16, 4, conv_sd_rows(n, rows_per_sample), 8), dtype=torch.float16, device=device)
 
 
-def conv_layer_sd(geom, x, w_sd, bias, out, n, Cin, Cout, relu, flag=None):
+def conv_layer_sd(geom, x, w_sd, bias, out, n, Cin, Cout, relu, flag=None, d_n=None, D=0, W=0):
     """x: fp32 channel-blocked [n, Cin/4, S_in, 4] or presplit fp16 [Cin/16, 4, rows, 8]; out likewise (dtype decides);
-    ``flag``: int32[1] fp16-range flag (sticky)."""
+    ``flag``: int32[1] fp16-range flag (sticky); ``d_n``: device-side sample count; D, W: input raster of GEOM_VALID3D."""
     ev = None
     if profiler is not None:
-        taps = 27 if geom == GEOM_CYL3D else 9
-        ev = profiler.span("conv_desc", 2.0 * n * 140 * Cout * Cin * taps)
+        if geom == GEOM_VALID3D:
+            ev = profiler.span("conv_cost", 0.0)
+        else:
+            ev = profiler.span("conv_desc", 2.0 * n * 140 * Cout * Cin * (27 if geom == GEOM_CYL3D else 9))
         ev[0].record()
     in_sd, out_sd = x.dtype == torch.float16, out.dtype == torch.float16
     _check(load_library().bx_conv_layer_sd(geom, _dp(x, None, "x"), int(in_sd), _dp(w_sd, torch.float16, "w_sd"), _dp(bias, F32, "bias"),
-                                           _dp(out, None, "out"), int(out_sd), int(n), Cin, Cout, int(bool(relu)), _dp(flag, I32, "flag"), _stream()),
-           "bx_conv_layer_sd")
+                                           _dp(out, None, "out"), int(out_sd), int(n), _dp(d_n, I32, "d_n"), Cin, Cout, int(D), int(W), int(bool(relu)),
+                                           _dp(flag, I32, "flag"), _stream()), "bx_conv_layer_sd")
     if ev:
         ev[1].record()
     return out

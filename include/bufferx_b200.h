@@ -103,7 +103,7 @@ int bx_spt_pnt(const float *delta, int K, int P, const float *voxels, int V, int
                float voxel_r, int nv, const float *w, const float *b, float *feat, int32_t *dbg_vidx,
                float *dbg_inv, void *stream);
 /* Same computation; the features are written in the presplit padded fp16 format that bx_conv_layer_sd reads with bulk
- * copies: feat_sd [3 (radial slice = 16-channel chunk)][4 (split, kcore)][rows][8 x fp16], rows = bx_conv_sd_rows(K),
+ * copies: feat_sd [3 (radial slice = 16-channel chunk)][4 (split, kcore)][rows][8 x fp16], rows = bx_conv_sd_rows(K, 176),
  * zero rows and wrap columns included; V must be 3*7*20.  *d_flag |= 1 if a feature is outside fp16 range. */
 int bx_spt_pnt_sd(const float *delta, int K, int P, const float *voxels, int V, int azi_n, const float *rot,
                   float voxel_r, int nv, const float *w, const float *b, void *feat_sd, long long rows, int32_t *d_flag,
@@ -126,21 +126,24 @@ int bx_conv_layer(int geom, const float *in, const float *w, const float *bias, 
                   const float *equi_s, const float *equi_t, const int32_t *s_mids, const int32_t *t_mids,
                   void *stream);
 
-/* ---- a8 (descriptor stack): shifted-descriptor implicit GEMM, fp16-split operands -----------------------------
- * The production kernel of the eight Cylindrical_Net layers (models/patchnet.py:16-84; padding utils/common.py:265-310).
- * geom = BX_GEOM_CYL3D (16 channels x 3 radial slices, k=3x3x3; fp32 input only) or BX_GEOM_CYL2D (k=3x3).
+/* ---- a8 / a11: shifted-descriptor implicit GEMM, fp16-split operands ------------------------------------------
+ * The production kernel of the eight Cylindrical_Net layers (models/patchnet.py:16-84; padding utils/common.py:265-310)
+ * and of the k = (3,1,3) layers of CostNet (models/patchnet.py:151-210).
+ * geom = BX_GEOM_CYL3D (16 channels x 3 radial slices, k=3x3x3), BX_GEOM_CYL2D (k=3x3; circular azimuth / zero elevation
+ * padding) or BX_GEOM_VALID3D (un-padded k=3x1x3 over a D x W raster, D and W given; output (D-2) x (W-2)).
  * Activations come in two formats, chosen per side:
- *   presplit = 0  fp32 channel-blocked: in [n,Cin/4,S_in,4] (S_in = 140, or 3*140 for CYL3D), out [n,Cout/4,140,4];
- *   presplit = 1  the layer-to-layer format: fp16 images [C/16][split(hi,lo)][kcore(2)][rows][8] over the padded raster of
- *                 176 rows per sample (8 x 22: one zero row + 7 elevations, 20 azimuths + 2 wrap columns),
- *                 rows = bx_conv_sd_rows(n), x = hi + lo * 2^-11.  The kernel that writes it also writes the zero rows and
- *                 wrap columns, so the next layer's operand tiles are plain cp.async.bulk copies.
+ *   presplit = 0  fp32 channel-blocked: in [n,Cin/4,S_in,4], out [n,Cout/4,S_out,4];
+ *   presplit = 1  the layer-to-layer format: fp16 images [C/16][split(hi,lo)][kcore(2)][rows][8], x = hi + lo * 2^-11, over
+ *                 the GEMM row raster (cylindrical: 176 rows per sample = 8 x 22, one zero row + 7 elevations, 20 azimuths +
+ *                 2 wrap columns, written by the producing kernel; valid: D*W rows per sample), rows =
+ *                 bx_conv_sd_rows(n, rows per sample).  The consumer's operand tiles are plain cp.async.bulk copies.
+ * n = sample capacity; *d_n (optional, device) = the number of samples actually present (match count).
  * w_sd: fp16 hi/lo weight image [chunk][tap][kcore][split][NT][8] (ops.conv_sd_weights; NT = bx_conv_tc_ntile(Cout));
  * bias fp32 [Cout].  An activation with |x| >= 65000 cannot be split into fp16 operands -> *d_flag |= 1 (d_flag may be
  * NULL) and the caller re-runs the stack with bx_conv_layer_tc. */
 int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const void *w_sd, const float *bias, void *out, int out_presplit,
-                     int n, int Cin, int Cout, int relu, int32_t *d_flag, void *stream);
-long long bx_conv_sd_rows(int n);
+                     int n, const int32_t *d_n, int Cin, int Cout, int D, int W, int relu, int32_t *d_flag, void *stream);
+long long bx_conv_sd_rows(int n, int rows_per_sample);
 
 /* Tensor-core variant (tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulators in TMEM; same geometry
  * arguments).  Activations are CHANNEL-BLOCKED here: in [n][Cin/4][S_in][4], out [n][Cout/4][S_out][4] (a GEMM row

@@ -663,8 +663,8 @@ def _torch_layer(geom, x, W, b, relu, kd, kh, kw):
 def test_conv_layer_kernels(dev, geom, Cin, Cout, dims, k, n, impl):
     from bufferx_b200 import ops
     from bufferx_b200.models.patchnet import fold_conv_bn
-    if impl == "sd" and geom == "valid3d":
-        pytest.skip("the shifted-descriptor kernel serves the cylindrical (descriptor) layers only")
+    if impl == "sd" and geom == "valid3d" and (k != (3, 1, 3) or Cout % 16):
+        pytest.skip("of the un-padded geometries the shifted-descriptor kernel serves the k = (3,1,3) layers")
     g = torch.Generator().manual_seed(Cin * 1000 + Cout + n)
     D, H, W_ = dims
     kd, kh, kw = k
@@ -686,7 +686,9 @@ def test_conv_layer_kernels(dev, geom, Cin, Cout, dims, k, n, impl):
     if impl == "sd":                                                  # shifted-descriptor fp16-split kernel (production)
         out_cb = torch.full((n, Cout // 4, OD * OH * OW, 4), float("nan"), device=dev)
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        ops.conv_layer_sd(G, ops.to_blocked(xin), ops.conv_sd_weights(Wt.to(dev)), bf.to(dev), out_cb, n, Cin, Cout, relu, flag)
+        d_n = torch.tensor([n], dtype=torch.int32, device=dev) if geom == "valid3d" else None
+        ops.conv_layer_sd(G, ops.to_blocked(xin), ops.conv_sd_weights(Wt.to(dev)), bf.to(dev), out_cb, n + (3 if geom == "valid3d" else 0), Cin, Cout, relu,
+                          flag, d_n=d_n, D=D, W=W_)
         out = ops.from_blocked(out_cb)
         assert int(flag.item()) == 0
     elif impl == "tc":                                                # tensor-core kernel: channel-blocked activations
@@ -761,6 +763,33 @@ def test_conv_sd_presplit_formats(dev, Cin, Cout, n):
     o2 = torch.full((n, Cin // 4, 140, 4), float("nan"), device=dev)
     ops.conv_layer_sd(ops.GEOM_CYL2D, img, wt(W2), b2.to(dev), o2, n, Cout, Cin, False)
     assert rel(ops.from_blocked(o2).view(n, Cin, 7, 20), y2) < 3e-5
+
+
+def test_conv_sd_valid_raster_chain(dev):
+    """CostNet's k = (3,1,3) layers on the shifted-descriptor kernel: un-padded D x W rasters, a device-side sample count
+    below the capacity, presplit activations between the layers (16x16 -> 14x14 -> 12x12)."""
+    from bufferx_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    n, cap = 37, 50
+    x = torch.randn((n, 64, 16, 1, 16), generator=g)
+    W1 = torch.randn((64, 64, 3, 1, 3), generator=g) / (64 * 9) ** 0.5
+    W2 = torch.randn((128, 64, 3, 1, 3), generator=g) / (64 * 9) ** 0.5
+    b1, b2 = torch.randn(64, generator=g) * 0.1, torch.randn(128, generator=g) * 0.1
+    y1 = F.relu(F.conv3d(x, W1, b1))
+    y2 = F.relu(F.conv3d(y1, W2, b2))
+    wt = lambda W: ops.conv_sd_weights(W.reshape(W.shape[0], W.shape[1], 9).permute(2, 1, 0).contiguous().to(dev))
+    d_n = torch.tensor([n], dtype=torch.int32, device=dev)
+    xin = torch.zeros((cap, 16, 256, 4), device=dev)
+    xin[:n] = ops.to_blocked(x.to(dev).reshape(n, 64, 256))
+    mid = ops.conv_sd_buffer(cap, 64, dev, 14 * 14)
+    mid.fill_(float("nan"))
+    ops.conv_layer_sd(ops.GEOM_VALID3D, xin, wt(W1), b1.to(dev), mid, cap, 64, 64, True, None, d_n=d_n, D=16, W=16)
+    out = torch.full((cap, 32, 144, 4), float("nan"), device=dev)
+    ops.conv_layer_sd(ops.GEOM_VALID3D, mid, wt(W2), b2.to(dev), out, cap, 64, 128, True, None, d_n=d_n, D=14, W=14)
+    got = ops.from_blocked(out[:n]).view(n, 128, 12, 1, 12).cpu()
+    assert float((got - y2).abs().max() / y2.abs().max()) < 3e-5
+    assert torch.isnan(out[n:]).all()                 # samples beyond the device-side count are not touched
 
 
 def test_conv_sd_fp16_range_flag_and_fallback(dev):
