@@ -83,6 +83,67 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t leader, uint32_t tmem_d, uin
         : "memory");
 }
 
+// One epilogue thread's share of a finished tile: GEMM row R = t * 128 + 32 * quarter + lane, CW consecutive output channels
+// starting at ecs * CW: bias (+ReLU), then either fp32 channel-blocked stores of the valid rows or the presplit images of the
+// next layer (value, wrap-column copies, zero rows).
+template <int CW, int OUT_SD>
+__device__ __forceinline__ void sd_store_tile(const ConvSdParams &p, int t, int quarter, int ecs, int lane, int n_samples, const float (&run)[CW]) {
+    const long long R = (long long)t * SD_BM + quarter * 32 + lane;
+    const int s = (int)(R / p.rs), q = (int)(R - (long long)s * p.rs);
+    const int y = q / p.W, x = q - y * p.W;
+    const bool valid = s < n_samples && y < p.OD && x < p.OW;
+    const int S_out = p.S_out;
+    float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)s * (p.Cout >> 2) + ((ecs * CW) >> 2)) * S_out + (y * p.OW + x);
+    // OUT_SD: this row's value goes to padded row R + 23 (= (y + 1) * 22 + (x + 1)); azimuth 19 / 0 are duplicated into the
+    // wrap columns x' = 0 / 21; the rows that land on a zero row write zeros; everything else is dropped.
+    // (valid-convolution rasters of the cost-volume stack: compact output raster, no padding rows / columns)
+    const bool live = s < n_samples;
+    const bool wz = p.cyl && live && ((y == 7 && x <= 20) || (y == 6 && x == 21));       // zero row of sample s + 1
+    const long long pmain = p.cyl ? R + 23 : (long long)s * p.rs_out + y * p.OW + x;
+    const long long pdup = !p.cyl ? -1 : (x == 19 ? R + 3 : (x == 0 ? R + 43 : -1));
+    float omax = 0.0f;
+#pragma unroll
+    for (int c0 = 0; c0 < CW; c0 += 32) {
+        if (OUT_SD ? live : valid) {
+#pragma unroll
+            for (int c = 0; c < (CW < 32 ? CW : 32); c += 8) {
+                const int co = ecs * CW + c0 + c;
+                if (co < p.Cout) {
+                    float r[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        r[e] = run[c0 + c + e] + __ldg(p.bias + co + e);
+                        if (p.relu) r[e] = fmaxf(r[e], 0.0f);
+                    }
+                    if (!OUT_SD) {
+                        eo[(size_t)((c0 + c) >> 2) * S_out] = make_float4(r[0], r[1], r[2], r[3]);
+                        eo[(size_t)((c0 + c + 4) >> 2) * S_out] = make_float4(r[4], r[5], r[6], r[7]);
+                    } else {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float a = valid ? r[2 * e] : 0.0f, b = valid ? r[2 * e + 1] : 0.0f;
+                            const __half2 hh = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(hh);
+                            const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                            hi[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                            lo[e] = *reinterpret_cast<const uint32_t *>(&ll);
+                            omax = fmaxf(omax, fmaxf(fabsf(a), fabsf(b)));
+                        }
+                        // image (chunk = co / 16, kcore = (co / 8) & 1): [chunk][split][kcore][row][8]
+                        uint4 *img = reinterpret_cast<uint4 *>(p.out_sd) + (size_t)((co >> 4) * 4 + ((co >> 3) & 1)) * p.rows_out;
+                        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        if (valid || wz) { img[pmain] = vh; img[2 * p.rows_out + pmain] = vl; }
+                        if (valid && pdup >= 0) { img[pdup] = vh; img[2 * p.rows_out + pdup] = vl; }
+                        if (p.cyl && R < 22) { const uint4 z = make_uint4(0u, 0u, 0u, 0u); img[R] = z; img[2 * p.rows_out + R] = z; }   // zero row of sample 0
+                    }
+                }
+            }
+        }
+    }
+    if (OUT_SD && !(omax < 65000.0f) && p.flag) atomicOr(p.flag, 1);
+}
+
 // IN_SD = 0: fp32 channel-blocked input converted by the loader warps; 1: presplit padded fp16 images fetched with bulk copies.
 // OUT_SD = 0: fp32 channel-blocked output; 1: presplit padded fp16 images (zero rows and wrap columns written here).
 // MERGED (NT <= 64): per tap ah * [bh | bl] as ONE N = 2*NT instruction into [main | cross] + al * bh; both halves are cut
@@ -192,60 +253,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_XFREE + xset));
             }
-            const long long R = (long long)t * SD_BM + quarter * 32 + lane;
-            const int s = (int)(R / p.rs), q = (int)(R - (long long)s * p.rs);
-            const int y = q / p.W, x = q - y * p.W;
-            const bool valid = s < n_samples && y < p.OD && x < p.OW;
-            const int S_out = p.S_out;
-            float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)s * (p.Cout >> 2) + ((ecs * CW) >> 2)) * S_out + (y * p.OW + x);
-            // OUT_SD: this row's value goes to padded row R + 23 (= (y + 1) * 22 + (x + 1)); azimuth 19 / 0 are duplicated into the
-            // wrap columns x' = 0 / 21; the rows that land on a zero row write zeros; everything else is dropped.
-            // (valid-convolution rasters of the cost-volume stack: compact output raster, no padding rows / columns)
-            const bool live = s < n_samples;
-            const bool wz = p.cyl && live && ((y == 7 && x <= 20) || (y == 6 && x == 21));       // zero row of sample s + 1
-            const long long pmain = p.cyl ? R + 23 : (long long)s * p.rs_out + y * p.OW + x;
-            const long long pdup = !p.cyl ? -1 : (x == 19 ? R + 3 : (x == 0 ? R + 43 : -1));
-            float omax = 0.0f;
-#pragma unroll
-            for (int c0 = 0; c0 < CW; c0 += 32) {
-                if (OUT_SD ? live : valid) {
-#pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        const int co = ecs * CW + c0 + c;
-                        if (co < p.Cout) {
-                            float r[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                r[e] = run[c0 + c + e] + __ldg(p.bias + co + e);
-                                if (p.relu) r[e] = fmaxf(r[e], 0.0f);
-                            }
-                            if (!OUT_SD) {
-                                eo[(size_t)((c0 + c) >> 2) * S_out] = make_float4(r[0], r[1], r[2], r[3]);
-                                eo[(size_t)((c0 + c + 4) >> 2) * S_out] = make_float4(r[4], r[5], r[6], r[7]);
-                            } else {
-                                uint32_t hi[4], lo[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float a = valid ? r[2 * e] : 0.0f, b = valid ? r[2 * e + 1] : 0.0f;
-                                    const __half2 hh = __floats2half2_rn(a, b);
-                                    const float2 hf = __half22float2(hh);
-                                    const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
-                                    hi[e] = *reinterpret_cast<const uint32_t *>(&hh);
-                                    lo[e] = *reinterpret_cast<const uint32_t *>(&ll);
-                                    omax = fmaxf(omax, fmaxf(fabsf(a), fabsf(b)));
-                                }
-                                // image (chunk = co / 16, kcore = (co / 8) & 1): [chunk][split][kcore][row][8]
-                                uint4 *img = reinterpret_cast<uint4 *>(p.out_sd) + (size_t)((co >> 4) * 4 + ((co >> 3) & 1)) * p.rows_out;
-                                const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                                if (valid || wz) { img[pmain] = vh; img[2 * p.rows_out + pmain] = vl; }
-                                if (valid && pdup >= 0) { img[pdup] = vh; img[2 * p.rows_out + pdup] = vl; }
-                                if (p.cyl && R < 22) { const uint4 z = make_uint4(0u, 0u, 0u, 0u); img[R] = z; img[2 * p.rows_out + R] = z; }   // zero row of sample 0
-                            }
-                        }
-                    }
-                }
-            }
-            if (OUT_SD && !(omax < 65000.0f) && p.flag) atomicOr(p.flag, 1);
+            sd_store_tile<CW, OUT_SD>(p, t, quarter, ecs, lane, n_samples, run);
         }
     } else if (warp < NE + SD_NL) {
         if (IN_SD) {
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                         const long long pr = p0 + r;
                         const int s = (int)(pr / p.rs), q = (int)(pr - (long long)s * p.rs);
                         const int yp = q / 22, xp = q - yp * 22;
-                        if (s < n_samples && (yp != 0 || !p.cyl) && !p.dbg) {
+                        if (s < n_samples && (yp != 0 || !p.cyl) && !(p.dbg & 1)) {
                             const int xx = xp == 0 ? 19 : (xp == 21 ? 0 : xp - 1);
                             int pos = p.cyl ? (yp - 1) * 20 + xx : q, g0;       // valid rasters: the row IS the input position
                             if (p.is3d) { pos += c * 140; g0 = h * 2; } else { g0 = c * 4 + h * 2; }
@@ -406,8 +414,10 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                             mma_f16_ss(leader, d_set + NT, al, bb, DESC_HI, IDESC, 1u);
                         } else {
                             const uint32_t first = c == 0 ? 0u : 1u;
+                            if (!(p.dbg & 2)) {      // BX_SD_DBG=2: knock-out experiment (main products only)
                             mma_f16_ss(leader, d_cross, al, bb, DESC_HI, IDESC, (g == 0 && tt == 0) ? first : 1u);
                             mma_f16_ss(leader, d_cross, ah, bb + B_LO16, DESC_HI, IDESC, 1u);
+                            }
                             mma_f16_ss(leader, tmem_base + set * NT, ah, bb, DESC_HI, IDESC, (g == 0 && tt == 0) ? 0u : 1u);
                         }
                     }
@@ -428,6 +438,230 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Macro-tile variant (production for the descriptor stack): TWO adjacent 128-row tiles share every weight chunk.
+// Measured on conv_sd_kernel: with only a third of the MMAs issued the 128 -> 128 layer still took 72 % of its time -- the
+// kernel is bound by what an SM can pull from L2 (~43 B/clk per SM when all 148 do), and 87 % of that was the weight image,
+// re-streamed for every 128-row tile (589 KB per tile against 90 KB of activations).  Here a weight chunk (nine taps) is
+// fetched once per 256 rows: tile u = 0 runs its 27 (18) MMAs of the chunk, then tile u = 1 runs the same taps against the
+// same shared-memory weights.  The two tiles also replace the per-tile accumulator ping-pong: while tile 1's MMAs run, the
+// epilogue warps of tile 0 drain its segment, and vice versa -- one accumulator set per tile.
+// Presplit input only (bulk-copied A chunks); 8 epilogue warps per tile, one A producer, one weight producer, one MMA warp.
+template <int NT, int OUT_SD>
+__global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams p) {
+    constexpr bool MERGED = NT <= 64;
+    constexpr int NEW = 8;                        // epilogue warps per tile: 4 lane quarters x 2 column halves
+    constexpr int CW = NT / 2;
+    constexpr int LDW = CW < 32 ? CW : 32;        // columns per tcgen05.ld
+    constexpr int APROD_WARP = 2 * NEW, WGT_WARP = 2 * NEW + 1, MMA_WARP = 2 * NEW + 2;
+    constexpr int B_STAGE = 64 * NT, B_CHUNK = 9 * B_STAGE;   // nine taps of [kcore][split][n][16 B]
+    constexpr int TMEM_COLS = 4 * NT;             // MERGED: [main | cross] per tile; else main[2 tiles], cross[2 tiles]
+    constexpr int MAXNA = 12;
+    constexpr int BAR_AFULL = 0, BAR_AEMPTY = MAXNA, BAR_BFULL = 2 * MAXNA, BAR_BEMPTY = BAR_BFULL + 2;
+    constexpr int BAR_SEGDONE = BAR_BEMPTY + 2, BAR_ACCFREE = BAR_SEGDONE + 2, BAR_XDONE = BAR_ACCFREE + 2, BAR_XFREE = BAR_XDONE + 2;
+    constexpr int NBARS = BAR_XFREE + 2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bars[NBARS];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NA = p.NA, nchunks = p.nchunks;
+    const int n_samples = p.d_n ? min(*p.d_n, p.n) : p.n;
+    const int n_tiles = (int)(((long long)n_samples * p.rs + SD_BM - 1) / SD_BM);
+    const int n_macro = (n_tiles + 1) >> 1;
+
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < MAXNA; ++s) {
+            mbar_init(smem_u32(&bars[BAR_AFULL + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_AEMPTY + s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bars[BAR_BFULL + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_BEMPTY + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_SEGDONE + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_ACCFREE + s]), NEW);
+            mbar_init(smem_u32(&bars[BAR_XDONE + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_XFREE + s]), NEW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base = tmem_base_s;
+    uint32_t a_base = smem_u32(smem);
+    uint32_t b_base = a_base + (uint32_t)NA * SD_CHUNK;
+    uint32_t bar_base = smem_u32(&bars[0]);
+    asm volatile("" : "+r"(tmem_base), "+r"(a_base), "+r"(b_base), "+r"(bar_base));
+
+    if (warp < 2 * NEW) {
+        // =========================== epilogue warps of tile u ===============================================
+        const int u = warp >> 3, quarter = warp & 3, ecs = (warp >> 2) & 1;
+        const uint32_t tm_lane = (uint32_t)(quarter * 32) << 16;
+        const uint32_t d_main = tmem_base + tm_lane + (uint32_t)(MERGED ? u * 2 * NT : u * NT) + (uint32_t)(ecs * CW);
+        const uint32_t d_cross = tmem_base + tm_lane + (uint32_t)(MERGED ? u * 2 * NT + NT : 2 * NT + u * NT) + (uint32_t)(ecs * CW);
+        float run[CW];
+        uint32_t seg = 0, k = 0;
+        for (int m = blockIdx.x; m < n_macro; m += gridDim.x, ++k) {
+#pragma unroll
+            for (int c = 0; c < CW; ++c) run[c] = 0.0f;
+            for (int c = 0; c < nchunks; ++c, ++seg) {
+                mbar_wait(bar_base + 8u * (BAR_SEGDONE + u), seg & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c0 = 0; c0 < CW; c0 += LDW) {
+                    uint32_t v[LDW];
+                    if constexpr (MERGED) {
+                        uint32_t w[LDW];
+                        tmem_ld<LDW>(d_main + (uint32_t)c0, v);
+                        tmem_ld<LDW>(d_cross + (uint32_t)c0, w);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int e = 0; e < LDW; ++e) run[c0 + e] += fmaf(__uint_as_float(w[e]), 0.00048828125f, __uint_as_float(v[e]));
+                    } else {
+                        tmem_ld<LDW>(d_main + (uint32_t)c0, v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int e = 0; e < LDW; ++e) run[c0 + e] += __uint_as_float(v[e]);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_ACCFREE + u));
+            }
+            if constexpr (!MERGED) {      // the tile's cross chain: one read per tile, scaled by 2^-11
+                mbar_wait(bar_base + 8u * (BAR_XDONE + u), k & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c0 = 0; c0 < CW; c0 += LDW) {
+                    uint32_t w[LDW];
+                    tmem_ld<LDW>(d_cross + (uint32_t)c0, w);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < LDW; ++e) run[c0 + e] = fmaf(__uint_as_float(w[e]), 0.00048828125f, run[c0 + e]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_XFREE + u));
+            }
+            const int t = 2 * m + u;
+            if (t < n_tiles) sd_store_tile<CW, OUT_SD>(p, t, quarter, ecs, lane, n_samples, run);
+        }
+    } else if (warp == APROD_WARP) {
+        // =========================== A producer: chunk c of tile 0, chunk c of tile 1, chunk c + 1 of tile 0, ... ==========
+        if (lane == 0) {
+            uint32_t slot = 0, par = 0, round = 0;
+            for (int m = blockIdx.x; m < n_macro; m += gridDim.x)
+                for (int c = 0; c < nchunks; ++c)
+                    for (int u = 0; u < 2; ++u) {
+                        int t = 2 * m + u;
+                        if (t >= n_tiles) t = n_tiles - 1;       // odd tile count: the partner repeats the last tile (never stored)
+                        if (round) mbar_wait(bar_base + 8u * (BAR_AEMPTY + slot), par ^ 1u);
+                        mbar_arrive_expect_tx(bar_base + 8u * (BAR_AFULL + slot), (uint32_t)SD_CHUNK);
+                        const unsigned char *src = reinterpret_cast<const unsigned char *>(p.in_sd) + ((size_t)(c * 4) * p.rows_in + (size_t)t * SD_BM) * 16;
+#pragma unroll
+                        for (int im = 0; im < 4; ++im)
+                            bulk_g2s(a_base + slot * (uint32_t)SD_CHUNK + (uint32_t)im * SD_KCORE, src + (size_t)im * p.rows_in * 16, (uint32_t)SD_KCORE,
+                                     bar_base + 8u * (BAR_AFULL + slot));
+                        if (++slot == (uint32_t)NA) { slot = 0; par ^= 1u; round = 1; }
+                    }
+        }
+        __syncwarp();
+    } else if (warp == WGT_WARP) {
+        // =========================== weight producer: one bulk copy per chunk (nine taps), double-buffered ===============
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int m = blockIdx.x; m < n_macro; m += gridDim.x)
+                for (int c = 0; c < nchunks; ++c, ++q) {
+                    const uint32_t sb = q & 1u;
+                    if (q >= 2) mbar_wait(bar_base + 8u * (BAR_BEMPTY + sb), ((q >> 1) - 1) & 1u);
+                    mbar_arrive_expect_tx(bar_base + 8u * (BAR_BFULL + sb), (uint32_t)B_CHUNK);
+                    bulk_g2s(b_base + sb * (uint32_t)B_CHUNK, reinterpret_cast<const unsigned char *>(p.w) + (size_t)c * B_CHUNK, (uint32_t)B_CHUNK,
+                             bar_base + 8u * (BAR_BFULL + sb));
+                }
+        }
+        __syncwarp();
+    } else {
+        // =========================== MMA issuer =============================================================
+        constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+        constexpr uint32_t A_LBO = ((uint32_t)SD_KCORE >> 4) << 16;
+        constexpr uint32_t B_LBO = ((uint32_t)(2 * NT * 16) >> 4) << 16;
+        constexpr uint32_t A_SPLIT = (2u * SD_KCORE) >> 4, B_LO16 = (uint32_t)(NT * 16) >> 4;
+        constexpr uint32_t B_STAGE16 = (uint32_t)B_STAGE >> 4, B_CHUNK16 = (uint32_t)B_CHUNK >> 4, A_CHUNK16 = (uint32_t)SD_CHUNK >> 4;
+        const uint32_t leader = elect_leader();
+        const uint32_t a0 = (a_base >> 4) | A_LBO, b0 = (b_base >> 4) | B_LBO;
+        uint32_t slot = 0, a_par = 0, q = 0, seg = 0, k = 0;      // seg: segments finished per tile (same for both tiles)
+        for (int m = blockIdx.x; m < n_macro; m += gridDim.x, ++k) {
+            for (int c = 0; c < nchunks; ++c, ++q, ++seg) {
+                const uint32_t sb = q & 1u;
+                mbar_wait(bar_base + 8u * (BAR_BFULL + sb), (q >> 1) & 1u);
+                const uint32_t bg = b0 + sb * B_CHUNK16;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    mbar_wait(bar_base + 8u * (BAR_AFULL + slot), a_par);
+                    if (seg >= 1) mbar_wait(bar_base + 8u * (BAR_ACCFREE + u), (seg - 1) & 1u);
+                    if (!MERGED && c == 0 && k >= 1) mbar_wait(bar_base + 8u * (BAR_XFREE + u), (k - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t ac = a0 + slot * A_CHUNK16;
+                    const uint32_t d_set = tmem_base + (uint32_t)(MERGED ? u * 2 * NT : u * NT);
+                    const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT + u * NT);
+                    const uint32_t first = c == 0 ? 0u : 1u;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t ah = ac + (uint32_t)((tap / 3) * 22 + (tap % 3)), al = ah + A_SPLIT;
+                        const uint32_t bb = bg + (uint32_t)tap * B_STAGE16;
+                        if constexpr (MERGED) {
+                            mma_f16_ss(leader, d_set, ah, bb, DESC_HI, IDESC2, tap == 0 ? 0u : 1u);
+                            mma_f16_ss(leader, d_set + NT, al, bb, DESC_HI, IDESC, 1u);
+                        } else {
+                            mma_f16_ss(leader, d_cross, al, bb, DESC_HI, IDESC, tap == 0 ? first : 1u);
+                            mma_f16_ss(leader, d_cross, ah, bb + B_LO16, DESC_HI, IDESC, 1u);
+                            mma_f16_ss(leader, d_set, ah, bb, DESC_HI, IDESC, tap == 0 ? 0u : 1u);
+                        }
+                    }
+                    mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + u));
+                    mma_commit(leader, bar_base + 8u * (BAR_AEMPTY + slot));
+                    if (!MERGED && c == nchunks - 1) mma_commit(leader, bar_base + 8u * (BAR_XDONE + u));
+                    if (++slot == (uint32_t)NA) { slot = 0; a_par ^= 1u; }
+                }
+                mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sb));
+            }
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int NT, int OUT_SD>
+int launch_sd2(ConvSdParams p, cudaStream_t st) {
+    constexpr int B_RING = 2 * 9 * 64 * NT;
+    int na = (227 * 1024 - 1024 - B_RING) / SD_CHUNK;
+    if (na > 12) na = 12;
+    na &= ~1;                                   // chunks alternate between the two tiles
+    p.NA = na;
+    const int smem = na * SD_CHUNK + B_RING;
+    static BxPerDevice attr = {};
+    if (bx_needs_attr(attr, (size_t)smem))
+        BX_CUDA(cudaFuncSetAttribute(conv_sd2_kernel<NT, OUT_SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int sms = bx_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int n_macro = (p.n_tiles + 1) / 2;
+    const int grid = n_macro < sms ? n_macro : sms;
+    conv_sd2_kernel<NT, OUT_SD><<<grid, 19 * 32, smem, st>>>(p);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
 }
 
 template <int NT, int ECS, int IN_SD, int OUT_SD>
@@ -501,6 +735,16 @@ BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const voi
     p.rows_in = bx_conv_sd_rows(n, p.rs);
     p.rows_out = bx_conv_sd_rows(n, p.rs_out);
     cudaStream_t st = bx_stream(stream);
+    static int macro = -1;       // BX_SD_MACRO=0: one 128-row tile per weight pass everywhere (A/B switch, experiments)
+    if (macro < 0) { const char *e = getenv("BX_SD_MACRO"); macro = e ? atoi(e) : 1; }
+    // Two tiles per weight chunk (conv_sd2_kernel) where it measured faster at K = 9000 patches: Cout 128 (128->128: 1019 -> 975 us)
+    // and Cout 32 (64->32: 219 -> 189 us, 32->32: 120 -> 97 us).  Cout 64 is 8 % slower that way (its 864-cycle segments are
+    // shorter than a drain, and one accumulator set per tile then stalls the tensor core); BX_SD_MACRO=2 forces it everywhere.
+    if (macro && p.cyl && in_presplit && p.n_tiles >= 2) {
+        if (Cout > 64) return out_presplit ? launch_sd2<128, 1>(p, st) : launch_sd2<128, 0>(p, st);
+        if (Cout > 32) { if (macro >= 2) return out_presplit ? launch_sd2<64, 1>(p, st) : launch_sd2<64, 0>(p, st); }
+        else return out_presplit ? launch_sd2<32, 1>(p, st) : launch_sd2<32, 0>(p, st);
+    }
     if (Cout > 64) return dispatch_sd<128, 2>(p, in_presplit, out_presplit, st);
     if (Cout > 32) return dispatch_sd<64, 2>(p, in_presplit, out_presplit, st);
     return dispatch_sd<32, 1>(p, in_presplit, out_presplit, st);

@@ -255,7 +255,7 @@ BX_API int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint,
         BX_REQUIRE(n >= 1, "bx_fps: cloud %d is empty", b);
         if (n > maxN) maxN = n;
     }
-    BX_REQUIRE(maxN <= 131072, "bx_fps: N=%d exceeds the 131072-point register budget of one cluster", maxN);
+    BX_REQUIRE(maxN <= 524288, "bx_fps: N=%d exceeds the 524288-point register budget of one 16-CTA cluster", maxN);
     cudaStream_t st = bx_stream(stream);
     FpsOffsets d_off;
     for (int b = 0; b <= kMaxClouds; ++b) d_off.v[b] = h_offsets[b <= B ? b : B];
@@ -268,5 +268,9 @@ BX_API int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint,
     if (maxN <= 24576) return launch_fps<1024, 3>(xyz, d_off, B, 8, npoint, idx, kpts, st);
     if (maxN <= 32768) return launch_fps<1024, 4>(xyz, d_off, B, 8, npoint, idx, kpts, st);
     if (maxN <= 65536) return launch_fps<1024, 8>(xyz, d_off, B, 8, npoint, idx, kpts, st);
-    return launch_fps<1024, 8>(xyz, d_off, B, 16, npoint, idx, kpts, st);
+    if (maxN <= 131072) return launch_fps<1024, 8>(xyz, d_off, B, 16, npoint, idx, kpts, st);
+    // beyond 128 K points per cloud (raw LiDAR sweeps before voxel down-sampling): 512-thread CTAs leave 128 registers per
+    // thread, enough for 32 / 64 points each -- slower per iteration, same result contract
+    if (maxN <= 262144) return launch_fps<512, 32>(xyz, d_off, B, 16, npoint, idx, kpts, st);
+    return launch_fps<512, 64>(xyz, d_off, B, 16, npoint, idx, kpts, st);
 }

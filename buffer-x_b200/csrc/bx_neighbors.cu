@@ -31,7 +31,8 @@ __device__ __forceinline__ bool nd_less(double da, int ia, double db, int ib) { 
 
 __global__ void __launch_bounds__(RN_THREADS)
 radius_neighbors_kernel(const float *__restrict__ queries, int nq, const float *__restrict__ supports, const Batches bt,
-                        float radius, int *__restrict__ out, int cap, int *__restrict__ d_max_count) {
+                        float radius, int *__restrict__ out, int cap, int *__restrict__ d_max_count,
+                        double *__restrict__ big_d, int *__restrict__ big_i) {
     extern __shared__ unsigned char rn_smem[];
     double *sd = reinterpret_cast<double *>(rn_smem);          // RN_CAP
     int *si = reinterpret_cast<int *>(sd + RN_CAP);            // RN_CAP
@@ -60,6 +61,41 @@ radius_neighbors_kernel(const float *__restrict__ queries, int nq, const float *
     const int cnt = s_cnt;
     if (threadIdx.x == 0) atomicMax(d_max_count, cnt);
     if (out == nullptr) return;                      // counting pass
+    if (cnt > RN_CAP) {
+        // Ball too large for the shared-memory sort (needs the caller's global scratch rows of `cap` entries): collect the
+        // (distance, index) pairs again into global memory, then place every entry at its RANK -- the number of entries that
+        // precede it in (distance, index) order.  O(cnt^2 / 256) per query, exact, no power-of-two padding.
+        int *row = out + (size_t)i * cap;
+        if (big_d == nullptr || cnt > cap) {          // caller promised cap <= RN_CAP: truncating silently is not an option
+            for (int j = threadIdx.x; j < cap; j += RN_THREADS) row[j] = -1;
+            return;
+        }
+        double *gd = big_d + (size_t)i * cap;
+        int *gi = big_i + (size_t)i * cap;
+        __syncthreads();
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += RN_THREADS) {
+            const float *s = supports + 3 * (size_t)(off + j);
+            const double dx = qx - (double)s[0], dy = qy - (double)s[1], dz = qz - (double)s[2];
+            const double d = ((dx * dx) + (dy * dy)) + (dz * dz);
+            if (d < r2) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                gd[slot] = d;
+                gi[slot] = off + j;
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt; e += RN_THREADS) {
+            const double de = gd[e];
+            const int ie = gi[e];
+            int rank = 0;
+            for (int j = 0; j < cnt; ++j) rank += nd_less(gd[j], gi[j], de, ie) ? 1 : 0;
+            row[rank] = ie;
+        }
+        for (int j = cnt + threadIdx.x; j < cap; j += RN_THREADS) row[j] = bt.ns_total;
+        return;
+    }
     const int m = min(cnt, RN_CAP);
     int p2 = 1;
     while (p2 < m) p2 <<= 1;
@@ -183,10 +219,11 @@ __global__ void grid_emit_kernel(const unsigned long long *__restrict__ tkeys, c
 
 BX_API int bx_radius_neighbors(const float *queries, int nq, const float *supports, int ns, const int32_t *h_q_batches, int nqb,
                                const int32_t *h_s_batches, int nsb, float radius, int32_t *out, int cap, int32_t *d_max_count,
-                               void *stream) {
+                               double *scratch_d, int32_t *scratch_i, void *stream) {
     BX_REQUIRE(queries && supports && h_q_batches && h_s_batches && d_max_count, "bx_radius_neighbors: null pointer");
     BX_REQUIRE(nq >= 0 && ns >= 0 && nqb >= 1 && nqb <= 8 && nsb >= 1 && nsb <= 2, "bx_radius_neighbors: 1..8 query batches, 1..2 support clouds");
-    BX_REQUIRE(out == nullptr || (cap >= 1 && cap <= RN_CAP), "bx_radius_neighbors: capacity must be in [1,%d]", RN_CAP);
+    BX_REQUIRE(out == nullptr || cap >= 1, "bx_radius_neighbors: capacity must be >= 1");
+    BX_REQUIRE(out == nullptr || cap <= RN_CAP || (scratch_d && scratch_i), "bx_radius_neighbors: more than %d neighbours per ball need the global scratch rows", RN_CAP);
     Batches bt = {};
     bt.nqb = nqb;
     int acc = 0;
@@ -204,7 +241,7 @@ BX_API int bx_radius_neighbors(const float *queries, int nq, const float *suppor
     static BxPerDevice attr_done = {};
     if (bx_needs_attr(attr_done))
         BX_CUDA(cudaFuncSetAttribute(radius_neighbors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    radius_neighbors_kernel<<<nq, RN_THREADS, smem, st>>>(queries, nq, supports, bt, radius, out, cap, d_max_count);
+    radius_neighbors_kernel<<<nq, RN_THREADS, smem, st>>>(queries, nq, supports, bt, radius, out, cap, d_max_count, scratch_d, scratch_i);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

@@ -80,7 +80,7 @@ def load_library():
     lib.bx_consensus.argtypes = [P, P, P, P, P, c_int, c_int, c_float, P, P, P, P, P]
     lib.bx_ransac.argtypes = [P, P, P, P, c_int, c_double, c_double, c_double, c_int, c_uint64, P, P, P]
     lib.bx_refine.argtypes = [P, P, P, c_int, P, c_float, P, P, P]
-    lib.bx_radius_neighbors.argtypes = [P, c_int, P, c_int, P, c_int, P, c_int, c_float, P, c_int, P, P]
+    lib.bx_radius_neighbors.argtypes = [P, c_int, P, c_int, P, c_int, P, c_int, c_float, P, c_int, P, P, P, P]
     lib.bx_grid_subsample.argtypes = [P, c_int, c_float, P, P, c_int, P, P, P, P, P, P]
     _lib = lib
     return lib
@@ -570,13 +570,17 @@ def radius_neighbors(queries, supports, q_batches, s_batches, radius: float):
     dmax = torch.zeros(1, dtype=I32, device=queries.device)
     args = (_dp(queries, F32, "queries"), nq, _dp(supports, F32, "supports"), ns, qb.ctypes.data_as(c_void_p), len(qb),
             sb.ctypes.data_as(c_void_p), len(sb), float(radius))
-    _check(lib.bx_radius_neighbors(*args, None, 0, _dp(dmax), _stream()), "bx_radius_neighbors")
+    _check(lib.bx_radius_neighbors(*args, None, 0, _dp(dmax), None, None, _stream()), "bx_radius_neighbors")
     mc = int(dmax.item())
-    if mc > 4096:
-        raise BufferXError(f"bx_radius_neighbors: {mc} neighbours in one ball exceed the 4096-entry in-CTA sort")
     out = torch.empty((nq, max(mc, 1)), dtype=I32, device=queries.device)
+    sd = si = None
+    if mc > 4096:      # balls too large for the shared-memory sort: global scratch rows for the rank sort
+        if nq * mc * 12 > (8 << 30):
+            raise BufferXError(f"bx_radius_neighbors: {nq} queries x {mc} neighbours need more than 8 GB of scratch")
+        sd = torch.empty((nq, mc), dtype=torch.float64, device=queries.device)
+        si = torch.empty((nq, mc), dtype=I32, device=queries.device)
     if mc > 0:
-        _check(lib.bx_radius_neighbors(*args, _dp(out), mc, _dp(dmax), _stream()), "bx_radius_neighbors")
+        _check(lib.bx_radius_neighbors(*args, _dp(out), mc, _dp(dmax), _dp(sd), _dp(si), _stream()), "bx_radius_neighbors")
     return out[:, :mc]
 
 

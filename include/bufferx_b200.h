@@ -230,11 +230,13 @@ int bx_refine(const float *ss, const float *tt, const int32_t *d_n, int maxn, co
  * Replaces radius_neighbors.batch_query (cpp_wrappers/cpp_neighbors/wrapper.cpp:58-239 ->
  * neighbors/neighbors.cpp:334-480 batch_nanoflanntbb_neighbors).  h_q_batches / h_s_batches: HOST arrays
  * (1..8 query batches, 1..2 support clouds; query batch b searches support cloud b % 2 like the reference).
- * out == NULL: counting pass (only *d_max_count is written).  Otherwise out is [nq, cap] int32 (cap <= 4096),
- * rows sorted by distance and padded with ns; *d_max_count = largest true neighbour count. */
+ * out == NULL: counting pass (only *d_max_count is written).  Otherwise out is [nq, cap] int32, rows sorted by distance
+ * and padded with ns; *d_max_count = largest true neighbour count.  Balls of up to 4096 neighbours are sorted in shared
+ * memory; cap > 4096 needs scratch_d [nq, cap] doubles + scratch_i [nq, cap] int32 (global rank sort of the large balls;
+ * both may be NULL when cap <= 4096). */
 int bx_radius_neighbors(const float *queries, int nq, const float *supports, int ns, const int32_t *h_q_batches, int nqb,
                         const int32_t *h_s_batches, int nsb, float radius, int32_t *out, int cap, int32_t *d_max_count,
-                        void *stream);
+                        double *scratch_d, int32_t *scratch_i, void *stream);
 
 /* ---- a18: voxel-grid barycentre sub-sampling ------------------------------------------------
  * Replaces grid_subsampling.subsample (cpp_wrappers/cpp_subsampling/wrapper.cpp:631-859 ->

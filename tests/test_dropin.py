@@ -151,6 +151,37 @@ def test_load_state_dict_and_to_drop_captured_graphs(oracle):
 
 
 @pytest.mark.gpu
+def test_fp16_range_flag_reruns_the_pair_on_the_tf32_kernel(oracle):
+    """The shifted-descriptor conv kernel's sticky fp16-range flag rides in the pair's result block: when it is set, forward()
+    (eager and graph mode) recomputes the pair on the TF32 tensor-core kernel, keeps the model on it and clears the flag --
+    same counts, pose within rounding of the fp16-split path."""
+    import bufferx_b200 as bx
+    from bufferx_b200.se3 import compute_rre, compute_rte
+    from bufferx_b200.synth import init_synthetic_weights, make_pair, workload_cfg
+    dev = torch.device("cuda:0")
+    cfg = workload_cfg("C2")
+    cfg.patch.num_fps, cfg.patch.num_points_radius_estimate, cfg.match.iter_n = 384, 512, 5000
+    d = make_pair("C1", 31)
+    perms = oracle.draw_perms(cfg, 5000, 5000, 31)
+    for graphs in (False, True):
+        model = init_synthetic_weights(bx.BufferX(cfg), trained_pose=True).to(dev)
+        model.enable_cuda_graphs(graphs, slots_per_shape=1)
+        with torch.no_grad():
+            ref = model(d, perms=perms)
+            assert not model.Desc.conv_net.force_tf32
+            model.Desc.conv_net.overflow_flag(dev).fill_(1)          # as if an activation had left fp16 range
+            out = model(d, perms=perms)
+            assert model.Desc.conv_net.force_tf32 and model.Pose.conv.force_tf32
+            assert int(model.Desc.conv_net.overflow_flag(dev).item()) == 0
+            again = model(d, perms=perms)                            # stays on the TF32 kernel, no rerun needed
+        assert out[2:] == again[2:] and np.array_equal(out[0], again[0])
+        assert out[3] == ref[3] and abs(out[2] - ref[2]) <= 1 and out[4] == ref[4]
+        if ref[2] >= 3:
+            assert compute_rre(out[0], ref[0]) < 0.5 and compute_rte(out[0], ref[0]) < 0.01
+        model.enable_cuda_graphs(False)
+
+
+@pytest.mark.gpu
 def test_inputs_produced_on_another_stream_are_ordered(oracle):
     """forward_async copies CUDA inputs on the slot stream; it must wait for the producer stream."""
     import bufferx_b200 as bx
@@ -179,11 +210,18 @@ def test_inputs_produced_on_another_stream_are_ordered(oracle):
 
 
 @pytest.mark.gpu
-def test_radius_neighbors_cap_fails_loudly():
-    """More than 4096 neighbours in one ball exceed the in-CTA sort: the call must raise, not truncate."""
+def test_radius_neighbors_beyond_the_shared_memory_sort(oracle):
+    """Balls with more than 4096 neighbours (round 1: hard failure) take the global rank-sort path: same rows as the oracle,
+    including the exact-tie order (duplicated supports), next to small balls in the same call."""
     from bufferx_b200 import ops
     dev = torch.device("cuda:0")
-    pts = torch.rand((6000, 3), device=dev) * 0.01
+    rng = np.random.default_rng(2)
+    dense = (rng.random((6000, 3)) * 0.02).astype(np.float32)
+    dense[3000:3500] = dense[:500]                                   # exact distance ties
+    sparse = (rng.random((3000, 3)) * 5 + 1).astype(np.float32)
+    sup = np.concatenate([dense, sparse]).astype(np.float32)
+    qry = np.concatenate([dense[:5], sparse[:40]]).astype(np.float32)
     with torch.cuda.device(dev):
-        with pytest.raises(ops.BufferXError):
-            ops.radius_neighbors(pts[:4].contiguous(), pts, [4], [6000], 1.0)
+        got = ops.radius_neighbors(torch.from_numpy(qry).to(dev), torch.from_numpy(sup).to(dev), [len(qry)], [len(sup)], 0.5).cpu().numpy()
+    exp = oracle.radius_neighbors(qry, sup, [len(qry)], [len(sup)], 0.5)
+    assert got.shape == exp.shape and got.shape[1] >= 6000 and (got == exp).all()

@@ -35,7 +35,7 @@ def relerr(a, b):
 # ------------------------------------------------------------------------------------------------ a1
 @pytest.mark.parametrize("n,m,kind", [(300, 64, "dup"), (5000, 2000, "plain"), (20000, 2000, "plain"),
                                       (20000, 300, "dup"), (40000, 200, "plain"), (70000, 128, "plain"),
-                                      (120000, 96, "plain")])
+                                      (120000, 96, "plain"), (200000, 24, "plain"), (300000, 12, "dup")])
 def test_fps_bit_exact(dev, oracle, n, m, kind):
     from bufferx_b200 import ops
     rng = np.random.default_rng(n + m)
