@@ -446,8 +446,9 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
 // kernel is bound by what an SM can pull from L2 (~43 B/clk per SM when all 148 do), and 87 % of that was the weight image,
 // re-streamed for every 128-row tile (589 KB per tile against 90 KB of activations).  Here a weight chunk (nine taps) is
 // fetched once per 256 rows: tile u = 0 runs its 27 (18) MMAs of the chunk, then tile u = 1 runs the same taps against the
-// same shared-memory weights.  The two tiles also replace the per-tile accumulator ping-pong: while tile 1's MMAs run, the
-// epilogue warps of tile 0 drain its segment, and vice versa -- one accumulator set per tile.
+// same shared-memory weights.  Cout 128: one main accumulator per tile (while tile 1's MMAs run the epilogue warps of tile 0
+// drain its segment, and vice versa); Cout <= 64: two [main | cross] sets per tile (their 432-864-cycle segments are shorter
+// than a drain).
 // Presplit input only (bulk-copied A chunks); 8 epilogue warps per tile, one A producer, one weight producer, one MMA warp.
 template <int NT, int OUT_SD>
 __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams p) {
@@ -457,10 +458,11 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
     constexpr int LDW = CW < 32 ? CW : 32;        // columns per tcgen05.ld
     constexpr int APROD_WARP = 2 * NEW, WGT_WARP = 2 * NEW + 1, MMA_WARP = 2 * NEW + 2;
     constexpr int B_STAGE = 64 * NT, B_CHUNK = 9 * B_STAGE;   // nine taps of [kcore][split][n][16 B]
-    constexpr int TMEM_COLS = 4 * NT;             // MERGED: [main | cross] per tile; else main[2 tiles], cross[2 tiles]
+    constexpr int TMEM_COLS = MERGED ? 8 * NT : 4 * NT;   // MERGED: two [main | cross] sets per tile; else main[2 tiles], cross[2 tiles]
     constexpr int MAXNA = 12;
     constexpr int BAR_AFULL = 0, BAR_AEMPTY = MAXNA, BAR_BFULL = 2 * MAXNA, BAR_BEMPTY = BAR_BFULL + 2;
-    constexpr int BAR_SEGDONE = BAR_BEMPTY + 2, BAR_ACCFREE = BAR_SEGDONE + 2, BAR_XDONE = BAR_ACCFREE + 2, BAR_XFREE = BAR_XDONE + 2;
+    constexpr int NSET = MERGED ? 2 : 1;          // accumulator sets per tile (MERGED: 4 sets of [main | cross] = 8 * NT <= 512 columns)
+    constexpr int BAR_SEGDONE = BAR_BEMPTY + 2, BAR_ACCFREE = BAR_SEGDONE + 4, BAR_XDONE = BAR_ACCFREE + 4, BAR_XFREE = BAR_XDONE + 2;
     constexpr int NBARS = BAR_XFREE + 2;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[NBARS];
@@ -485,7 +487,9 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
             mbar_init(smem_u32(&bars[BAR_BFULL + s]), 1);
             mbar_init(smem_u32(&bars[BAR_BEMPTY + s]), 1);
             mbar_init(smem_u32(&bars[BAR_SEGDONE + s]), 1);
+            mbar_init(smem_u32(&bars[BAR_SEGDONE + 2 + s]), 1);
             mbar_init(smem_u32(&bars[BAR_ACCFREE + s]), NEW);
+            mbar_init(smem_u32(&bars[BAR_ACCFREE + 2 + s]), NEW);
             mbar_init(smem_u32(&bars[BAR_XDONE + s]), 1);
             mbar_init(smem_u32(&bars[BAR_XFREE + s]), NEW);
         }
@@ -504,16 +508,19 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
         // =========================== epilogue warps of tile u ===============================================
         const int u = warp >> 3, quarter = warp & 3, ecs = (warp >> 2) & 1;
         const uint32_t tm_lane = (uint32_t)(quarter * 32) << 16;
-        const uint32_t d_main = tmem_base + tm_lane + (uint32_t)(MERGED ? u * 2 * NT : u * NT) + (uint32_t)(ecs * CW);
-        const uint32_t d_cross = tmem_base + tm_lane + (uint32_t)(MERGED ? u * 2 * NT + NT : 2 * NT + u * NT) + (uint32_t)(ecs * CW);
+        const uint32_t d_main0 = tmem_base + tm_lane + (uint32_t)(MERGED ? u * 4 * NT : u * NT) + (uint32_t)(ecs * CW);
+        const uint32_t d_cross0 = tmem_base + tm_lane + (uint32_t)(MERGED ? u * 4 * NT + NT : 2 * NT + u * NT) + (uint32_t)(ecs * CW);
         float run[CW];
         uint32_t seg = 0, k = 0;
         for (int m = blockIdx.x; m < n_macro; m += gridDim.x, ++k) {
 #pragma unroll
             for (int c = 0; c < CW; ++c) run[c] = 0.0f;
             for (int c = 0; c < nchunks; ++c, ++seg) {
-                mbar_wait(bar_base + 8u * (BAR_SEGDONE + u), seg & 1u);
+                const uint32_t sp = NSET == 2 ? (seg & 1u) : 0u;                 // which of the tile's sets this segment used
+                const uint32_t bidx = (uint32_t)u * 2u + sp;
+                mbar_wait(bar_base + 8u * (BAR_SEGDONE + bidx), (NSET == 2 ? (seg >> 1) : seg) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_main = d_main0 + sp * (2u * NT), d_cross = d_cross0 + sp * (2u * NT);
 #pragma unroll
                 for (int c0 = 0; c0 < CW; c0 += LDW) {
                     uint32_t v[LDW];
@@ -533,9 +540,10 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_ACCFREE + u));
+                if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_ACCFREE + bidx));
             }
             if constexpr (!MERGED) {      // the tile's cross chain: one read per tile, scaled by 2^-11
+                const uint32_t d_cross = d_cross0;
                 mbar_wait(bar_base + 8u * (BAR_XDONE + u), k & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -607,11 +615,12 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     mbar_wait(bar_base + 8u * (BAR_AFULL + slot), a_par);
-                    if (seg >= 1) mbar_wait(bar_base + 8u * (BAR_ACCFREE + u), (seg - 1) & 1u);
+                    const uint32_t sp = NSET == 2 ? (seg & 1u) : 0u, bidx = (uint32_t)u * 2u + sp;
+                    if (seg >= (uint32_t)NSET) mbar_wait(bar_base + 8u * (BAR_ACCFREE + bidx), (NSET == 2 ? ((seg >> 1) - 1) : (seg - 1)) & 1u);
                     if (!MERGED && c == 0 && k >= 1) mbar_wait(bar_base + 8u * (BAR_XFREE + u), (k - 1) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t ac = a0 + slot * A_CHUNK16;
-                    const uint32_t d_set = tmem_base + (uint32_t)(MERGED ? u * 2 * NT : u * NT);
+                    const uint32_t d_set = tmem_base + (MERGED ? ((uint32_t)u * 2u + sp) * (2u * NT) : (uint32_t)u * NT);
                     const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT + u * NT);
                     const uint32_t first = c == 0 ? 0u : 1u;
 #pragma unroll
@@ -627,7 +636,7 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
                             mma_f16_ss(leader, d_set, ah, bb, DESC_HI, IDESC, tap == 0 ? 0u : 1u);
                         }
                     }
-                    mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + u));
+                    mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + bidx));
                     mma_commit(leader, bar_base + 8u * (BAR_AEMPTY + slot));
                     if (!MERGED && c == nchunks - 1) mma_commit(leader, bar_base + 8u * (BAR_XDONE + u));
                     if (++slot == (uint32_t)NA) { slot = 0; a_par ^= 1u; }
@@ -737,12 +746,13 @@ BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const voi
     cudaStream_t st = bx_stream(stream);
     static int macro = -1;       // BX_SD_MACRO=0: one 128-row tile per weight pass everywhere (A/B switch, experiments)
     if (macro < 0) { const char *e = getenv("BX_SD_MACRO"); macro = e ? atoi(e) : 1; }
-    // Two tiles per weight chunk (conv_sd2_kernel) where it measured faster at K = 9000 patches: Cout 128 (128->128: 1019 -> 975 us)
-    // and Cout 32 (64->32: 219 -> 189 us, 32->32: 120 -> 97 us).  Cout 64 is 8 % slower that way (its 864-cycle segments are
-    // shorter than a drain, and one accumulator set per tile then stalls the tensor core); BX_SD_MACRO=2 forces it everywhere.
+    // Two tiles per weight chunk (conv_sd2_kernel) where it measured faster at K = 9000 patches: 128->128 (1019 -> 980 us) and
+    // Cout 32 (64->32: 219 -> 190 us, 32->32: 120 -> 98 us).  64->128 (560 vs 572 us) and the Cout 64 layers (305 vs 323 us, with
+    // two accumulator sets per tile) are not: their weight stream is small against the per-tile costs.  BX_SD_MACRO=2 forces
+    // the macro-tile kernel everywhere, 0 disables it.
     if (macro && p.cyl && in_presplit && p.n_tiles >= 2) {
-        if (Cout > 64) return out_presplit ? launch_sd2<128, 1>(p, st) : launch_sd2<128, 0>(p, st);
-        if (Cout > 32) { if (macro >= 2) return out_presplit ? launch_sd2<64, 1>(p, st) : launch_sd2<64, 0>(p, st); }
+        if (Cout > 64) { if (macro >= 2 || p.nchunks >= 8) return out_presplit ? launch_sd2<128, 1>(p, st) : launch_sd2<128, 0>(p, st); }
+        else if (Cout > 32) { if (macro >= 2) return out_presplit ? launch_sd2<64, 1>(p, st) : launch_sd2<64, 0>(p, st); }
         else return out_presplit ? launch_sd2<32, 1>(p, st) : launch_sd2<32, 0>(p, st);
     }
     if (Cout > 64) return dispatch_sd<128, 2>(p, in_presplit, out_presplit, st);
