@@ -25,6 +25,8 @@ EXACT = ["bx_api.cu", "bx_fps.cu", "bx_radius.cu", "bx_patches.cu", "bx_spt.cu",
 FAST = ["bx_conv.cu", "bx_conv_tc.cu", "bx_conv_sd.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+if os.environ.get("BX_SD_KPAD"):          # experiment: pad between the K halves of the conv_sd A images
+    COMMON = COMMON + ["-DSD_KPAD=" + os.environ["BX_SD_KPAD"]]
 if os.environ.get("BX_BUILD_TRACE"):      # debugging aid: clock64 stage timeline in the tensor-core convolution
     COMMON = COMMON + ["-DBX_TC_TRACE"]
 

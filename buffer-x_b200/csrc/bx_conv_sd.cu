@@ -45,7 +45,11 @@ namespace {
 constexpr int SD_BM = 128;                       // GEMM rows per tile
 constexpr int SD_AROWS = 176;                    // tile rows + halo (2*22 + 2 = 46 -> 48)
 constexpr int SD_SROWS = 176;                    // padded rows per sample (8 x 22)
-constexpr int SD_KCORE = SD_AROWS * 16;          // bytes of one (split, kcore) image of a chunk: [row][8 x fp16]
+constexpr int SD_KBYTES = SD_AROWS * 16;         // payload bytes of one (split, kcore) image of a chunk: [row][8 x fp16]
+#ifndef SD_KPAD
+#define SD_KPAD 0
+#endif
+constexpr int SD_KCORE = SD_KBYTES + SD_KPAD;    // its stride in shared memory (experiment: +64 shifts the second K half by 16 banks)
 constexpr int SD_CHUNK = 4 * SD_KCORE;           // [split(hi,lo)][kcore(2)]
 constexpr int SD_NL = 4;                         // loader warps
 
@@ -265,11 +269,11 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                 for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
                     for (int c = 0; c < nchunks; ++c) {
                         if (round) mbar_wait(bar_base + 8u * (BAR_AEMPTY + slot), par ^ 1u);
-                        mbar_arrive_expect_tx(bar_base + 8u * (BAR_AFULL + slot), (uint32_t)SD_CHUNK);
+                        mbar_arrive_expect_tx(bar_base + 8u * (BAR_AFULL + slot), 4u * (uint32_t)SD_KBYTES);
                         const unsigned char *src = reinterpret_cast<const unsigned char *>(p.in_sd) + ((size_t)(c * 4) * p.rows_in + (size_t)t * SD_BM) * 16;
 #pragma unroll
                         for (int im = 0; im < 4; ++im)
-                            bulk_g2s(a_base + slot * (uint32_t)SD_CHUNK + (uint32_t)im * SD_KCORE, src + (size_t)im * p.rows_in * 16, (uint32_t)SD_KCORE,
+                            bulk_g2s(a_base + slot * (uint32_t)SD_CHUNK + (uint32_t)im * SD_KCORE, src + (size_t)im * p.rows_in * 16, (uint32_t)SD_KBYTES,
                                      bar_base + 8u * (BAR_AFULL + slot));
                         if (++slot == (uint32_t)NA) { slot = 0; par ^= 1u; round = 1; }
                     }
@@ -383,6 +387,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
         const uint32_t leader = elect_leader();
         const uint32_t a0 = (a_base >> 4) | A_LBO, b0 = (b_base >> 4) | B_LBO;
         const int Wrow = p.W;                                              // tap (g, tt) reads rows R + g * W + tt
+        const uint32_t shift_on = (p.dbg & 4) ? 0u : 1u;                   // BX_SD_DBG=4: every tap reads the unshifted (128-byte aligned) view (timing experiment)
         uint32_t slot = 0, a_par = 0, sbq = 0, b_par = 0, seg = 0, k = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
             const uint32_t xset = k & 1;
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                     const uint32_t bg = b0 + sbq * (3u * B_STAGE16);
 #pragma unroll
                     for (int tt = 0; tt < 3; ++tt) {
-                        const uint32_t ah = ac + (uint32_t)(g * Wrow + tt), al = ah + A_SPLIT;    // one row = 16 B = one address unit
+                        const uint32_t ah = ac + shift_on * (uint32_t)(g * Wrow + tt), al = ah + A_SPLIT;    // one row = 16 B = one address unit
                         const uint32_t bb = bg + (uint32_t)tt * B_STAGE16;                         // rows 0..NT-1 = bh, NT..2NT-1 = bl
                         // ah * [bh | bl] -> [main | cross] in ONE N = 2*NT instruction (the hi activations are read once for
                         // both products), then al * bh into the cross columns
@@ -571,11 +576,11 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
                         int t = 2 * m + u;
                         if (t >= n_tiles) t = n_tiles - 1;       // odd tile count: the partner repeats the last tile (never stored)
                         if (round) mbar_wait(bar_base + 8u * (BAR_AEMPTY + slot), par ^ 1u);
-                        mbar_arrive_expect_tx(bar_base + 8u * (BAR_AFULL + slot), (uint32_t)SD_CHUNK);
+                        mbar_arrive_expect_tx(bar_base + 8u * (BAR_AFULL + slot), 4u * (uint32_t)SD_KBYTES);
                         const unsigned char *src = reinterpret_cast<const unsigned char *>(p.in_sd) + ((size_t)(c * 4) * p.rows_in + (size_t)t * SD_BM) * 16;
 #pragma unroll
                         for (int im = 0; im < 4; ++im)
-                            bulk_g2s(a_base + slot * (uint32_t)SD_CHUNK + (uint32_t)im * SD_KCORE, src + (size_t)im * p.rows_in * 16, (uint32_t)SD_KCORE,
+                            bulk_g2s(a_base + slot * (uint32_t)SD_CHUNK + (uint32_t)im * SD_KCORE, src + (size_t)im * p.rows_in * 16, (uint32_t)SD_KBYTES,
                                      bar_base + 8u * (BAR_AFULL + slot));
                         if (++slot == (uint32_t)NA) { slot = 0; par ^= 1u; round = 1; }
                     }
