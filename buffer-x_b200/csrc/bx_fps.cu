@@ -64,6 +64,17 @@ __device__ __forceinline__ void fps_st_cluster_f32(uint32_t a, float v) {
 __device__ __forceinline__ void fps_arrive_cluster(uint32_t rbar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
 }
+// One-way exchange: st.async writes 16 bytes into the peer's shared memory AND completes that many transaction bytes on the
+// peer's mbarrier when they have landed -- no separate release-arrive that has to wait for the stores (one DSMEM trip
+// instead of two per iteration).
+__device__ __forceinline__ void fps_st_async_v4(uint32_t raddr, uint4 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void fps_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fps_wait_cluster(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -105,7 +116,9 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
     __shared__ float w_z[2][32];
     __shared__ uint4 c_a[2][16];
     __shared__ float c_z[2][16];
+    __shared__ uint4 x_a[2][16][2];                      // st.async exchange: two 16-byte halves per (parity, sender)
     __shared__ __align__(8) unsigned long long cbar[2];   // one exchange barrier per parity, CL arrivals each
+    __shared__ __align__(8) unsigned long long xbar[2];   // st.async exchange: 1 arrival (own expect_tx) + 32 * CL bytes per phase
 
     float px[PPT], py[PPT], pz[PPT], tmp[PPT];
     const int stride = CL * THREADS;
@@ -133,6 +146,8 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&cbar[0])), "r"(CL) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&cbar[1])), "r"(CL) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&xbar[0])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&xbar[1])), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster.sync();  // every CTA of the cluster is resident (and its barriers initialised) before any DSMEM access
@@ -169,18 +184,39 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, const FpsOffsets offsets, 
             c.hi = a.x; c.lo = a.y; c.x = __uint_as_float(a.z); c.y = __uint_as_float(a.w); c.z = w_z[par][lane];
         }
         Cand cb = warp_best(c);
-        if (CL > 1) {
+        if (CL > 1 && sync_mode == 0) {
+            // production: every CTA posts its candidate into every peer's slot with st.async (data + transaction bytes in one
+            // DSMEM trip); a CTA's barrier phase completes when its own expect_tx arrival and all 32 * CL bytes are in.
+            if (warp == 0) {
+                if (lane == 0) fps_expect_tx(fps_smem_u32(&xbar[par]), 32u * (uint32_t)CL);
+                if (lane < CL) {
+                    const uint32_t dst = fps_mapa(fps_smem_u32(&x_a[par][rank][0]), (uint32_t)lane);
+                    const uint32_t rb = fps_mapa(fps_smem_u32(&xbar[par]), (uint32_t)lane);
+                    fps_st_async_v4(dst, make_uint4(cb.hi, cb.lo, __float_as_uint(cb.x), __float_as_uint(cb.y)), rb);
+                    fps_st_async_v4(dst + 16u, make_uint4(__float_as_uint(cb.z), 0u, 0u, 0u), rb);
+                }
+            }
+            fps_wait_cluster(fps_smem_u32(&xbar[par]), (uint32_t)(((j >> 1) - (par ? 0 : 1)) & 1));
+            Cand g;
+            g.hi = 0u; g.lo = 0u; g.x = p0x; g.y = p0y; g.z = p0z;
+            if (lane < CL) {
+                const uint4 a = x_a[par][lane][0];
+                g.hi = a.x; g.lo = a.y; g.x = __uint_as_float(a.z); g.y = __uint_as_float(a.w);
+                g.z = __uint_as_float(x_a[par][lane][1].x);
+            }
+            cb = warp_best(g);
+        } else if (CL > 1) {
             if (warp == 0 && lane < CL) {   // lane = destination CTA: candidate into its slot [rank], then arrive on its barrier
                 fps_st_cluster_v4(fps_mapa(fps_smem_u32(&c_a[par][rank]), (uint32_t)lane),
                                   make_uint4(cb.hi, cb.lo, __float_as_uint(cb.x), __float_as_uint(cb.y)));
                 fps_st_cluster_f32(fps_mapa(fps_smem_u32(&c_z[par][rank]), (uint32_t)lane), cb.z);
-                if (!sync_mode) fps_arrive_cluster(fps_mapa(fps_smem_u32(&cbar[par]), (uint32_t)lane));
+                if (sync_mode != 1) fps_arrive_cluster(fps_mapa(fps_smem_u32(&cbar[par]), (uint32_t)lane));
             }
             // Buffers and barriers are double-buffered by parity: a peer can only be one iteration ahead (its next
             // wait needs our next arrive), so slot [par] is not rewritten before everybody has read it.
             // sync_mode (BX_FPS_SYNC=1, verification only): the same exchange ordered by a plain cluster.sync() -- the form
             // compute-sanitizer's racecheck models; results are bit-identical (tests/test_gpu_parity.py).
-            if (sync_mode) cluster.sync();
+            if (sync_mode == 1) cluster.sync();
             else fps_wait_cluster(fps_smem_u32(&cbar[par]), (uint32_t)(((j >> 1) - (par ? 0 : 1)) & 1));
             Cand g;
             g.hi = 0u; g.lo = 0u; g.x = p0x; g.y = p0y; g.z = p0z;
@@ -224,8 +260,8 @@ int launch_fps(const float *xyz, const FpsOffsets off, int B, int CL, int npoint
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    static int sync_mode = -1;     // BX_FPS_SYNC=1: cluster.sync() exchange (racecheck-clean reference form of the mbarrier exchange)
-    if (sync_mode < 0) { const char *e = getenv("BX_FPS_SYNC"); sync_mode = (e && atoi(e)) ? 1 : 0; }
+    static int sync_mode = -1;     // BX_FPS_SYNC: 0 = st.async exchange (production), 1 = cluster.sync() (racecheck-clean reference form),
+    if (sync_mode < 0) { const char *e = getenv("BX_FPS_SYNC"); sync_mode = e ? atoi(e) : 0; }   // 2 = remote stores + mbarrier arrive / acquire wait (round 1)
     if (g_fps_sync_override >= 0) sync_mode = g_fps_sync_override;
     BX_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, off, npoint, idx, kpts, sync_mode));
     ++g_bx_launches;
@@ -234,9 +270,9 @@ int launch_fps(const float *xyz, const FpsOffsets off, int B, int CL, int npoint
 
 }  // namespace
 
-// Verification switch: 1 = order the per-iteration cluster exchange with cluster.sync() instead of the remote-mbarrier
-// arrive / acquire-wait pair (same data path, same results; the form compute-sanitizer racecheck models), 0 = production,
-// -1 = follow the BX_FPS_SYNC environment variable.  Returns the previous value.
+// Exchange switch: 0 = st.async + transaction-count mbarrier (production), 1 = plain stores ordered by cluster.sync() (the form
+// compute-sanitizer racecheck models), 2 = remote stores + remote mbarrier arrive / acquire wait (round 1's production);
+// same results in all three.  -1 = follow the BX_FPS_SYNC environment variable.  Returns the previous value.
 BX_API int bx_fps_set_sync_mode(int mode) {
     const int old = g_fps_sync_override;
     g_fps_sync_override = mode;

@@ -50,8 +50,9 @@ unsigned long long bx_launch_count(void); /* kernels launched by this library si
  * idx: [B,npoint] int32 (index inside the cloud); kpts: [B,npoint,3] (may be NULL).
  * Limit: N <= 131072 per cloud. */
 int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint, int32_t *idx, float *kpts, void *stream);
-/* Verification switch for the FPS cluster exchange: 1 = cluster.sync() per iteration (racecheck-clean reference form),
- * 0 = remote mbarrier arrive + acquire wait (production), -1 = BX_FPS_SYNC environment variable.  Returns the old value. */
+/* Switch for the FPS cluster exchange: 0 = st.async + transaction-count mbarrier (production), 1 = cluster.sync() per iteration
+ * (racecheck-clean reference form), 2 = remote stores + remote mbarrier arrive / acquire wait (round 1), -1 = BX_FPS_SYNC
+ * environment variable.  Same results in every mode.  Returns the old value. */
 int bx_fps_set_sync_mode(int mode);
 
 /* ---- a2: density-aware radius estimation ----------------------------------------------------

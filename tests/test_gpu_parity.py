@@ -63,12 +63,14 @@ def test_fps_mbarrier_exchange_equals_cluster_sync_exchange(dev, oracle, n, m):
     d = cu(xyz, dev)
     old = lib.bx_fps_set_sync_mode(1)
     try:
-        a, _ = ops.fps(d, [0, n], m)
+        a, _ = ops.fps(d, [0, n], m)                 # cluster.sync() exchange (racecheck-clean reference form)
         lib.bx_fps_set_sync_mode(0)
-        b, _ = ops.fps(d, [0, n], m)
+        b, _ = ops.fps(d, [0, n], m)                 # st.async + transaction-count mbarrier (production)
+        lib.bx_fps_set_sync_mode(2)
+        c, _ = ops.fps(d, [0, n], m)                 # remote stores + mbarrier arrive / acquire wait (round 1)
     finally:
         lib.bx_fps_set_sync_mode(old)
-    assert torch.equal(a, b) and (a[0].cpu().numpy() == oracle.fps(xyz, m)).all()
+    assert torch.equal(a, b) and torch.equal(a, c) and (a[0].cpu().numpy() == oracle.fps(xyz, m)).all()
 
 
 def test_fps_two_clouds_one_launch(dev, oracle):
