@@ -78,6 +78,11 @@ int bx_radius_estimate(const float *kpts, int Kr, const float *pts, int N, int64
 int bx_permute_cloud(const float *pts, const int32_t *perm, int N, float *out4, void *stream);
 int bx_select_patches(const float *pts4, int N, const float *kpts, int K, float radius, const float *d_radius,
                       int P, int32_t *idx, float *patches, void *stream);
+/* Same result, segmented form (alternative implementation, not faster; cross-checked in the tests): independent (key-point, 2048-point segment) tasks write hit masks and counts
+ * into `workspace` (bx_select_patches_workspace_bytes(N, K) bytes), a second pass places the hits at their ordered offsets. */
+int bx_select_patches_seg(const float *pts4, int N, const float *kpts, int K, float radius, const float *d_radius, int P,
+                          int32_t *idx, float *patches, void *workspace, void *stream);
+long long bx_select_patches_workspace_bytes(int N, int K);
 
 /* Plain ordered ball query (pointnet2_ops.ball_query; utils/common.py:442): xyz [n,3] packed. */
 int bx_ball_query(const float *xyz, int n, const float *qry, int m, float radius, int nsample, int32_t *idx,

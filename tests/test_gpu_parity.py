@@ -108,10 +108,15 @@ def test_select_patches_bit_exact(dev, oracle, radius, P):
     kp = pts[oracle.fps(pts, K)]
     pts4 = ops.permute_cloud(cu(pts, dev), cu(perm, dev))
     assert (pts4[:, :3].cpu().numpy() == pts[perm]).all()
-    pat, idx = ops.select_patches(pts4, cu(kp, dev), radius, P, want_idx=True)
     eidx, epat = oracle.select_patches(pts, perm, kp, radius, P)
-    assert (idx.cpu().numpy() == eidx).all()
-    assert (pat.cpu().numpy() == epat).all()
+    for scan in (True, False):          # streaming (production) and segmented two-pass form
+        ops.SELECT_PATCHES_SCAN = scan
+        try:
+            pat, idx = ops.select_patches(pts4, cu(kp, dev), radius, P, want_idx=True)
+        finally:
+            ops.SELECT_PATCHES_SCAN = True
+        assert (idx.cpu().numpy() == eidx).all(), f"scan={scan}"
+        assert (pat.cpu().numpy() == epat).all(), f"scan={scan}"
     # device-side radius gives the same result
     pat2, _ = ops.select_patches(pts4, cu(kp, dev), torch.tensor([radius], dtype=torch.float32, device=dev), P)
     assert (pat2.cpu().numpy() == epat).all()
