@@ -61,6 +61,7 @@ struct ConvSdParams {
     int *flag;
     int n, Cout, nchunks, is3d, S_in, G_in, relu, n_tiles, NA, dbg;
     const int *d_n;            // optional device-side sample count (<= n): the match lists of the cost-volume stack
+    const float *fa, *fb;      // COSTAB loader: the factor maps A [n,8,3*20,4], B [n,8,3*18,4] of bx_costvol_ab (else NULL)
     int cyl, rs, W, OD, OW, S_out, rs_out;   // raster geometry: rows per sample, row stride, valid output extent, output rasters
     const __half *in_sd;       // IN_SD: presplit padded input  [nchunks][split,kcore (4)][rows_in][8 x fp16]
     __half *out_sd;            // OUT_SD: presplit padded output [Cout/16][4][rows_out][8 x fp16] = the next layer's in_sd
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                         const long long pr = p0 + r;
                         const int s = (int)(pr / p.rs), q = (int)(pr - (long long)s * p.rs);
                         const int yp = q / 22, xp = q - yp * 22;
-                        if (s < n_samples && (yp != 0 || !p.cyl) && !(p.dbg & 1)) {
+                        if (s < n_samples && (yp != 0 || !p.cyl) && !(p.dbg & 1) && !p.fa) {
                             const int xx = xp == 0 ? 19 : (xp == 21 ? 0 : xp - 1);
                             int pos = p.cyl ? (yp - 1) * 20 + xx : q, g0;       // valid rasters: the row IS the input position
                             if (p.is3d) { pos += c * 140; g0 = h * 2; } else { g0 = c * 4 + h * 2; }
@@ -324,6 +325,42 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                 const int slot = j % NA;
                 if (j >= NA) mbar_wait(bar_base + 8u * (BAR_AEMPTY + slot), (uint32_t)(((j / NA) - 1) & 1));
                 unsigned char *dst = smem + (size_t)slot * SD_CHUNK;
+                if (p.fa) {
+                    // second CostNet layer: the first layer's activation relu(A[c][k][(l - n) mod 20] - B[c][k][l]) is regenerated
+                    // here from the factor maps (models/BUFFERX.py:39-69 + patchnet.py:192-198, factorised by bx_costvol_ab).  Raster
+                    // row q = (n, l) of the 18 x 18 grid; chunk c = (k = c / 2, channels 16 * (c % 2) ...): the k dimension of the
+                    // 3x3x3 kernel is folded into the channels, the taps are (dn, dl).  The 14.6 KB of factors per match are L2
+                    // hits, so all loads of the chunk are issued here, no cross-chunk prefetch.
+                    const long long p0 = (long long)t * SD_BM;
+                    const int kk = c >> 1, cb = (c & 1) * 4;
+                    float4 va[ITEMS][2], vb[ITEMS][2];
+#pragma unroll
+                    for (int m = 0; m < ITEMS; ++m) {
+                        const int idx = ltid + m * SD_NL * 32;
+                        va[m][0] = va[m][1] = vb[m][0] = vb[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (idx < 2 * SD_AROWS) {
+                            const int h = idx >= SD_AROWS ? 1 : 0, r = idx - h * SD_AROWS;
+                            const long long pr = p0 + r;
+                            const int s = (int)(pr / 324), q = (int)(pr - (long long)s * 324);
+                            const int nn = q / 18, ll = q - nn * 18;
+                            if (s < n_samples) {
+                                int sh = ll - nn;
+                                sh = sh < 0 ? sh + 20 : sh;
+                                const float4 *sa = reinterpret_cast<const float4 *>(p.fa) + ((size_t)s * 8 + cb + h * 2) * 60 + kk * 20 + sh;
+                                const float4 *sb = reinterpret_cast<const float4 *>(p.fb) + ((size_t)s * 8 + cb + h * 2) * 54 + kk * 18 + ll;
+                                va[m][0] = __ldg(sa); va[m][1] = __ldg(sa + 60);
+                                vb[m][0] = __ldg(sb); vb[m][1] = __ldg(sb + 54);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < ITEMS; ++m) {
+                        cur[m][0] = make_float4(fmaxf(va[m][0].x - vb[m][0].x, 0.f), fmaxf(va[m][0].y - vb[m][0].y, 0.f), fmaxf(va[m][0].z - vb[m][0].z, 0.f),
+                                                fmaxf(va[m][0].w - vb[m][0].w, 0.f));
+                        cur[m][1] = make_float4(fmaxf(va[m][1].x - vb[m][1].x, 0.f), fmaxf(va[m][1].y - vb[m][1].y, 0.f), fmaxf(va[m][1].z - vb[m][1].z, 0.f),
+                                                fmaxf(va[m][1].w - vb[m][1].w, 0.f));
+                    }
+                }
 #pragma unroll
                 for (int m = 0; m < ITEMS; ++m) {
                     const int idx = ltid + m * SD_NL * 32;
@@ -763,4 +800,30 @@ BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const voi
     if (Cout > 64) return dispatch_sd<128, 2>(p, in_presplit, out_presplit, st);
     if (Cout > 32) return dispatch_sd<64, 2>(p, in_presplit, out_presplit, st);
     return dispatch_sd<32, 1>(p, in_presplit, out_presplit, st);
+}
+
+/* Second CostNet layer on the shifted-descriptor kernel: conv 32 -> 64, k = 3x3x3 over the regenerated first activation
+ * relu(A - B) [32, 18, 3, 18] (see bx_costvol_ab), computed as a 96 -> 64 convolution with k = (3,1,3) over the 18 x 18 (n, l)
+ * raster -- the three k rows become channel chunks.  w_sd: ops.conv_sd_weights_costab image; out: [n,16,256,4] fp32 or the
+ * presplit image over the 16 x 16 output raster (rows = bx_conv_sd_rows(n, 256)). */
+BX_API int bx_conv_layer_sd_costab(const float *fa, const float *fb, const void *w_sd, const float *bias, void *out, int out_presplit, int n,
+                                   const int32_t *d_n, int relu, int32_t *d_flag, void *stream) {
+    BX_REQUIRE(fa && fb && w_sd && bias && out, "bx_conv_layer_sd_costab: null pointer");
+    BX_REQUIRE(((reinterpret_cast<uintptr_t>(fa) | reinterpret_cast<uintptr_t>(fb) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
+                 reinterpret_cast<uintptr_t>(w_sd)) & 15) == 0, "bx_conv_layer_sd_costab: pointers must be 16-byte aligned");
+    if (n <= 0) return BX_OK;
+    ConvSdParams p = {};
+    p.w = reinterpret_cast<const __half *>(w_sd); p.bias = bias; p.flag = d_flag; p.d_n = d_n;
+    p.fa = fa; p.fb = fb;
+    p.in = fa;                     // unused by the COSTAB loader
+    p.out = out_presplit ? nullptr : reinterpret_cast<float *>(out);
+    p.out_sd = out_presplit ? reinterpret_cast<__half *>(out) : nullptr;
+    p.n = n; p.Cout = 64; p.relu = relu;
+    p.is3d = 0; p.cyl = 0; p.nchunks = 6; p.G_in = 8;
+    p.rs = 324; p.W = 18; p.OD = 16; p.OW = 16; p.S_out = 256; p.rs_out = 256; p.S_in = 324;
+    p.dbg = 0;
+    p.n_tiles = (int)(((long long)n * p.rs + SD_BM - 1) / SD_BM);
+    p.rows_in = bx_conv_sd_rows(n, p.rs);
+    p.rows_out = bx_conv_sd_rows(n, p.rs_out);
+    return dispatch_sd<64, 2>(p, 0, out_presplit, bx_stream(stream));
 }

@@ -188,7 +188,16 @@ class CostNet(_ConvStack):
                 D, H, W = OD, OH, OW
                 continue
             # tensor-core layers exchange channel-blocked activations [maxM, C/4, positions, 4]
-            out = torch.empty((maxM, l["cout"], OD * OH * OW) if USE_FFMA else (maxM, l["cout"] // 4, OD * OH * OW, 4), dtype=torch.float32, device=dev)
+            def _f32_out():
+                return torch.empty((maxM, l["cout"], OD * OH * OW) if USE_FFMA else (maxM, l["cout"] // 4, OD * OH * OW, 4), dtype=torch.float32, device=dev)
+            if factored and i == 1 and use_sd:       # regenerated first activation -> 96 -> 64 conv over the 18 x 18 raster
+                if "w_sd_ab" not in l:
+                    l["w_sd_ab"] = ops.conv_sd_weights_costab(l["w"])
+                out = ops.conv_sd_buffer(maxM, 64, dev, 256) if L[2].get("w_sd") is not None else _f32_out()
+                ops.conv_layer_sd_costab(fa, fb, l["w_sd_ab"], l["b"], out, maxM, l["relu"], flag, d_n=d_M)
+                cur, D, H, W = out, OD, OH, OW
+                continue
+            out = _f32_out()
             if factored and i == 1:
                 conv(ops.GEOM_COSTAB, None, w, l["b"], out, maxM, l["cin"], l["cout"], D, H, W, kd, kh, kw, l["relu"],
                      d_n=d_M, equi_s=fa, equi_t=fb)

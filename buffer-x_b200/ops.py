@@ -23,7 +23,7 @@ SYMBOLS = [
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
     "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab", "bx_concat_matches",
-    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes",
+    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes", "bx_conv_layer_sd_costab",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
@@ -71,6 +71,7 @@ def load_library():
     lib.bx_conv_tc_ntile.argtypes = [c_int]
     lib.bx_conv_layer_sd.argtypes = [c_int, P, c_int, P, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P]
     lib.bx_conv_sd_rows.argtypes = [c_int, c_int]
+    lib.bx_conv_layer_sd_costab.argtypes = [P, P, P, P, P, c_int, c_int, P, c_int, P, P]
     lib.bx_fps_set_sync_mode.argtypes = [c_int]
     lib.bx_spt_pnt_sd.argtypes = [P, c_int, c_int, P, c_int, c_int, P, c_float, c_int, P, P, P, c_int64, P, P]
     lib.bx_conv_sd_rows.restype = c_int64
@@ -407,6 +408,28 @@ def conv_layer_sd(geom, x, w_sd, bias, out, n, Cin, Cout, relu, flag=None, d_n=N
     _check(load_library().bx_conv_layer_sd(geom, _dp(x, None, "x"), int(in_sd), _dp(w_sd, torch.float16, "w_sd"), _dp(bias, F32, "bias"),
                                            _dp(out, None, "out"), int(out_sd), int(n), _dp(d_n, I32, "d_n"), Cin, Cout, int(D), int(W), int(bool(relu)),
                                            _dp(flag, I32, "flag"), _stream()), "bx_conv_layer_sd")
+    if ev:
+        ev[1].record()
+    return out
+
+
+def conv_sd_weights_costab(Wt: torch.Tensor) -> torch.Tensor:
+    """Second CostNet layer [27 taps (dn, dk, dl), 32, 64] -> the conv_sd image of the equivalent 96 -> 64, k = (3,1,3) layer:
+    chunk = (dk, 16 channels), taps (dn, dl)."""
+    assert Wt.shape == (27, 32, 64)
+    W = Wt.view(3, 3, 3, 32, 64).permute(1, 0, 2, 3, 4).reshape(3, 9, 32, 64)          # [dk, tap = dn*3+dl, c, co]
+    W = W.permute(1, 0, 2, 3).reshape(9, 96, 64).contiguous()                            # channel = dk * 32 + c
+    return conv_sd_weights(W)
+
+
+def conv_layer_sd_costab(fa, fb, w_sd, bias, out, n, relu, flag=None, d_n=None):
+    """relu(A - B) regenerated from the factor maps -> 96 -> 64 conv over the 18 x 18 raster (bx_conv_layer_sd_costab)."""
+    ev = profiler.span("conv_cost", 0.0) if profiler is not None else None
+    if ev:
+        ev[0].record()
+    _check(load_library().bx_conv_layer_sd_costab(_dp(fa, F32, "fa"), _dp(fb, F32, "fb"), _dp(w_sd, torch.float16, "w_sd"), _dp(bias, F32, "bias"),
+                                                  _dp(out, None, "out"), int(out.dtype == torch.float16), int(n), _dp(d_n, I32, "d_n"), int(bool(relu)),
+                                                  _dp(flag, I32, "flag"), _stream()), "bx_conv_layer_sd_costab")
     if ev:
         ev[1].record()
     return out
