@@ -313,12 +313,12 @@ constexpr int LRF_WARPS = 4;
 
 __global__ void __launch_bounds__(LRF_WARPS * 32)
 lrf_kernel(const float *__restrict__ patches, int K, int P, float des_r_v, const float *__restrict__ d_des_r, int flags,
-           float *__restrict__ delta, float *__restrict__ Rt, float *__restrict__ rand_axis) {
+           float *__restrict__ delta, float *__restrict__ Rt, float *__restrict__ rand_axis, int r_group) {
     const int aligned = flags & 1, stable = flags & 2;
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * LRF_WARPS + (threadIdx.x >> 5);
     if (k >= K) return;
-    const float des_r = d_des_r ? *d_des_r : des_r_v;
+    const float des_r = d_des_r ? d_des_r[r_group > 0 ? k / r_group : 0] : des_r_v;     // batched call: one radius per r_group patches
     const float *pt = patches + (size_t)k * P * 3;
     float *dl = delta + (size_t)k * P * 3;
     const float cx = pt[3 * (P - 1)], cy = pt[3 * (P - 1) + 1], cz = pt[3 * (P - 1) + 2];
@@ -468,11 +468,16 @@ BX_API int bx_ball_query(const float *xyz, int n, const float *qry, int m, float
 
 BX_API int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r, int flags, float *delta,
                   float *Rt, float *rand_axis, void *stream) {
+    return bx_lrf_batched(patches, K, P, des_r, d_des_r, 0, flags, delta, Rt, rand_axis, stream);
+}
+
+BX_API int bx_lrf_batched(const float *patches, int K, int P, float des_r, const float *d_des_r, int r_group, int flags, float *delta,
+                          float *Rt, float *rand_axis, void *stream) {
     BX_REQUIRE(patches && delta && Rt && rand_axis, "bx_lrf: null pointer");
-    BX_REQUIRE(K >= 0 && P >= 1, "bx_lrf: bad sizes");
+    BX_REQUIRE(K >= 0 && P >= 1 && r_group >= 0, "bx_lrf: bad sizes");
     if (K == 0) return BX_OK;
     lrf_kernel<<<(K + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, 0, bx_stream(stream)>>>(patches, K, P, des_r, d_des_r,
-                                                                                           flags, delta, Rt, rand_axis);
+                                                                                           flags, delta, Rt, rand_axis, r_group);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

@@ -350,7 +350,7 @@ class BufferX(nn.Module):
                     if not pm.is_cuda or pm.dtype != torch.int32:
                         pm = pm.to(dev, dtype=torch.int32, non_blocking=True)
                     jobs.append((pts_c, k_c, r_dev[i:i + 1], pm))
-            batched = self.Desc.forward_multi(jobs, aligned)
+            batched = self.Desc.forward_multi(jobs, aligned, radii=r_dev)
             desc_t.toc()
         if batched is not None and S <= 8:
             # all scales at once: per-scale mutual matching into rows of one [S,K] buffer, one concatenation kernel

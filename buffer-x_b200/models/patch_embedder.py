@@ -112,7 +112,7 @@ class MiniSpinNet(nn.Module):
             out.update(idx=idx, raw_patches=patches, vidx=res[1], inv=res[2], feat=ops.from_blocked(feat), x=x_cf)
         return out
 
-    def forward_multi(self, jobs, is_aligned_to_global_z):
+    def forward_multi(self, jobs, is_aligned_to_global_z, radii=None):
         """Descriptors of several (cloud, key-points, radius, permutation) jobs in ONE pass through SPT, the
         convolution stack and the pooling layer (all CTA-per-patch kernels: batching the 2 x num_scales calls of a
         pair removes five of six launch tails and wave-quantisation losses).  Per-job results are views into the
@@ -129,14 +129,19 @@ class MiniSpinNet(nn.Module):
         ra_all = torch.empty((Kt, 3), dtype=torch.float32, device=dev)
         Rs, axes = [], []
         o = 0
+        # `radii` = the contiguous device array of per-scale radii when the jobs are (src, tgt) per scale with equal key-point
+        # counts: the local reference frames of all jobs then run in ONE launch (patch k uses radii[k // (2 K)])
+        one_lrf = radii is not None and len(set(Ks)) == 1 and len(jobs) == 2 * radii.numel()
         for (pts, kpts, des_r, perm), K in zip(jobs, Ks):
             pts4 = ops.permute_cloud(pts.contiguous(), perm)
             ops.select_patches(pts4, kpts.contiguous(), des_r, P, patches=patches[o:o + K])
-            _, R, ra = ops.lrf(patches[o:o + K], des_r, bool(is_aligned_to_global_z), delta=delta[o:o + K], Rt=R_all[o:o + K],
-                               ra=ra_all[o:o + K])
-            Rs.append(R)
-            axes.append(ra)
+            if not one_lrf:
+                ops.lrf(patches[o:o + K], des_r, bool(is_aligned_to_global_z), delta=delta[o:o + K], Rt=R_all[o:o + K], ra=ra_all[o:o + K])
+            Rs.append(R_all[o:o + K])
+            axes.append(ra_all[o:o + K])
             o += K
+        if one_lrf:
+            ops.lrf(patches, radii, bool(is_aligned_to_global_z), delta=delta, Rt=R_all, ra=ra_all, r_group=2 * Ks[0])
         net = self.conv_net
         if not pn.USE_FFMA and not net.force_tf32 and self.rad_n * self.ele_n * self.azi_n == 420 and self.azi_n == 20:
             # production: features straight into the presplit fp16 format the first conv layer fetches with bulk copies

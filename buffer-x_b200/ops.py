@@ -23,7 +23,7 @@ SYMBOLS = [
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
     "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab", "bx_concat_matches",
-    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes", "bx_conv_layer_sd_costab",
+    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes", "bx_conv_layer_sd_costab", "bx_lrf_batched",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
@@ -65,6 +65,7 @@ def load_library():
     lib.bx_select_patches_workspace_bytes.restype = c_int64
     lib.bx_ball_query.argtypes = [P, c_int, P, c_int, c_float, c_int, P, P]
     lib.bx_lrf.argtypes = [P, c_int, c_int, c_float, P, c_int, P, P, P, P]
+    lib.bx_lrf_batched.argtypes = [P, c_int, c_int, c_float, P, c_int, c_int, P, P, P, P]
     lib.bx_spt_pnt.argtypes = [P, c_int, c_int, P, c_int, c_int, P, c_float, c_int, P, P, P, P, P, P]
     lib.bx_conv_layer.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_layer_tc.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
@@ -248,7 +249,7 @@ def ball_query(xyz: torch.Tensor, qry: torch.Tensor, radius: float, nsample: int
     return idx
 
 
-def lrf(patches: torch.Tensor, des_r, aligned: bool, delta=None, Rt=None, ra=None):
+def lrf(patches: torch.Tensor, des_r, aligned: bool, delta=None, Rt=None, ra=None, r_group=0):
     K, P, _ = patches.shape
     dev = patches.device
     if delta is None:
@@ -260,7 +261,7 @@ def lrf(patches: torch.Tensor, des_r, aligned: bool, delta=None, Rt=None, ra=Non
     rv, rp = (0.0, _dp(des_r, F32, "des_r")) if isinstance(des_r, torch.Tensor) else (float(des_r), None)
     with _Span("lrf", 24.0 * K * P):
         flags = int(bool(aligned)) | (2 if os.environ.get("BX_LRF", "").lower() == "stable" else 0)
-        _check(load_library().bx_lrf(_dp(patches, F32, "patches"), K, P, rv, rp, flags, _dp(delta), _dp(Rt), _dp(ra), _stream()), "bx_lrf")
+        _check(load_library().bx_lrf_batched(_dp(patches, F32, "patches"), K, P, rv, rp, int(r_group), flags, _dp(delta), _dp(Rt), _dp(ra), _stream()), "bx_lrf")
     return delta, Rt, ra
 
 

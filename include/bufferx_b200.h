@@ -96,6 +96,10 @@ int bx_ball_query(const float *xyz, int n, const float *qry, int m, float radius
  * sin = |z x e_z|/|z|) instead of the reference's theta = acos(cos) -> sin(theta), cos(theta) (default, literal). */
 int bx_lrf(const float *patches, int K, int P, float des_r, const float *d_des_r, int flags, float *delta,
            float *Rt, float *rand_axis, void *stream);
+/* The same over the patches of several (cloud, scale) key-point sets in one launch: patch k uses the device radius
+ * d_des_r[k / r_group] (r_group > 0; r_group == 0: d_des_r[0] / des_r like bx_lrf). */
+int bx_lrf_batched(const float *patches, int K, int P, float des_r, const float *d_des_r, int r_group, int flags, float *delta,
+                   float *Rt, float *rand_axis, void *stream);
 
 /* ---- a6+a7: spherical-voxel transformer + point layer ---------------------------------------
  * Replaces MiniSpinNet.SPT (models/patch_embedder.py:150-165: get_voxel_coordinate,
