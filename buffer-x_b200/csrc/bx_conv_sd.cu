@@ -42,6 +42,23 @@
 
 namespace {
 
+// -DBX_TC_TRACE builds (BX_BUILD_TRACE=1): where the MMA warp and one epilogue warp of the middle CTA spend their cycles
+// (BX_SD_TRACE=<nchunks*1000+Cout> prints the split once per process): [0] MMA warp total, [1] waiting for A chunks, [2] for a
+// free accumulator set, [3] for weights, [4] for the cross accumulator, [5] epilogue warp 0 total, [6] waiting for segments,
+// [7] storing tiles.
+#ifdef BX_TC_TRACE
+__device__ unsigned long long g_sd_trace[8];
+#define SD_TR_DECL long long tr_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long t_ = 0; const bool tron_ = blockIdx.x == gridDim.x / 2
+#define SD_TR_T0() do { if (tron_) t_ = clock64(); } while (0)
+#define SD_TR_ADD(i) do { if (tron_) tr_[i] += clock64() - t_; } while (0)
+#define SD_TR_OUT(i) do { if (tron_ && lane == 0) g_sd_trace[i] = (unsigned long long)tr_[i]; } while (0)
+#else
+#define SD_TR_DECL
+#define SD_TR_T0()
+#define SD_TR_ADD(i)
+#define SD_TR_OUT(i)
+#endif
+
 constexpr int SD_BM = 128;                       // GEMM rows per tile
 constexpr int SD_AROWS = 176;                    // tile rows + halo (2*22 + 2 = 46 -> 48)
 constexpr int SD_SROWS = 176;                    // padded rows per sample (8 x 22)
@@ -66,11 +83,21 @@ struct ConvSdParams {
     const __half *in_sd;       // IN_SD: presplit padded input  [nchunks][split,kcore (4)][rows_in][8 x fp16]
     __half *out_sd;            // OUT_SD: presplit padded output [Cout/16][4][rows_out][8 x fp16] = the next layer's in_sd
     long long rows_in, rows_out;
+    int nbs;                   // weight ring length in super-stages (<= SD_MAXNBS); resident: == nchunks * 3, every stage is loaded once
+    int resident;              // the whole weight image stays in shared memory (fits for Cin * Cout <= 64 * 64): no re-streaming per tile
+    int stagger;               // experiment (BX_SD_STAGGER=<cycles>): CTA b starts (b % 16) * stagger cycles late so the tile stores of the SMs do not coincide
 };
+constexpr int SD_MAXNBS = 12;
 
 // B ring: one bulk copy / one mbarrier per SUPER-STAGE of three taps (the MMA warp's issue loop is the critical resource:
 // every barrier wait costs it ~90 cycles), NBS super-stages deep.
-template <int NT> struct SdRing { static constexpr int SB = 3, NBS = NT == 128 ? 3 : (NT == 64 ? 4 : 6); };   // deeper rings (5 / 8 / 12) measured: no gain
+// Depth: the ring has to cover the L2 -> shared-memory latency of a bulk copy (~1.5-2 k cycles with all SMs streaming) PLUS the
+// time until the MMAs that read a stage have retired (tcgen05.commit): the trace build showed the MMA warp waiting 400-500
+// cycles per chunk for weights with rings of 1.3 chunks (round 2, first half); now two chunks and more.
+#ifndef SD_NBS_MUL
+#define SD_NBS_MUL 2
+#endif
+template <int NT> struct SdRing { static constexpr int SB = 3, NBS = SD_NBS_MUL * (NT == 128 ? 3 : (NT == 64 ? 4 : 6)); };
 
 __device__ __forceinline__ void mma_f16_ss(uint32_t leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -89,64 +116,72 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t leader, uint32_t tmem_d, uin
 }
 
 // One epilogue thread's share of a finished tile: GEMM row R = t * 128 + 32 * quarter + lane, CW consecutive output channels
-// starting at ecs * CW: bias (+ReLU), then either fp32 channel-blocked stores of the valid rows or the presplit images of the
-// next layer (value, wrap-column copies, zero rows).
+// starting at ecs * CW.  `run` already holds bias + sum (the running sums start from the bias); here: ReLU, then either fp32
+// channel-blocked stores of the valid rows or the presplit images of the next layer (value, wrap-column copies, zero rows).
+// The epilogue warps are the kernel's second critical resource (a tile's store used to cost them as long as three of its
+// four chunks take the tensor core): rows that produce nothing skip the arithmetic, the index arithmetic is 32-bit, the
+// image pointers advance by additions.
 template <int CW, int OUT_SD>
 __device__ __forceinline__ void sd_store_tile(const ConvSdParams &p, int t, int quarter, int ecs, int lane, int n_samples, const float (&run)[CW]) {
-    const long long R = (long long)t * SD_BM + quarter * 32 + lane;
-    const int s = (int)(R / p.rs), q = (int)(R - (long long)s * p.rs);
-    const int y = q / p.W, x = q - y * p.W;
-    const bool valid = s < n_samples && y < p.OD && x < p.OW;
-    const int S_out = p.S_out;
-    float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)s * (p.Cout >> 2) + ((ecs * CW) >> 2)) * S_out + (y * p.OW + x);
-    // OUT_SD: this row's value goes to padded row R + 23 (= (y + 1) * 22 + (x + 1)); azimuth 19 / 0 are duplicated into the
-    // wrap columns x' = 0 / 21; the rows that land on a zero row write zeros; everything else is dropped.
-    // (valid-convolution rasters of the cost-volume stack: compact output raster, no padding rows / columns)
-    const bool live = s < n_samples;
-    const bool wz = p.cyl && live && ((y == 7 && x <= 20) || (y == 6 && x == 21));       // zero row of sample s + 1
-    const long long pmain = p.cyl ? R + 23 : (long long)s * p.rs_out + y * p.OW + x;
-    const long long pdup = !p.cyl ? -1 : (x == 19 ? R + 3 : (x == 0 ? R + 43 : -1));
-    float omax = 0.0f;
+    const uint32_t R = (uint32_t)t * SD_BM + (uint32_t)(quarter * 32 + lane);            // host: rows < 2^31
+    const uint32_t s = R / (uint32_t)p.rs, q = R - s * (uint32_t)p.rs;
+    const uint32_t y = q / (uint32_t)p.W, x = q - y * (uint32_t)p.W;
+    const bool live = (int)s < n_samples;
+    const bool valid = live && (int)y < p.OD && (int)x < p.OW;
+    if constexpr (!OUT_SD) {
+        if (!valid) return;
+        const int S_out = p.S_out;
+        float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)s * (p.Cout >> 2) + ((ecs * CW) >> 2)) * S_out + (y * p.OW + x);
 #pragma unroll
-    for (int c0 = 0; c0 < CW; c0 += 32) {
-        if (OUT_SD ? live : valid) {
+        for (int c = 0; c < CW; c += 4) {
+            if (ecs * CW + c < p.Cout) {
+                float r[4];
 #pragma unroll
-            for (int c = 0; c < (CW < 32 ? CW : 32); c += 8) {
-                const int co = ecs * CW + c0 + c;
-                if (co < p.Cout) {
-                    float r[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        r[e] = run[c0 + c + e] + __ldg(p.bias + co + e);
-                        if (p.relu) r[e] = fmaxf(r[e], 0.0f);
-                    }
-                    if (!OUT_SD) {
-                        eo[(size_t)((c0 + c) >> 2) * S_out] = make_float4(r[0], r[1], r[2], r[3]);
-                        eo[(size_t)((c0 + c + 4) >> 2) * S_out] = make_float4(r[4], r[5], r[6], r[7]);
-                    } else {
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float a = valid ? r[2 * e] : 0.0f, b = valid ? r[2 * e + 1] : 0.0f;
-                            const __half2 hh = __floats2half2_rn(a, b);
-                            const float2 hf = __half22float2(hh);
-                            const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
-                            hi[e] = *reinterpret_cast<const uint32_t *>(&hh);
-                            lo[e] = *reinterpret_cast<const uint32_t *>(&ll);
-                            omax = fmaxf(omax, fmaxf(fabsf(a), fabsf(b)));
-                        }
-                        // image (chunk = co / 16, kcore = (co / 8) & 1): [chunk][split][kcore][row][8]
-                        uint4 *img = reinterpret_cast<uint4 *>(p.out_sd) + (size_t)((co >> 4) * 4 + ((co >> 3) & 1)) * p.rows_out;
-                        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        if (valid || wz) { img[pmain] = vh; img[2 * p.rows_out + pmain] = vl; }
-                        if (valid && pdup >= 0) { img[pdup] = vh; img[2 * p.rows_out + pdup] = vl; }
-                        if (p.cyl && R < 22) { const uint4 z = make_uint4(0u, 0u, 0u, 0u); img[R] = z; img[2 * p.rows_out + R] = z; }   // zero row of sample 0
-                    }
-                }
+                for (int e = 0; e < 4; ++e) r[e] = p.relu ? fmaxf(run[c + e], 0.0f) : run[c + e];
+                eo[(size_t)(c >> 2) * S_out] = make_float4(r[0], r[1], r[2], r[3]);
             }
         }
+    } else {
+        // this row's value goes to padded row R + 23 (= (y + 1) * 22 + (x + 1)); azimuth 19 / 0 are duplicated into the wrap
+        // columns x' = 0 / 21; the rows that land on a zero row write zeros; everything else is dropped.
+        // (valid-convolution rasters of the cost-volume stack: compact output raster, no padding rows / columns)
+        const bool wz = p.cyl && live && ((y == 7 && x <= 20) || (y == 6 && x == 21));       // zero row of sample s + 1
+        const bool z0 = p.cyl && R < 22;                                                       // zero row of sample 0
+        if (!valid && !wz && !z0) return;
+        const size_t rows = (size_t)p.rows_out;
+        const size_t pmain = p.cyl ? (size_t)R + 23 : (size_t)s * p.rs_out + y * p.OW + x;
+        const long long pdup = !p.cyl ? -1 : (x == 19 ? (long long)R + 3 : (x == 0 ? (long long)R + 43 : -1));
+        const int co0 = ecs * CW;
+        // image (chunk = co / 16, kcore = (co / 8) & 1): [chunk][split][kcore][row][8]
+        uint4 *img = reinterpret_cast<uint4 *>(p.out_sd) + (size_t)((co0 >> 4) * 4 + ((co0 >> 3) & 1)) * rows;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        float omax = 0.0f;
+#pragma unroll
+        for (int c = 0; c < CW; c += 8) {
+            if (co0 + c < p.Cout) {
+                if (valid) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a = run[c + 2 * e], b = run[c + 2 * e + 1];
+                        if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                        const __half2 hh = __floats2half2_rn(a, b);
+                        const float2 hf = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+                        hi[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                        lo[e] = *reinterpret_cast<const uint32_t *>(&ll);
+                        omax = fmaxf(omax, fmaxf(fabsf(a), fabsf(b)));
+                    }
+                    const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    img[pmain] = vh; img[2 * rows + pmain] = vl;
+                    if (pdup >= 0) { img[pdup] = vh; img[2 * rows + pdup] = vl; }
+                } else if (wz) { img[pmain] = z; img[2 * rows + pmain] = z; }
+                if (z0) { img[R] = z; img[2 * rows + R] = z; }
+            }
+            img += (((co0 + c) >> 3) & 1) ? 3 * rows : rows;         // kcore 0 -> 1: next image; kcore 1 -> next chunk's kcore 0
+        }
+        if (!(omax < 65000.0f) && p.flag) atomicOr(p.flag, 1);
     }
-    if (OUT_SD && !(omax < 65000.0f) && p.flag) atomicOr(p.flag, 1);
 }
 
 // IN_SD = 0: fp32 channel-blocked input converted by the loader warps; 1: presplit padded fp16 images fetched with bulk copies.
@@ -159,17 +194,21 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
     constexpr bool MERGED = NT <= 64;
     constexpr int NE = 4 * ECS, MMA_WARP = NE + SD_NL, WGT_WARP = NE + SD_NL + 1;
     constexpr int CW = NT / ECS;                  // accumulator columns of one epilogue warp
-    constexpr int SB = SdRing<NT>::SB, NBS = SdRing<NT>::NBS;
+    constexpr int SB = SdRing<NT>::SB;
+    const int NBS = p.nbs;
     constexpr int B_STAGE = 64 * NT;              // [kcore][split][n][16 B]
-    constexpr int TMEM_COLS = 4 * NT;             // MERGED: two sets of [main | cross]; else main[2], cross[2]
+    constexpr int NSETS = MERGED ? 4 : 2;         // accumulator sets in flight: MERGED four [main | cross] pairs (the epilogue warps may lag
+                                                  // three chunks behind the tensor core, e.g. while they store the previous tile); else main[2], cross[2]
+    constexpr int TMEM_COLS = MERGED ? NSETS * 2 * NT : 4 * NT;
     constexpr int MAXNA = 12;
     // barriers
-    constexpr int BAR_AFULL = 0, BAR_AEMPTY = MAXNA, BAR_BFULL = 2 * MAXNA, BAR_BEMPTY = BAR_BFULL + NBS;
-    constexpr int BAR_SEGDONE = BAR_BEMPTY + NBS, BAR_ACCFREE = BAR_SEGDONE + 2, BAR_XDONE = BAR_ACCFREE + 2, BAR_XFREE = BAR_XDONE + 2;
+    constexpr int BAR_AFULL = 0, BAR_AEMPTY = MAXNA, BAR_BFULL = 2 * MAXNA, BAR_BEMPTY = BAR_BFULL + SD_MAXNBS;
+    constexpr int BAR_SEGDONE = BAR_BEMPTY + SD_MAXNBS, BAR_ACCFREE = BAR_SEGDONE + 4, BAR_XDONE = BAR_ACCFREE + 4, BAR_XFREE = BAR_XDONE + 2;
     constexpr int NBARS = BAR_XFREE + 2;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[NBARS];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_s[128];        // the running sums of a tile start from the bias
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NA = p.NA, nchunks = p.nchunks;
@@ -187,18 +226,21 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
             mbar_init(smem_u32(&bars[BAR_AFULL + s]), IN_SD ? 1 : SD_NL);
             mbar_init(smem_u32(&bars[BAR_AEMPTY + s]), 1);
         }
-        for (int s = 0; s < NBS; ++s) {
+        for (int s = 0; s < SD_MAXNBS; ++s) {
             mbar_init(smem_u32(&bars[BAR_BFULL + s]), 1);
             mbar_init(smem_u32(&bars[BAR_BEMPTY + s]), 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 4; ++s) {
             mbar_init(smem_u32(&bars[BAR_SEGDONE + s]), 1);
             mbar_init(smem_u32(&bars[BAR_ACCFREE + s]), NE);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&bars[BAR_XDONE + s]), 1);
             mbar_init(smem_u32(&bars[BAR_XFREE + s]), NE);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < 128) bias_s[threadIdx.x] = (int)threadIdx.x < p.Cout ? __ldg(p.bias + threadIdx.x) : 0.0f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -214,12 +256,21 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
         const uint32_t tm_lane = (uint32_t)(quarter * 32) << 16;
         float run[CW];
         int seg = 0, k = 0;
+        SD_TR_DECL;
+#ifdef BX_TC_TRACE
+        const long long te0_ = clock64();
+#endif
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
 #pragma unroll
-            for (int c = 0; c < CW; ++c) run[c] = 0.0f;
+            for (int c = 0; c < CW; c += 4) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[ecs * CW + c]);
+                run[c] = b4.x; run[c + 1] = b4.y; run[c + 2] = b4.z; run[c + 3] = b4.w;
+            }
             for (int jj = 0; jj < nseg; ++jj, ++seg) {
-                const int set = seg & 1;
-                mbar_wait(bar_base + 8u * (BAR_SEGDONE + set), (uint32_t)((seg >> 1) & 1));
+                const int set = seg & (NSETS - 1);
+                SD_TR_T0();
+                mbar_wait(bar_base + 8u * (BAR_SEGDONE + set), (uint32_t)((seg / NSETS) & 1));
+                SD_TR_ADD(6);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int c0 = 0; c0 < CW; c0 += 32) {
@@ -258,8 +309,13 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_XFREE + xset));
             }
+            SD_TR_T0();
             sd_store_tile<CW, OUT_SD>(p, t, quarter, ecs, lane, n_samples, run);
+            SD_TR_ADD(7);
         }
+#ifdef BX_TC_TRACE
+        if (warp == 0) { tr_[5] = clock64() - te0_; SD_TR_OUT(5); SD_TR_OUT(6); SD_TR_OUT(7); }
+#endif
     } else if (warp < NE + SD_NL) {
         if (IN_SD) {
             // =========================== A producer: presplit images by bulk copy =================================
@@ -397,6 +453,7 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
             int q = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
                 for (int ss = 0; ss < n_super; ++ss, ++q) {
+                    if (p.resident && q >= n_super) break;            // resident weights: loaded by the first tile, never again
                     const int sb = q % NBS;
                     const uint32_t useb = (uint32_t)(q / NBS);
                     if (useb > 0) mbar_wait(bar_base + 8u * (BAR_BEMPTY + sb), (useb - 1) & 1);
@@ -426,23 +483,40 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
         const int Wrow = p.W;                                              // tap (g, tt) reads rows R + g * W + tt
         const uint32_t shift_on = (p.dbg & 4) ? 0u : 1u;                   // BX_SD_DBG=4: every tap reads the unshifted (128-byte aligned) view (timing experiment)
         uint32_t slot = 0, a_par = 0, sbq = 0, b_par = 0, seg = 0, k = 0;
+        if (p.stagger > 0) {
+            const long long ts = clock64(), wait = (long long)(blockIdx.x & 15) * p.stagger;
+            while (clock64() - ts < wait) { }
+        }
+        SD_TR_DECL;
+#ifdef BX_TC_TRACE
+        const long long tm0_ = clock64();
+#endif
+        const bool resident = p.resident != 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
             const uint32_t xset = k & 1;
             if (!MERGED && k >= 2) {
+                SD_TR_T0();
                 mbar_wait(bar_base + 8u * (BAR_XFREE + xset), ((k >> 1) - 1) & 1);
+                SD_TR_ADD(4);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const uint32_t d_cross = tmem_base + (2u * NT + xset * NT);
             for (int c = 0; c < nchunks; ++c) {
-                const uint32_t set = seg & 1;
+                const uint32_t set = seg & (uint32_t)(NSETS - 1);
+                SD_TR_T0();
                 mbar_wait(bar_base + 8u * (BAR_AFULL + slot), a_par);
-                if (seg >= 2) mbar_wait(bar_base + 8u * (BAR_ACCFREE + set), ((seg >> 1) - 1) & 1);
+                SD_TR_ADD(1);
+                SD_TR_T0();
+                if (seg >= (uint32_t)NSETS) mbar_wait(bar_base + 8u * (BAR_ACCFREE + set), ((seg / NSETS) - 1) & 1);
+                SD_TR_ADD(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ac = a0 + slot * A_CHUNK16;
                 const uint32_t d_set = tmem_base + set * (2u * NT);      // [main | cross]
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    mbar_wait(bar_base + 8u * (BAR_BFULL + sbq), b_par);
+                    SD_TR_T0();
+                    if (!resident || k == 0) mbar_wait(bar_base + 8u * (BAR_BFULL + sbq), b_par);
+                    SD_TR_ADD(3);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t bg = b0 + sbq * (3u * B_STAGE16);
 #pragma unroll
@@ -463,8 +537,8 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                             mma_f16_ss(leader, tmem_base + set * NT, ah, bb, DESC_HI, IDESC, (g == 0 && tt == 0) ? 0u : 1u);
                         }
                     }
-                    mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sbq));
-                    if (++sbq == NBS) { sbq = 0; b_par ^= 1u; }
+                    if (!resident) mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sbq));
+                    if (++sbq == (uint32_t)NBS) { sbq = 0; b_par ^= 1u; }
                 }
                 mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + set));
                 mma_commit(leader, bar_base + 8u * (BAR_AEMPTY + slot));     // the chunk's MMAs have read the slot
@@ -473,6 +547,9 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
             }
             if (!MERGED) mma_commit(leader, bar_base + 8u * (BAR_XDONE + xset));
         }
+#ifdef BX_TC_TRACE
+        tr_[0] = clock64() - tm0_; SD_TR_OUT(0); SD_TR_OUT(1); SD_TR_OUT(2); SD_TR_OUT(3); SD_TR_OUT(4);
+#endif
         __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -509,6 +586,7 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[NBARS];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_s[128];        // the running sums of a tile start from the bias
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NA = p.NA, nchunks = p.nchunks;
@@ -537,6 +615,7 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < 128) bias_s[threadIdx.x] = (int)threadIdx.x < p.Cout ? __ldg(p.bias + threadIdx.x) : 0.0f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -554,13 +633,22 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
         const uint32_t d_cross0 = tmem_base + tm_lane + (uint32_t)(MERGED ? u * 4 * NT + NT : 2 * NT + u * NT) + (uint32_t)(ecs * CW);
         float run[CW];
         uint32_t seg = 0, k = 0;
+        SD_TR_DECL;
+#ifdef BX_TC_TRACE
+        const long long te0_ = clock64();
+#endif
         for (int m = blockIdx.x; m < n_macro; m += gridDim.x, ++k) {
 #pragma unroll
-            for (int c = 0; c < CW; ++c) run[c] = 0.0f;
+            for (int c = 0; c < CW; c += 4) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[ecs * CW + c]);
+                run[c] = b4.x; run[c + 1] = b4.y; run[c + 2] = b4.z; run[c + 3] = b4.w;
+            }
             for (int c = 0; c < nchunks; ++c, ++seg) {
                 const uint32_t sp = NSET == 2 ? (seg & 1u) : 0u;                 // which of the tile's sets this segment used
                 const uint32_t bidx = (uint32_t)u * 2u + sp;
+                SD_TR_T0();
                 mbar_wait(bar_base + 8u * (BAR_SEGDONE + bidx), (NSET == 2 ? (seg >> 1) : seg) & 1u);
+                SD_TR_ADD(6);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_main = d_main0 + sp * (2u * NT), d_cross = d_cross0 + sp * (2u * NT);
 #pragma unroll
@@ -601,8 +689,13 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
                 if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_XFREE + u));
             }
             const int t = 2 * m + u;
+            SD_TR_T0();
             if (t < n_tiles) sd_store_tile<CW, OUT_SD>(p, t, quarter, ecs, lane, n_samples, run);
+            SD_TR_ADD(7);
         }
+#ifdef BX_TC_TRACE
+        if (warp == 0) { tr_[5] = clock64() - te0_; SD_TR_OUT(5); SD_TR_OUT(6); SD_TR_OUT(7); }
+#endif
     } else if (warp == APROD_WARP) {
         // =========================== A producer: chunk c of tile 0, chunk c of tile 1, chunk c + 1 of tile 0, ... ==========
         if (lane == 0) {
@@ -649,17 +742,29 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
         const uint32_t leader = elect_leader();
         const uint32_t a0 = (a_base >> 4) | A_LBO, b0 = (b_base >> 4) | B_LBO;
         uint32_t slot = 0, a_par = 0, q = 0, seg = 0, k = 0;      // seg: segments finished per tile (same for both tiles)
+        SD_TR_DECL;
+#ifdef BX_TC_TRACE
+        const long long tm0_ = clock64();
+#endif
         for (int m = blockIdx.x; m < n_macro; m += gridDim.x, ++k) {
             for (int c = 0; c < nchunks; ++c, ++q, ++seg) {
                 const uint32_t sb = q & 1u;
+                SD_TR_T0();
                 mbar_wait(bar_base + 8u * (BAR_BFULL + sb), (q >> 1) & 1u);
+                SD_TR_ADD(3);
                 const uint32_t bg = b0 + sb * B_CHUNK16;
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
+                    SD_TR_T0();
                     mbar_wait(bar_base + 8u * (BAR_AFULL + slot), a_par);
+                    SD_TR_ADD(1);
                     const uint32_t sp = NSET == 2 ? (seg & 1u) : 0u, bidx = (uint32_t)u * 2u + sp;
+                    SD_TR_T0();
                     if (seg >= (uint32_t)NSET) mbar_wait(bar_base + 8u * (BAR_ACCFREE + bidx), (NSET == 2 ? ((seg >> 1) - 1) : (seg - 1)) & 1u);
+                    SD_TR_ADD(2);
+                    SD_TR_T0();
                     if (!MERGED && c == 0 && k >= 1) mbar_wait(bar_base + 8u * (BAR_XFREE + u), (k - 1) & 1u);
+                    SD_TR_ADD(4);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t ac = a0 + slot * A_CHUNK16;
                     const uint32_t d_set = tmem_base + (MERGED ? ((uint32_t)u * 2u + sp) * (2u * NT) : (uint32_t)u * NT);
@@ -686,6 +791,9 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
                 mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sb));
             }
         }
+#ifdef BX_TC_TRACE
+        tr_[0] = clock64() - tm0_; SD_TR_OUT(0); SD_TR_OUT(1); SD_TR_OUT(2); SD_TR_OUT(3); SD_TR_OUT(4);
+#endif
         __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -694,6 +802,29 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
+
+#ifdef BX_TC_TRACE
+static void sd_trace_print(const ConvSdParams &p, const char *kern, int n_tiles, cudaStream_t st) {
+    static int want = -2, seen[32][2], nseen = 0;    // BX_SD_TRACE=1: every layer shape, at its third launch
+    if (want == -2) { const char *e = getenv("BX_SD_TRACE"); want = e ? atoi(e) : -1; }
+    if (want < 0) return;
+    const int key = p.nchunks * 1000 + p.Cout;
+    int i = 0;
+    while (i < nseen && seen[i][0] != key) ++i;
+    if (i == nseen) { if (nseen == 32) return; seen[nseen][0] = key; seen[nseen++][1] = 0; }
+    if (++seen[i][1] != 3) return;
+    cudaStreamSynchronize(st);
+    unsigned long long h[8];
+    cudaMemcpyFromSymbol(h, g_sd_trace, sizeof(h));
+    const double tiles = (n_tiles + 147) / 148, per = tiles * p.nchunks;
+    printf("[sd trace] %s nchunks %d Cout %d: per chunk-tile  MMA warp %.0f cyc = wait A %.0f + wait acc %.0f + wait W %.0f + wait cross %.0f + issue %.0f | "
+           "epilogue warp %.0f = wait seg %.0f + store %.0f + drain %.0f\n", kern, p.nchunks, p.Cout, h[0] / per, h[1] / per, h[2] / per, h[3] / per, h[4] / per,
+           (h[0] - h[1] - h[2] - h[3] - h[4]) / per, h[5] / per, h[6] / per, h[7] / per, (h[5] - h[6] - h[7]) / per);
+    fflush(stdout);
+}
+#else
+static inline void sd_trace_print(const ConvSdParams &, const char *, int, cudaStream_t) {}
+#endif
 
 template <int NT, int OUT_SD>
 int launch_sd2(ConvSdParams p, cudaStream_t st) {
@@ -712,12 +843,22 @@ int launch_sd2(ConvSdParams p, cudaStream_t st) {
     const int grid = n_macro < sms ? n_macro : sms;
     conv_sd2_kernel<NT, OUT_SD><<<grid, 19 * 32, smem, st>>>(p);
     BX_LAUNCH_CHECK();
+    sd_trace_print(p, "conv_sd2", p.n_tiles, st);
     return BX_OK;
 }
 
 template <int NT, int ECS, int IN_SD, int OUT_SD>
 int launch_sd(ConvSdParams p, cudaStream_t st) {
-    constexpr int B_RING = SdRing<NT>::SB * SdRing<NT>::NBS * 64 * NT;
+    // the whole weight image resident in shared memory when it leaves room for >= 6 A chunks (Cin * Cout <= 64 * 64: 144 KB),
+    // else a ring of SdRing<NT>::NBS super-stages of three taps
+    constexpr int B_SUPER = SdRing<NT>::SB * 64 * NT;
+    static int res_mode = -1;      // BX_SD_RESIDENT=0 disables (A/B switch)
+    if (res_mode < 0) { const char *e = getenv("BX_SD_RESIDENT"); res_mode = e ? atoi(e) : 1; }
+    const int n_super = p.nchunks * 3;
+    p.resident = res_mode && n_super <= SD_MAXNBS && (227 * 1024 - 1024 - n_super * B_SUPER) / SD_CHUNK >= 6;
+    p.nbs = p.resident ? n_super : (SdRing<NT>::NBS < SD_MAXNBS ? SdRing<NT>::NBS : SD_MAXNBS);
+    { static int stg = -1; if (stg < 0) { const char *e = getenv("BX_SD_STAGGER"); stg = e ? atoi(e) : 0; } p.stagger = stg; }
+    const int B_RING = p.nbs * B_SUPER;
     int na = 2 * p.nchunks;
     const int na_max = (227 * 1024 - 1024 - B_RING) / SD_CHUNK;
     if (na > na_max) na = na_max;
@@ -732,6 +873,7 @@ int launch_sd(ConvSdParams p, cudaStream_t st) {
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
     conv_sd_kernel<NT, ECS, IN_SD, OUT_SD><<<grid, (4 * ECS + SD_NL + 2) * 32, smem, st>>>(p);
     BX_LAUNCH_CHECK();
+    sd_trace_print(p, "conv_sd", p.n_tiles, st);
     return BX_OK;
 }
 
@@ -781,7 +923,7 @@ BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const voi
     }
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("BX_SD_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     const long long rows = (long long)n * p.rs;
-    BX_REQUIRE(rows / SD_BM < 0x7fffffffLL, "bx_conv_layer_sd: too many samples");
+    BX_REQUIRE(rows + 4 * SD_BM < 0x7fffffffLL, "bx_conv_layer_sd: too many samples (raster rows must stay below 2^31)");
     p.n_tiles = (int)((rows + SD_BM - 1) / SD_BM);
     p.rows_in = bx_conv_sd_rows(n, p.rs);
     p.rows_out = bx_conv_sd_rows(n, p.rs_out);
