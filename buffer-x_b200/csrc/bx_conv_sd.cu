@@ -97,7 +97,7 @@ constexpr int SD_MAXNBS = 12;
 #ifndef SD_NBS_MUL
 #define SD_NBS_MUL 2
 #endif
-template <int NT> struct SdRing { static constexpr int SB = 3, NBS = SD_NBS_MUL * (NT == 128 ? 3 : (NT == 64 ? 4 : 6)); };
+template <int NT> struct SdRing { static constexpr int SB = 3, NBS = NT == 128 ? 3 * SD_NBS_MUL : 12; };
 
 __device__ __forceinline__ void mma_f16_ss(uint32_t leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -121,9 +121,9 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t leader, uint32_t tmem_d, uin
 // The epilogue warps are the kernel's second critical resource (a tile's store used to cost them as long as three of its
 // four chunks take the tensor core): rows that produce nothing skip the arithmetic, the index arithmetic is 32-bit, the
 // image pointers advance by additions.
-template <int CW, int OUT_SD>
-__device__ __forceinline__ void sd_store_tile(const ConvSdParams &p, int t, int quarter, int ecs, int lane, int n_samples, const float (&run)[CW]) {
-    const uint32_t R = (uint32_t)t * SD_BM + (uint32_t)(quarter * 32 + lane);            // host: rows < 2^31
+template <int CW, int OUT_SD, class Get8>
+__device__ __forceinline__ void sd_store_rows(const ConvSdParams &p, int t, int row, int co0, int n_samples, Get8 get8) {
+    const uint32_t R = (uint32_t)t * SD_BM + (uint32_t)row;            // host: rows < 2^31
     const uint32_t s = R / (uint32_t)p.rs, q = R - s * (uint32_t)p.rs;
     const uint32_t y = q / (uint32_t)p.W, x = q - y * (uint32_t)p.W;
     const bool live = (int)s < n_samples;
@@ -131,15 +131,15 @@ __device__ __forceinline__ void sd_store_tile(const ConvSdParams &p, int t, int 
     if constexpr (!OUT_SD) {
         if (!valid) return;
         const int S_out = p.S_out;
-        float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)s * (p.Cout >> 2) + ((ecs * CW) >> 2)) * S_out + (y * p.OW + x);
+        float4 *eo = reinterpret_cast<float4 *>(p.out) + ((size_t)s * (p.Cout >> 2) + (co0 >> 2)) * S_out + (y * p.OW + x);
 #pragma unroll
-        for (int c = 0; c < CW; c += 4) {
-            if (ecs * CW + c < p.Cout) {
-                float r[4];
+        for (int c = 0; c < CW; c += 8) {
+            float r[8];
+            get8(c, r);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) r[e] = p.relu ? fmaxf(run[c + e], 0.0f) : run[c + e];
-                eo[(size_t)(c >> 2) * S_out] = make_float4(r[0], r[1], r[2], r[3]);
-            }
+            for (int e = 0; e < 8; ++e) r[e] = p.relu ? fmaxf(r[e], 0.0f) : r[e];
+            if (co0 + c < p.Cout) eo[(size_t)(c >> 2) * S_out] = make_float4(r[0], r[1], r[2], r[3]);
+            if (co0 + c + 4 < p.Cout) eo[(size_t)((c >> 2) + 1) * S_out] = make_float4(r[4], r[5], r[6], r[7]);
         }
     } else {
         // this row's value goes to padded row R + 23 (= (y + 1) * 22 + (x + 1)); azimuth 19 / 0 are duplicated into the wrap
@@ -151,7 +151,6 @@ __device__ __forceinline__ void sd_store_tile(const ConvSdParams &p, int t, int 
         const size_t rows = (size_t)p.rows_out;
         const size_t pmain = p.cyl ? (size_t)R + 23 : (size_t)s * p.rs_out + y * p.OW + x;
         const long long pdup = !p.cyl ? -1 : (x == 19 ? (long long)R + 3 : (x == 0 ? (long long)R + 43 : -1));
-        const int co0 = ecs * CW;
         // image (chunk = co / 16, kcore = (co / 8) & 1): [chunk][split][kcore][row][8]
         uint4 *img = reinterpret_cast<uint4 *>(p.out_sd) + (size_t)((co0 >> 4) * 4 + ((co0 >> 3) & 1)) * rows;
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -160,10 +159,12 @@ __device__ __forceinline__ void sd_store_tile(const ConvSdParams &p, int t, int 
         for (int c = 0; c < CW; c += 8) {
             if (co0 + c < p.Cout) {
                 if (valid) {
+                    float r[8];
+                    get8(c, r);
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float a = run[c + 2 * e], b = run[c + 2 * e + 1];
+                        float a = r[2 * e], b = r[2 * e + 1];
                         if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
                         const __half2 hh = __floats2half2_rn(a, b);
                         const float2 hf = __half22float2(hh);
@@ -184,15 +185,39 @@ __device__ __forceinline__ void sd_store_tile(const ConvSdParams &p, int t, int 
     }
 }
 
+// the epilogue warps' own store: values from their running sums
+template <int CW, int OUT_SD>
+__device__ __forceinline__ void sd_store_tile(const ConvSdParams &p, int t, int quarter, int ecs, int lane, int n_samples, const float (&run)[CW]) {
+    sd_store_rows<CW, OUT_SD>(p, t, quarter * 32 + lane, ecs * CW, n_samples, [&](int c, float (&r)[8]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = run[c + e];
+    });
+}
+
 // IN_SD = 0: fp32 channel-blocked input converted by the loader warps; 1: presplit padded fp16 images fetched with bulk copies.
 // OUT_SD = 0: fp32 channel-blocked output; 1: presplit padded fp16 images (zero rows and wrap columns written here).
 // MERGED (NT <= 64): per tap ah * [bh | bl] as ONE N = 2*NT instruction into [main | cross] + al * bh; both halves are cut
 // and drained per segment.  NT = 128 (N = 256 instructions and twice the drain traffic measured 5 % SLOWER there): three
 // N = 128 instructions per tap, main ping-pong per segment, cross accumulators one chain per tile (ping-pong by tile).
+// STAGED (presplit in and out, the descriptor stack's layer-to-layer case): the epilogue warps only park a finished tile
+// (bias + sum, fp32) in a shared-memory staging buffer and go back to draining; four STORER warps do ReLU, the fp16 split
+// and the global stores (values, wrap copies, zero rows) while the next tile is computed.  Measured before: the store took the
+// epilogue warps 2600 (Cout 64) / 5200 (Cout 128) cycles per tile, mostly waiting for the LSU, and the tensor core stalled on
+// accumulator sets meanwhile.
+template <int NT, int IN_SD, int OUT_SD> struct SdRoles {
+    static constexpr bool STAGED = IN_SD && OUT_SD;
+    static constexpr int NST = 4;          // storer warps, one tile row per thread.  Eight (two per row, half the channels each: 19 warps, 107 registers)
+                                           // measured 15-25 % SLOWER on the Cout 64 layers
+    static constexpr int NLW = STAGED ? 1 + NST : SD_NL;
+};
+
 template <int NT, int ECS, int IN_SD, int OUT_SD>
-__global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(const ConvSdParams p) {
+__global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2) * 32, 1) conv_sd_kernel(const ConvSdParams p) {
     constexpr bool MERGED = NT <= 64;
-    constexpr int NE = 4 * ECS, MMA_WARP = NE + SD_NL, WGT_WARP = NE + SD_NL + 1;
+    constexpr bool STAGED = SdRoles<NT, IN_SD, OUT_SD>::STAGED;
+    constexpr int NLW = SdRoles<NT, IN_SD, OUT_SD>::NLW;       // warps between the epilogue warps and the MMA warp: loaders, or A producer + storers
+    constexpr int NST = SdRoles<NT, IN_SD, OUT_SD>::NST;
+    constexpr int NE = 4 * ECS, MMA_WARP = NE + NLW, WGT_WARP = NE + NLW + 1;
     constexpr int CW = NT / ECS;                  // accumulator columns of one epilogue warp
     constexpr int SB = SdRing<NT>::SB;
     const int NBS = p.nbs;
@@ -204,7 +229,8 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
     // barriers
     constexpr int BAR_AFULL = 0, BAR_AEMPTY = MAXNA, BAR_BFULL = 2 * MAXNA, BAR_BEMPTY = BAR_BFULL + SD_MAXNBS;
     constexpr int BAR_SEGDONE = BAR_BEMPTY + SD_MAXNBS, BAR_ACCFREE = BAR_SEGDONE + 4, BAR_XDONE = BAR_ACCFREE + 4, BAR_XFREE = BAR_XDONE + 2;
-    constexpr int NBARS = BAR_XFREE + 2;
+    constexpr int BAR_STAGED = BAR_XFREE + 2, BAR_STFREE = BAR_STAGED + 1;
+    constexpr int NBARS = BAR_STFREE + 1;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[NBARS];
     __shared__ uint32_t tmem_base_s;
@@ -215,6 +241,8 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
     const int n_samples = p.d_n ? min(*p.d_n, p.n) : p.n;
     const int n_tiles = (int)(((long long)n_samples * p.rs + SD_BM - 1) / SD_BM);   // <= the host's bound the grid was sized for
     const int n_stages = nchunks * 9;
+    // staging buffer of one finished tile, fp32 [NT / 4][128 rows][4]: behind the A and B rings
+    float4 *const stage = reinterpret_cast<float4 *>(smem + (size_t)NA * SD_CHUNK + (size_t)p.nbs * SdRing<NT>::SB * 64 * NT);
     const int nseg = nchunks;                    // one accumulator segment per 16-channel chunk (nine main MMAs, K = 144)
 
     if (warp == MMA_WARP) {
@@ -238,6 +266,8 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
             mbar_init(smem_u32(&bars[BAR_XDONE + s]), 1);
             mbar_init(smem_u32(&bars[BAR_XFREE + s]), NE);
         }
+        mbar_init(smem_u32(&bars[BAR_STAGED]), NE);
+        mbar_init(smem_u32(&bars[BAR_STFREE]), NST);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 128) bias_s[threadIdx.x] = (int)threadIdx.x < p.Cout ? __ldg(p.bias + threadIdx.x) : 0.0f;
@@ -250,7 +280,21 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
     uint32_t bar_base = smem_u32(&bars[0]);
     asm volatile("" : "+r"(tmem_base), "+r"(a_base), "+r"(b_base), "+r"(bar_base));
 
-    if (warp < NE) {
+    if (STAGED && warp > NE && warp < NE + NLW) {
+        // =========================== storers: staged tile -> ReLU, fp16 split, global stores ========================
+        constexpr int SCW = NT * 4 / NST;                            // channels per storer thread
+        const int sw = warp - NE - 1, row = (sw & 3) * 32 + lane, sc0 = (sw >> 2) * SCW;
+        uint32_t k = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+            mbar_wait(bar_base + 8u * BAR_STAGED, k & 1u);
+            sd_store_rows<SCW, OUT_SD>(p, t, row, sc0, n_samples, [&](int c, float (&r)[8]) {
+                const float4 u0 = stage[((sc0 + c) >> 2) * SD_BM + row], u1 = stage[(((sc0 + c) >> 2) + 1) * SD_BM + row];
+                r[0] = u0.x; r[1] = u0.y; r[2] = u0.z; r[3] = u0.w; r[4] = u1.x; r[5] = u1.y; r[6] = u1.z; r[7] = u1.w;
+            });
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_base + 8u * BAR_STFREE);
+        }
+    } else if (warp < NE) {
         // =========================== epilogue: segment drains, bias, ReLU, stores ==========================
         const int quarter = warp & 3, ecs = warp >> 2;
         const uint32_t tm_lane = (uint32_t)(quarter * 32) << 16;
@@ -310,13 +354,22 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                 if (lane == 0) mbar_arrive(bar_base + 8u * (BAR_XFREE + xset));
             }
             SD_TR_T0();
-            sd_store_tile<CW, OUT_SD>(p, t, quarter, ecs, lane, n_samples, run);
+            if constexpr (STAGED) {
+                if (k >= 1) mbar_wait(bar_base + 8u * BAR_STFREE, (uint32_t)((k - 1) & 1));      // the storers have read the previous tile
+#pragma unroll
+                for (int c = 0; c < CW; c += 4)
+                    stage[((ecs * CW + c) >> 2) * SD_BM + quarter * 32 + lane] = make_float4(run[c], run[c + 1], run[c + 2], run[c + 3]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + 8u * BAR_STAGED);
+            } else {
+                sd_store_tile<CW, OUT_SD>(p, t, quarter, ecs, lane, n_samples, run);
+            }
             SD_TR_ADD(7);
         }
 #ifdef BX_TC_TRACE
         if (warp == 0) { tr_[5] = clock64() - te0_; SD_TR_OUT(5); SD_TR_OUT(6); SD_TR_OUT(7); }
 #endif
-    } else if (warp < NE + SD_NL) {
+    } else if (warp < NE + NLW) {
         if (IN_SD) {
             // =========================== A producer: presplit images by bulk copy =================================
             // A chunk's four (split, kcore) images are four contiguous 2816-byte runs of the previous layer's output: one
@@ -492,6 +545,10 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
         const long long tm0_ = clock64();
 #endif
         const bool resident = p.resident != 0;
+        // look-ahead probes (mbar_test): the barrier the NEXT step needs is tested before this step's MMAs are issued
+        const uint32_t probe = (p.dbg & 8) ? 0u : 1u;         // BX_SD_DBG=8: blocking waits only (A/B switch)
+        uint32_t pa = probe & mbar_test(bar_base + 8u * (BAR_AFULL + slot), a_par), pc = 1u;
+        uint32_t pb = probe & mbar_test(bar_base + 8u * (BAR_BFULL + sbq), b_par);
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
             const uint32_t xset = k & 1;
             if (!MERGED && k >= 2) {
@@ -501,24 +558,37 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const uint32_t d_cross = tmem_base + (2u * NT + xset * NT);
+            const bool wait_b = !resident || k == 0;
             for (int c = 0; c < nchunks; ++c) {
                 const uint32_t set = seg & (uint32_t)(NSETS - 1);
                 SD_TR_T0();
-                mbar_wait(bar_base + 8u * (BAR_AFULL + slot), a_par);
+                if (!pa) mbar_wait(bar_base + 8u * (BAR_AFULL + slot), a_par);
                 SD_TR_ADD(1);
                 SD_TR_T0();
-                if (seg >= (uint32_t)NSETS) mbar_wait(bar_base + 8u * (BAR_ACCFREE + set), ((seg / NSETS) - 1) & 1);
+                if (!pc) mbar_wait(bar_base + 8u * (BAR_ACCFREE + set), ((seg / NSETS) - 1) & 1);
                 SD_TR_ADD(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ac = a0 + slot * A_CHUNK16;
                 const uint32_t d_set = tmem_base + set * (2u * NT);      // [main | cross]
+                // the next chunk's A slot and accumulator set
+                uint32_t slot_n = slot + 1, a_par_n = a_par;
+                if (slot_n == (uint32_t)NA) { slot_n = 0; a_par_n ^= 1u; }
+                const uint32_t seg_n = seg + 1, set_n = seg_n & (uint32_t)(NSETS - 1);
+                uint32_t pa_n = 0u, pc_n = 1u;
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
                     SD_TR_T0();
-                    if (!resident || k == 0) mbar_wait(bar_base + 8u * (BAR_BFULL + sbq), b_par);
+                    if (wait_b && !pb) mbar_wait(bar_base + 8u * (BAR_BFULL + sbq), b_par);
                     SD_TR_ADD(3);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t bg = b0 + sbq * (3u * B_STAGE16);
+                    uint32_t sbq_n = sbq + 1, b_par_n = b_par;
+                    if (sbq_n == (uint32_t)NBS) { sbq_n = 0; b_par_n ^= 1u; }
+                    const uint32_t pb_n = probe & mbar_test(bar_base + 8u * (BAR_BFULL + sbq_n), b_par_n);
+                    if (g == 2) {
+                        pa_n = probe & mbar_test(bar_base + 8u * (BAR_AFULL + slot_n), a_par_n);
+                        if (seg_n >= (uint32_t)NSETS) pc_n = probe & mbar_test(bar_base + 8u * (BAR_ACCFREE + set_n), ((seg_n / NSETS) - 1) & 1);
+                    }
 #pragma unroll
                     for (int tt = 0; tt < 3; ++tt) {
                         const uint32_t ah = ac + shift_on * (uint32_t)(g * Wrow + tt), al = ah + A_SPLIT;    // one row = 16 B = one address unit
@@ -538,12 +608,11 @@ __global__ void __launch_bounds__((4 * ECS + SD_NL + 2) * 32, 1) conv_sd_kernel(
                         }
                     }
                     if (!resident) mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sbq));
-                    if (++sbq == (uint32_t)NBS) { sbq = 0; b_par ^= 1u; }
+                    sbq = sbq_n; b_par = b_par_n; pb = pb_n;
                 }
                 mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + set));
                 mma_commit(leader, bar_base + 8u * (BAR_AEMPTY + slot));     // the chunk's MMAs have read the slot
-                ++seg;
-                if (++slot == (uint32_t)NA) { slot = 0; a_par ^= 1u; }
+                seg = seg_n; slot = slot_n; a_par = a_par_n; pa = pa_n; pc = pc_n;
             }
             if (!MERGED) mma_commit(leader, bar_base + 8u * (BAR_XDONE + xset));
         }
@@ -746,21 +815,26 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
 #ifdef BX_TC_TRACE
         const long long tm0_ = clock64();
 #endif
+        // look-ahead probes (mbar_test): the barriers of the NEXT step are tested before this step's MMAs are issued
+        const uint32_t probe = (p.dbg & 16) ? 1u : 0u;       // measured: the look-ahead probes do not pay here (A chunks arrive just in time: a failed probe + wait costs more)
+        uint32_t pa = probe & mbar_test(bar_base + 8u * (BAR_AFULL + slot), a_par), pc = probe;
+        uint32_t pb = probe & mbar_test(bar_base + 8u * BAR_BFULL, 0u);
         for (int m = blockIdx.x; m < n_macro; m += gridDim.x, ++k) {
             for (int c = 0; c < nchunks; ++c, ++q, ++seg) {
                 const uint32_t sb = q & 1u;
                 SD_TR_T0();
-                mbar_wait(bar_base + 8u * (BAR_BFULL + sb), (q >> 1) & 1u);
+                if (!pb) mbar_wait(bar_base + 8u * (BAR_BFULL + sb), (q >> 1) & 1u);
+                pb = 0u;
                 SD_TR_ADD(3);
                 const uint32_t bg = b0 + sb * B_CHUNK16;
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     SD_TR_T0();
-                    mbar_wait(bar_base + 8u * (BAR_AFULL + slot), a_par);
+                    if (!pa) mbar_wait(bar_base + 8u * (BAR_AFULL + slot), a_par);
                     SD_TR_ADD(1);
                     const uint32_t sp = NSET == 2 ? (seg & 1u) : 0u, bidx = (uint32_t)u * 2u + sp;
                     SD_TR_T0();
-                    if (seg >= (uint32_t)NSET) mbar_wait(bar_base + 8u * (BAR_ACCFREE + bidx), (NSET == 2 ? ((seg >> 1) - 1) : (seg - 1)) & 1u);
+                    if (!pc && seg >= (uint32_t)NSET) mbar_wait(bar_base + 8u * (BAR_ACCFREE + bidx), (NSET == 2 ? ((seg >> 1) - 1) : (seg - 1)) & 1u);
                     SD_TR_ADD(2);
                     SD_TR_T0();
                     if (!MERGED && c == 0 && k >= 1) mbar_wait(bar_base + 8u * (BAR_XFREE + u), (k - 1) & 1u);
@@ -770,6 +844,17 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
                     const uint32_t d_set = tmem_base + (MERGED ? ((uint32_t)u * 2u + sp) * (2u * NT) : (uint32_t)u * NT);
                     const uint32_t d_cross = tmem_base + (uint32_t)(2 * NT + u * NT);
                     const uint32_t first = c == 0 ? 0u : 1u;
+                    // probes for the next (tile, chunk) step
+                    uint32_t slot_n = slot + 1, a_par_n = a_par;
+                    if (slot_n == (uint32_t)NA) { slot_n = 0; a_par_n ^= 1u; }
+                    uint32_t pa_n = 0u, pc_n = 0u;
+                    if (probe) {
+                        pa_n = mbar_test(bar_base + 8u * (BAR_AFULL + slot_n), a_par_n);
+                        const uint32_t seg_n = u == 0 ? seg : seg + 1u, u_n = u == 0 ? 1u : 0u;
+                        const uint32_t bidx_n = u_n * 2u + (NSET == 2 ? (seg_n & 1u) : 0u);
+                        pc_n = seg_n >= (uint32_t)NSET ? mbar_test(bar_base + 8u * (BAR_ACCFREE + bidx_n), (NSET == 2 ? ((seg_n >> 1) - 1) : (seg_n - 1)) & 1u) : 1u;
+                        if (u == 1) pb = mbar_test(bar_base + 8u * (BAR_BFULL + ((q + 1u) & 1u)), ((q + 1u) >> 1) & 1u);
+                    }
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const uint32_t ah = ac + (uint32_t)((tap / 3) * 22 + (tap % 3)), al = ah + A_SPLIT;
@@ -786,7 +871,7 @@ __global__ void __launch_bounds__(19 * 32, 1) conv_sd2_kernel(const ConvSdParams
                     mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + bidx));
                     mma_commit(leader, bar_base + 8u * (BAR_AEMPTY + slot));
                     if (!MERGED && c == nchunks - 1) mma_commit(leader, bar_base + 8u * (BAR_XDONE + u));
-                    if (++slot == (uint32_t)NA) { slot = 0; a_par ^= 1u; }
+                    slot = slot_n; a_par = a_par_n; pa = pa_n; pc = pc_n;
                 }
                 mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sb));
             }
@@ -831,6 +916,7 @@ int launch_sd2(ConvSdParams p, cudaStream_t st) {
     constexpr int B_RING = 2 * 9 * 64 * NT;
     int na = (227 * 1024 - 1024 - B_RING) / SD_CHUNK;
     if (na > 12) na = 12;
+    { static int cap = -1; if (cap < 0) { const char *e = getenv("BX_SD_NA"); cap = e ? atoi(e) : 0; } if (cap >= 2 && na > cap) na = cap; }
     na &= ~1;                                   // chunks alternate between the two tiles
     p.NA = na;
     const int smem = na * SD_CHUNK + B_RING;
@@ -855,23 +941,26 @@ int launch_sd(ConvSdParams p, cudaStream_t st) {
     static int res_mode = -1;      // BX_SD_RESIDENT=0 disables (A/B switch)
     if (res_mode < 0) { const char *e = getenv("BX_SD_RESIDENT"); res_mode = e ? atoi(e) : 1; }
     const int n_super = p.nchunks * 3;
-    p.resident = res_mode && n_super <= SD_MAXNBS && (227 * 1024 - 1024 - n_super * B_SUPER) / SD_CHUNK >= 6;
+    constexpr int STAGE_BYTES = SdRoles<NT, IN_SD, OUT_SD>::STAGED ? NT * SD_BM * 4 : 0;
+    p.resident = res_mode && n_super <= SD_MAXNBS && (227 * 1024 - 2048 - STAGE_BYTES - n_super * B_SUPER) / SD_CHUNK >= 4;
     p.nbs = p.resident ? n_super : (SdRing<NT>::NBS < SD_MAXNBS ? SdRing<NT>::NBS : SD_MAXNBS);
+    while (!p.resident && p.nbs > 3 && (227 * 1024 - 2048 - STAGE_BYTES - p.nbs * B_SUPER) / SD_CHUNK < 4) --p.nbs;   // leave room for four A chunks
     { static int stg = -1; if (stg < 0) { const char *e = getenv("BX_SD_STAGGER"); stg = e ? atoi(e) : 0; } p.stagger = stg; }
     const int B_RING = p.nbs * B_SUPER;
     int na = 2 * p.nchunks;
-    const int na_max = (227 * 1024 - 1024 - B_RING) / SD_CHUNK;
+    const int na_max = (227 * 1024 - 2048 - STAGE_BYTES - B_RING) / SD_CHUNK;
     if (na > na_max) na = na_max;
     if (na > 12) na = 12;
+    { static int cap = -1; if (cap < 0) { const char *e = getenv("BX_SD_NA"); cap = e ? atoi(e) : 0; } if (cap >= 2 && na > cap) na = cap; }
     p.NA = na;
-    const int smem = na * SD_CHUNK + B_RING;
+    const int smem = na * SD_CHUNK + B_RING + STAGE_BYTES;
     static BxPerDevice attr = {};
     if (bx_needs_attr(attr, (size_t)smem))
         BX_CUDA(cudaFuncSetAttribute(conv_sd_kernel<NT, ECS, IN_SD, OUT_SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int sms = bx_device_sm_count();
     if (sms <= 0) sms = 148;
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-    conv_sd_kernel<NT, ECS, IN_SD, OUT_SD><<<grid, (4 * ECS + SD_NL + 2) * 32, smem, st>>>(p);
+    conv_sd_kernel<NT, ECS, IN_SD, OUT_SD><<<grid, (4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2) * 32, smem, st>>>(p);
     BX_LAUNCH_CHECK();
     sd_trace_print(p, "conv_sd", p.n_tiles, st);
     return BX_OK;
@@ -929,7 +1018,7 @@ BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const voi
     p.rows_out = bx_conv_sd_rows(n, p.rs_out);
     cudaStream_t st = bx_stream(stream);
     static int macro = -1;       // BX_SD_MACRO=0: one 128-row tile per weight pass everywhere (A/B switch, experiments)
-    if (macro < 0) { const char *e = getenv("BX_SD_MACRO"); macro = e ? atoi(e) : 1; }
+    if (macro < 0) { const char *e = getenv("BX_SD_MACRO"); macro = e ? atoi(e) : 0; }
     // Two tiles per weight chunk (conv_sd2_kernel) where it measured faster at K = 9000 patches: 128->128 (1019 -> 980 us) and
     // Cout 32 (64->32: 219 -> 190 us, 32->32: 120 -> 98 us).  64->128 (560 vs 572 us) and the Cout 64 layers (305 vs 323 us, with
     // two accumulator sets per tile) are not: their weight stream is small against the per-tile costs.  BX_SD_MACRO=2 forces

@@ -88,6 +88,23 @@ static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) 
         : "memory");
 }
 
+// Non-blocking probe of a barrier phase (1 = completed).  The MMA warp issues it BEFORE a batch of MMAs and looks at the result
+// after them: a completed mbarrier.try_wait still costs the warp ~100 cycles of round trip, which the batch then hides; only
+// a phase that is not complete falls back to mbar_wait.
+static __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(r)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return r;
+}
+
 // tcgen05.ld 32 lanes x CW consecutive 32-bit columns (CW = 8, 16 or 32) into v[0..CW)
 template <int CW>
 static __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CW]) {
