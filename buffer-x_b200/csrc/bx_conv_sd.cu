@@ -85,6 +85,7 @@ struct ConvSdParams {
     long long rows_in, rows_out;
     int nbs;                   // weight ring length in super-stages (<= SD_MAXNBS); resident: == nchunks * 3, every stage is loaded once
     int resident;              // the whole weight image stays in shared memory (fits for Cin * Cout <= 64 * 64): no re-streaming per tile
+    int wchunk;                // 1: a weight stage is a whole 16-channel chunk (nine taps, one copy / one barrier per chunk); 0: three taps
     int stagger;               // experiment (BX_SD_STAGGER=<cycles>): CTA b starts (b % 16) * stagger cycles late so the tile stores of the SMs do not coincide
 };
 constexpr int SD_MAXNBS = 12;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
     const int n_tiles = (int)(((long long)n_samples * p.rs + SD_BM - 1) / SD_BM);   // <= the host's bound the grid was sized for
     const int n_stages = nchunks * 9;
     // staging buffer of one finished tile, fp32 [NT / 4][128 rows][4]: behind the A and B rings
-    float4 *const stage = reinterpret_cast<float4 *>(smem + (size_t)NA * SD_CHUNK + (size_t)p.nbs * SdRing<NT>::SB * 64 * NT);
+    float4 *const stage = reinterpret_cast<float4 *>(smem + (size_t)NA * SD_CHUNK + (size_t)p.nbs * (p.wchunk ? 9 : SdRing<NT>::SB) * 64 * NT);
     const int nseg = nchunks;                    // one accumulator segment per 16-channel chunk (nine main MMAs, K = 144)
 
     if (warp == MMA_WARP) {
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
     } else if (warp == WGT_WARP) {
         // =========================== weight producer ========================================================
         if (lane == 0) {
-            const int n_super = n_stages / SB;
+            const int n_super = p.wchunk ? nchunks : n_stages / SB;
             int q = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
                 for (int ss = 0; ss < n_super; ++ss, ++q) {
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
                     const int sb = q % NBS;
                     const uint32_t useb = (uint32_t)(q / NBS);
                     if (useb > 0) mbar_wait(bar_base + 8u * (BAR_BEMPTY + sb), (useb - 1) & 1);
-                    constexpr uint32_t bytes = (uint32_t)SB * (uint32_t)B_STAGE;
+                    const uint32_t bytes = (uint32_t)(p.wchunk ? 9 : SB) * (uint32_t)B_STAGE;
                     mbar_arrive_expect_tx(bar_base + 8u * (BAR_BFULL + sb), bytes);
                     bulk_g2s(b_base + (uint32_t)sb * bytes, reinterpret_cast<const unsigned char *>(p.w) + (size_t)ss * bytes, bytes,
                              bar_base + 8u * (BAR_BFULL + sb));
@@ -559,6 +560,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
             }
             const uint32_t d_cross = tmem_base + (2u * NT + xset * NT);
             const bool wait_b = !resident || k == 0;
+            const bool wchunk = p.wchunk != 0;
             for (int c = 0; c < nchunks; ++c) {
                 const uint32_t set = seg & (uint32_t)(NSETS - 1);
                 SD_TR_T0();
@@ -578,13 +580,13 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
                     SD_TR_T0();
-                    if (wait_b && !pb) mbar_wait(bar_base + 8u * (BAR_BFULL + sbq), b_par);
+                    if (wait_b && !pb && (!wchunk || g == 0)) mbar_wait(bar_base + 8u * (BAR_BFULL + sbq), b_par);
                     SD_TR_ADD(3);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t bg = b0 + sbq * (3u * B_STAGE16);
-                    uint32_t sbq_n = sbq + 1, b_par_n = b_par;
-                    if (sbq_n == (uint32_t)NBS) { sbq_n = 0; b_par_n ^= 1u; }
-                    const uint32_t pb_n = probe & mbar_test(bar_base + 8u * (BAR_BFULL + sbq_n), b_par_n);
+                    const uint32_t bg = wchunk ? b0 + sbq * (9u * B_STAGE16) + (uint32_t)g * (3u * B_STAGE16) : b0 + sbq * (3u * B_STAGE16);
+                    uint32_t sbq_n = sbq, b_par_n = b_par;
+                    if (!wchunk || g == 2) { if (++sbq_n == (uint32_t)NBS) { sbq_n = 0; b_par_n ^= 1u; } }
+                    const uint32_t pb_n = (!wchunk || g == 2) ? (probe & mbar_test(bar_base + 8u * (BAR_BFULL + sbq_n), b_par_n)) : 1u;
                     if (g == 2) {
                         pa_n = probe & mbar_test(bar_base + 8u * (BAR_AFULL + slot_n), a_par_n);
                         if (seg_n >= (uint32_t)NSETS) pc_n = probe & mbar_test(bar_base + 8u * (BAR_ACCFREE + set_n), ((seg_n / NSETS) - 1) & 1);
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
                             mma_f16_ss(leader, tmem_base + set * NT, ah, bb, DESC_HI, IDESC, (g == 0 && tt == 0) ? 0u : 1u);
                         }
                     }
-                    if (!resident) mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sbq));
+                    if (!resident && (!wchunk || g == 2)) mma_commit(leader, bar_base + 8u * (BAR_BEMPTY + sbq));
                     sbq = sbq_n; b_par = b_par_n; pb = pb_n;
                 }
                 mma_commit(leader, bar_base + 8u * (BAR_SEGDONE + set));
@@ -945,8 +947,13 @@ int launch_sd(ConvSdParams p, cudaStream_t st) {
     p.resident = res_mode && n_super <= SD_MAXNBS && (227 * 1024 - 2048 - STAGE_BYTES - n_super * B_SUPER) / SD_CHUNK >= 4;
     p.nbs = p.resident ? n_super : (SdRing<NT>::NBS < SD_MAXNBS ? SdRing<NT>::NBS : SD_MAXNBS);
     while (!p.resident && p.nbs > 3 && (227 * 1024 - 2048 - STAGE_BYTES - p.nbs * B_SUPER) / SD_CHUNK < 4) --p.nbs;   // leave room for four A chunks
+    // streamed weights of the narrow layers: whole-chunk stages (one 36 KB copy and one barrier per chunk instead of three of 12 KB)
+    static int wc_mode = -1;
+    if (wc_mode < 0) { const char *e = getenv("BX_SD_WCHUNK"); wc_mode = e ? atoi(e) : 1; }
+    p.wchunk = wc_mode && !p.resident && NT <= 64;
+    if (p.wchunk) { p.nbs /= 3; if (p.nbs > 4) p.nbs = 4; if (p.nbs < 2) p.nbs = 2; }
     { static int stg = -1; if (stg < 0) { const char *e = getenv("BX_SD_STAGGER"); stg = e ? atoi(e) : 0; } p.stagger = stg; }
-    const int B_RING = p.nbs * B_SUPER;
+    const int B_RING = p.nbs * B_SUPER * (p.wchunk ? 3 : 1);
     int na = 2 * p.nchunks;
     const int na_max = (227 * 1024 - 2048 - STAGE_BYTES - B_RING) / SD_CHUNK;
     if (na > na_max) na = na_max;
