@@ -39,14 +39,14 @@ constexpr int SP_SUB = SP_CH / SP_SPLIT;      // points of a chunk scanned by on
 constexpr int SP_STEPS = SP_SUB / 32;         // ballots per warp and chunk
 constexpr int BQ_WARPS = 8;
 
-__global__ void __launch_bounds__(SP_WARPS * 32)
-select_patches_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ kpts, int K, float radius,
-                      const float *__restrict__ d_radius, int P, int *__restrict__ idx, float *__restrict__ patches) {
+__device__ __forceinline__ void select_patches_body(const float4 *__restrict__ pts4, int N, const float *__restrict__ kpts, int K, float radius,
+                                                    const float *__restrict__ d_radius, int P, int *__restrict__ idx, float *__restrict__ patches,
+                                                    int block) {
     __shared__ float4 tile[SP_CH];
     __shared__ int s_cnt[SP_KP][SP_SPLIT], s_first[SP_KP][SP_SPLIT];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kl = warp / SP_SPLIT, part = warp % SP_SPLIT;      // key-point of the CTA, quarter of the chunk
-    const int k = blockIdx.x * SP_KP + kl;
+    const int k = block * SP_KP + kl;
     const bool valid = k < K;
     const int kk = valid ? k : K - 1;
     const float r = d_radius ? *d_radius : radius;
@@ -138,6 +138,31 @@ select_patches_kernel(const float4 *__restrict__ pts4, int N, const float *__res
         out[3 * s + 1] = y;
         out[3 * s + 2] = z;
     }
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+select_patches_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ kpts, int K, float radius,
+                      const float *__restrict__ d_radius, int P, int *__restrict__ idx, float *__restrict__ patches) {
+    select_patches_body(pts4, N, kpts, K, radius, d_radius, P, idx, patches, blockIdx.x);
+}
+
+// All (cloud, scale) key-point sets of a pair in ONE launch: job j = (permuted cloud j, key-points j, device radius j); its
+// patches are rows [koff_j, koff_j + K_j) of one buffer.  Six launches of 375 CTAs (2.5 per SM) become one of 2250.
+constexpr int SP_MAXJOBS = 16;
+struct SpJobs {
+    const float4 *pts4[SP_MAXJOBS];
+    const float *kpts[SP_MAXJOBS];
+    const float *d_radius[SP_MAXJOBS];
+    int N[SP_MAXJOBS], K[SP_MAXJOBS], boff[SP_MAXJOBS + 1], koff[SP_MAXJOBS];
+    int njobs;
+};
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+select_patches_batched_kernel(const SpJobs jobs, int P, float *__restrict__ patches) {
+    int j = 0;
+    while (j + 1 < jobs.njobs && (int)blockIdx.x >= jobs.boff[j + 1]) ++j;
+    select_patches_body(jobs.pts4[j], jobs.N[j], jobs.kpts[j], jobs.K[j], 0.0f, jobs.d_radius[j], P, nullptr,
+                        patches + (size_t)jobs.koff[j] * P * 3, (int)blockIdx.x - jobs.boff[j]);
 }
 
 // ---- segmented form of select_patches (alternative, BX_PATCHES=seg): the same ordered "first P hits", fully parallel ------
@@ -427,6 +452,31 @@ BX_API int bx_select_patches(const float *pts4, int N, const float *kpts, int K,
     if (K == 0) return BX_OK;
     select_patches_kernel<<<(K + SP_KP - 1) / SP_KP, SP_WARPS * 32, 0, bx_stream(stream)>>>(
         reinterpret_cast<const float4 *>(pts4), N, kpts, K, radius, d_radius, P, idx, patches);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
+BX_API int bx_select_patches_batched(int njobs, const void *const *pts4, const int32_t *N, const void *const *kpts, const int32_t *K,
+                                     const void *const *d_radius, int P, float *patches, void *stream) {
+    BX_REQUIRE(pts4 && N && kpts && K && d_radius && patches, "bx_select_patches_batched: null pointer");
+    BX_REQUIRE(njobs >= 1 && njobs <= SP_MAXJOBS && P >= 1, "bx_select_patches_batched: njobs=%d out of range [1,%d]", njobs, SP_MAXJOBS);
+    SpJobs jobs = {};
+    jobs.njobs = njobs;
+    int blocks = 0, koff = 0;
+    for (int j = 0; j < njobs; ++j) {
+        BX_REQUIRE(pts4[j] && kpts[j] && d_radius[j] && N[j] >= 1 && K[j] >= 0, "bx_select_patches_batched: bad job %d", j);
+        BX_REQUIRE((reinterpret_cast<uintptr_t>(pts4[j]) & 15) == 0, "bx_select_patches_batched: pts4 must be 16-byte aligned");
+        jobs.pts4[j] = reinterpret_cast<const float4 *>(pts4[j]);
+        jobs.kpts[j] = reinterpret_cast<const float *>(kpts[j]);
+        jobs.d_radius[j] = reinterpret_cast<const float *>(d_radius[j]);
+        jobs.N[j] = N[j]; jobs.K[j] = K[j];
+        jobs.boff[j] = blocks; jobs.koff[j] = koff;
+        blocks += (K[j] + SP_KP - 1) / SP_KP;
+        koff += K[j];
+    }
+    jobs.boff[njobs] = blocks;
+    if (blocks == 0) return BX_OK;
+    select_patches_batched_kernel<<<blocks, SP_WARPS * 32, 0, bx_stream(stream)>>>(jobs, P, patches);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

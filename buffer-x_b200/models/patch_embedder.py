@@ -132,13 +132,21 @@ class MiniSpinNet(nn.Module):
         # `radii` = the contiguous device array of per-scale radii when the jobs are (src, tgt) per scale with equal key-point
         # counts: the local reference frames of all jobs then run in ONE launch (patch k uses radii[k // (2 K)])
         one_lrf = radii is not None and len(set(Ks)) == 1 and len(jobs) == 2 * radii.numel()
+        one_sel = len(jobs) <= 16 and ops.SELECT_PATCHES_SCAN and all(isinstance(j[2], torch.Tensor) for j in jobs)   # all patch gatherings of the pair in one launch
+        sel = []
         for (pts, kpts, des_r, perm), K in zip(jobs, Ks):
-            pts4 = ops.permute_cloud(pts.contiguous(), perm)
-            ops.select_patches(pts4, kpts.contiguous(), des_r, P, patches=patches[o:o + K])
-            if not one_lrf:
-                ops.lrf(patches[o:o + K], des_r, bool(is_aligned_to_global_z), delta=delta[o:o + K], Rt=R_all[o:o + K], ra=ra_all[o:o + K])
+            sel.append((ops.permute_cloud(pts.contiguous(), perm), kpts.contiguous(), des_r))
             Rs.append(R_all[o:o + K])
             axes.append(ra_all[o:o + K])
+            o += K
+        if one_sel:
+            ops.select_patches_batched(sel, P, patches)
+        o = 0
+        for (pts4, kpts, des_r), K in zip(sel, Ks):
+            if not one_sel:
+                ops.select_patches(pts4, kpts, des_r, P, patches=patches[o:o + K])
+            if not one_lrf:
+                ops.lrf(patches[o:o + K], des_r, bool(is_aligned_to_global_z), delta=delta[o:o + K], Rt=R_all[o:o + K], ra=ra_all[o:o + K])
             o += K
         if one_lrf:
             ops.lrf(patches, radii, bool(is_aligned_to_global_z), delta=delta, Rt=R_all, ra=ra_all, r_group=2 * Ks[0])

@@ -78,6 +78,11 @@ int bx_radius_estimate(const float *kpts, int Kr, const float *pts, int N, int64
 int bx_permute_cloud(const float *pts, const int32_t *perm, int N, float *out4, void *stream);
 int bx_select_patches(const float *pts4, int N, const float *kpts, int K, float radius, const float *d_radius,
                       int P, int32_t *idx, float *patches, void *stream);
+/* The same for several (permuted cloud, key-point set, device radius) jobs in ONE launch (all 2 x num_scales jobs of a pair):
+ * job j reads pts4[j] (N[j] points), kpts[j] (K[j] key-points), *d_radius[j]; its patches are rows
+ * [sum_{i<j} K[i], ...) of `patches`.  The pointer arrays are HOST arrays of device pointers (<= 16 jobs). */
+int bx_select_patches_batched(int njobs, const void *const *pts4, const int32_t *N, const void *const *kpts, const int32_t *K,
+                              const void *const *d_radius, int P, float *patches, void *stream);
 /* Same result, segmented form (alternative implementation, not faster; cross-checked in the tests): independent (key-point, 2048-point segment) tasks write hit masks and counts
  * into `workspace` (bx_select_patches_workspace_bytes(N, K) bytes), a second pass places the hits at their ordered offsets. */
 int bx_select_patches_seg(const float *pts4, int N, const float *kpts, int K, float radius, const float *d_radius, int P,

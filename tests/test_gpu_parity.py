@@ -122,6 +122,23 @@ def test_select_patches_bit_exact(dev, oracle, radius, P):
     assert (pat2.cpu().numpy() == epat).all()
 
 
+def test_select_patches_batched_equals_per_job(dev, oracle):
+    """bx_select_patches_batched (all (cloud, scale) jobs of a pair in one launch) against the oracle job by job: different
+    clouds, key-point counts (one not a multiple of the 4 key-points of a CTA) and radii, incl. an empty-ball radius."""
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(77)
+    P, jobs, expect = 128, [], []
+    for n, K, radius in ((9000, 300, 0.5), (5000, 157, 0.9), (9000, 300, 0.01), (2049, 1, 3.0)):
+        pts = (rng.uniform(-3, 3, size=(n, 3)) * [1, 1, 0.3]).astype(np.float32)
+        perm = rng.permutation(n).astype(np.int32)
+        kp = pts[oracle.fps(pts, K)]
+        jobs.append((ops.permute_cloud(cu(pts, dev), cu(perm, dev)), cu(kp, dev), torch.tensor([radius], dtype=torch.float32, device=dev)))
+        expect.append(oracle.select_patches(pts, perm, kp, radius, P)[1])
+    out = torch.full((sum(j[1].shape[0] for j in jobs), P, 3), float("nan"), dtype=torch.float32, device=dev)
+    ops.select_patches_batched(jobs, P, out)
+    assert (out.cpu().numpy() == np.concatenate(expect)).all()
+
+
 def test_ball_query_bit_exact(dev, oracle):
     from bufferx_b200 import ops
     rng = np.random.default_rng(9)
