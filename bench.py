@@ -13,7 +13,7 @@ all-gather of the 32-float result records, is INSIDE the timed region.
   e2e   : the same metric through the public API ``BufferX.forward_async(data_source)`` with HOST (pinned) tensors:
           H2D of both clouds and the six permutations and D2H of the result block inside the timed region;
           ``e2e_single_call`` = latency of the reference-style serial ``model(data_source)`` call (eager and graph mode).
-  roofline     : the dominant kernel (conv_tc_kernel of the descriptor conv stack), algorithmic FLOPs / CUDA-event time
+  roofline     : the dominant kernel (conv_sd_kernel, the descriptor conv stack), algorithmic FLOPs / CUDA-event time
                  of its launches in an eager pass of this run.
   kernels      : the HBM-side kernels north_star names (neighbour gather, RANSAC inlier count) as GB/s, and the shares of
                  the other stages.
@@ -49,7 +49,7 @@ def measured_peaks():
 
 
 def conv_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc_kernel launch, averaged over the layers of one batched
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_sd_kernel launch, averaged over the layers of one batched
     descriptor pass, from the committed `ncu --set full` capture (profiles/r02_conv_traffic.json, else round 1's)."""
     for name in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
         try:
@@ -435,9 +435,9 @@ def main():
         e2e = n_pairs_timed / (ms_e2e / 1e3)
         cd = prof.get("conv_desc", dict(launches=0, ms=0.0, work=0.0))
         ach_tf = cd["work"] / (cd["ms"] / 1e3) / 1e12 if cd["ms"] > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (Cylindrical_Net layers; tcgen05 kind::tf32, 3xTF32 split, fp32-equivalent FLOPs)",
+        roof = {"bound": "tensor", "kernel": "conv_sd_kernel (Cylindrical_Net layers; shifted-descriptor implicit GEMM, tcgen05 kind::f16 on fp16 hi/lo split operands = 3 MMAs per fp32-grade product, fp32-equivalent FLOPs)",
                 "achieved": ach_tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf"],
-                "peak_source": f"{pk['src']} bf16 dense (sustained); the 3-pass TF32 ceiling is ~375 TFLOP/s fp32-equivalent",
+                "peak_source": f"{pk['src']} bf16 dense (sustained); three fp16 MMAs per product over the 176-row padded raster put the ceiling of this formulation at 0.265 of it",
                 "launches": cd["launches"], "avg_launch_ms": cd["ms"] / max(cd["launches"], 1),
                 "share_of_step": cd["ms"] / ms_eager if ms_eager else None, "traffic": conv_traffic(),
                 "measured_in": "eager (non-graph) pass of this run: per-kernel CUDA-event brackets need individual launches"}

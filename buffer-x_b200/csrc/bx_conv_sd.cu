@@ -85,6 +85,7 @@ struct ConvSdParams {
     long long rows_in, rows_out;
     int nbs;                   // weight ring length in super-stages (<= SD_MAXNBS); resident: == nchunks * 3, every stage is loaded once
     int resident;              // the whole weight image stays in shared memory (fits for Cin * Cout <= 64 * 64): no re-streaming per tile
+    int *tile_ctr;             // dynamic tile scheduling (presplit-input kernels): [0] next tile, [1] CTAs that have finished; NULL = static stride
     int wchunk;                // 1: a weight stage is a whole 16-channel chunk (nine taps, one copy / one barrier per chunk); 0: three taps
     int stagger;               // experiment (BX_SD_STAGGER=<cycles>): CTA b starts (b % 16) * stagger cycles late so the tile stores of the SMs do not coincide
 };
@@ -230,10 +231,12 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
     // barriers
     constexpr int BAR_AFULL = 0, BAR_AEMPTY = MAXNA, BAR_BFULL = 2 * MAXNA, BAR_BEMPTY = BAR_BFULL + SD_MAXNBS;
     constexpr int BAR_SEGDONE = BAR_BEMPTY + SD_MAXNBS, BAR_ACCFREE = BAR_SEGDONE + 4, BAR_XDONE = BAR_ACCFREE + 4, BAR_XFREE = BAR_XDONE + 2;
-    constexpr int BAR_STAGED = BAR_XFREE + 2, BAR_STFREE = BAR_STAGED + 1;
-    constexpr int NBARS = BAR_STFREE + 1;
+    constexpr int BAR_STAGED = BAR_XFREE + 2, BAR_STFREE = BAR_STAGED + 1, BAR_TILE = BAR_STFREE + 1;
+    constexpr int TRING = 32;                     // published tile indices: the A producer is at most 12 (one-chunk tiles) + 7 tiles ahead of the storers
+    constexpr int NBARS = BAR_TILE + TRING;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[NBARS];
+    __shared__ int tile_ring[TRING];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[128];        // the running sums of a tile start from the bias
 
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
         }
         mbar_init(smem_u32(&bars[BAR_STAGED]), NE);
         mbar_init(smem_u32(&bars[BAR_STFREE]), NST);
+        for (int s = 0; s < TRING; ++s) mbar_init(smem_u32(&bars[BAR_TILE + s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 128) bias_s[threadIdx.x] = (int)threadIdx.x < p.Cout ? __ldg(p.bias + threadIdx.x) : 0.0f;
@@ -281,12 +285,24 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
     uint32_t bar_base = smem_u32(&bars[0]);
     asm volatile("" : "+r"(tmem_base), "+r"(a_base), "+r"(b_base), "+r"(bar_base));
 
+    // Tile sequence of this CTA.  Static: blockIdx.x, + gridDim.x, ...  Dynamic (presplit input, p.tile_ctr): the A producer
+    // draws the next tile from a global counter and publishes it in a shared-memory ring; every other role reads the k-th
+    // entry (-1 = no more tiles).  With several pairs in flight a convolution often starts with some SMs still held by
+    // another stream's kernels (the FPS clusters keep 16 SMs for 2.2 ms): with the static stride the CTAs that start late
+    // still own 1/148 of the tiles each and the whole launch waits for them (measured: ~0.2-0.4 ms per pair).
+    const bool dyn = IN_SD && p.tile_ctr != nullptr;
+    auto tile_of = [&](uint32_t k) -> int {
+        if (!dyn) { const long long t = (long long)blockIdx.x + (long long)k * gridDim.x; return t < n_tiles ? (int)t : -1; }
+        mbar_wait(bar_base + 8u * (BAR_TILE + (k & (TRING - 1))), (k / TRING) & 1u);
+        return tile_ring[k & (TRING - 1)];
+    };
+
     if (STAGED && warp > NE && warp < NE + NLW) {
         // =========================== storers: staged tile -> ReLU, fp16 split, global stores ========================
         constexpr int SCW = NT * 4 / NST;                            // channels per storer thread
         const int sw = warp - NE - 1, row = (sw & 3) * 32 + lane, sc0 = (sw >> 2) * SCW;
         uint32_t k = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+        for (int t = tile_of(0); t >= 0; t = tile_of(++k)) {
             mbar_wait(bar_base + 8u * BAR_STAGED, k & 1u);
             sd_store_rows<SCW, OUT_SD>(p, t, row, sc0, n_samples, [&](int c, float (&r)[8]) {
                 const float4 u0 = stage[((sc0 + c) >> 2) * SD_BM + row], u1 = stage[(((sc0 + c) >> 2) + 1) * SD_BM + row];
@@ -305,7 +321,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
 #ifdef BX_TC_TRACE
         const long long te0_ = clock64();
 #endif
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+        for (int t = tile_of(0); t >= 0; t = tile_of((uint32_t)++k)) {
 #pragma unroll
             for (int c = 0; c < CW; c += 4) {
                 const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[ecs * CW + c]);
@@ -377,7 +393,17 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
             // thread keeps NA chunks in flight; no register staging, no conversion.
             if (warp == NE && lane == 0) {
                 uint32_t slot = 0, par = 0, round = 0;
-                for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+                for (uint32_t k = 0;; ++k) {
+                    int t;
+                    if (dyn) {           // draw the next tile and publish it to the other roles
+                        t = atomicAdd(p.tile_ctr, 1);
+                        if (t >= n_tiles) t = -1;
+                        tile_ring[k & (TRING - 1)] = t;
+                        mbar_arrive(bar_base + 8u * (BAR_TILE + (k & (TRING - 1))));
+                    } else {
+                        t = tile_of(k);
+                    }
+                    if (t < 0) break;
                     for (int c = 0; c < nchunks; ++c) {
                         if (round) mbar_wait(bar_base + 8u * (BAR_AEMPTY + slot), par ^ 1u);
                         mbar_arrive_expect_tx(bar_base + 8u * (BAR_AFULL + slot), 4u * (uint32_t)SD_KBYTES);
@@ -388,6 +414,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
                                      bar_base + 8u * (BAR_AFULL + slot));
                         if (++slot == (uint32_t)NA) { slot = 0; par ^= 1u; round = 1; }
                     }
+                }
             }
             __syncwarp();
         } else {
@@ -505,9 +532,9 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
         if (lane == 0) {
             const int n_super = p.wchunk ? nchunks : n_stages / SB;
             int q = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+            for (uint32_t k = 0; tile_of(k) >= 0; ++k) {
+                if (p.resident && k >= 1) break;                      // resident weights: loaded by the first tile, never again
                 for (int ss = 0; ss < n_super; ++ss, ++q) {
-                    if (p.resident && q >= n_super) break;            // resident weights: loaded by the first tile, never again
                     const int sb = q % NBS;
                     const uint32_t useb = (uint32_t)(q / NBS);
                     if (useb > 0) mbar_wait(bar_base + 8u * (BAR_BEMPTY + sb), (useb - 1) & 1);
@@ -516,6 +543,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
                     bulk_g2s(b_base + (uint32_t)sb * bytes, reinterpret_cast<const unsigned char *>(p.w) + (size_t)ss * bytes, bytes,
                              bar_base + 8u * (BAR_BFULL + sb));
                 }
+            }
         }
         __syncwarp();
     } else {
@@ -550,7 +578,7 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
         const uint32_t probe = (p.dbg & 8) ? 0u : 1u;         // BX_SD_DBG=8: blocking waits only (A/B switch)
         uint32_t pa = probe & mbar_test(bar_base + 8u * (BAR_AFULL + slot), a_par), pc = 1u;
         uint32_t pb = probe & mbar_test(bar_base + 8u * (BAR_BFULL + sbq), b_par);
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+        for (; tile_of(k) >= 0; ++k) {
             const uint32_t xset = k & 1;
             if (!MERGED && k >= 2) {
                 SD_TR_T0();
@@ -627,6 +655,10 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
     __syncthreads();
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+    if (dyn && tid == 0) {      // the last CTA to finish rewinds the counters for the next launch that uses them
+        __threadfence();
+        if (atomicAdd(p.tile_ctr + 1, 1) == (int)gridDim.x - 1) { p.tile_ctr[0] = 0; p.tile_ctr[1] = 0; __threadfence(); }
     }
 }
 
@@ -966,6 +998,7 @@ int launch_sd(ConvSdParams p, cudaStream_t st) {
         BX_CUDA(cudaFuncSetAttribute(conv_sd_kernel<NT, ECS, IN_SD, OUT_SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int sms = bx_device_sm_count();
     if (sms <= 0) sms = 148;
+    { static int gcap = -1; if (gcap < 0) { const char *e = getenv("BX_SD_GRID"); gcap = e ? atoi(e) : 0; } if (gcap > 0 && sms > gcap) sms = gcap; }   // experiment
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
     conv_sd_kernel<NT, ECS, IN_SD, OUT_SD><<<grid, (4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2) * 32, smem, st>>>(p);
     BX_LAUNCH_CHECK();
@@ -989,7 +1022,7 @@ BX_API long long bx_conv_sd_rows(int n, int rows_per_sample) {
 }
 
 BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const void *w_sd, const float *bias, void *out, int out_presplit,
-                            int n, const int32_t *d_n, int Cin, int Cout, int D, int W, int relu, int32_t *d_flag, void *stream) {
+                            int n, const int32_t *d_n, int Cin, int Cout, int D, int W, int relu, int32_t *d_flag, int32_t *d_tile_ctr, void *stream) {
     BX_REQUIRE(in && w_sd && bias && out, "bx_conv_layer_sd: null pointer");
     BX_REQUIRE(geom == BX_GEOM_CYL3D || geom == BX_GEOM_CYL2D || geom == BX_GEOM_VALID3D, "bx_conv_layer_sd: geometry must be CYL3D, CYL2D or VALID3D (k = 3x1x3)");
     BX_REQUIRE(n >= 0 && Cin >= 16 && Cin % 16 == 0 && Cout >= 4 && Cout % 4 == 0 && Cout <= 128, "bx_conv_layer_sd: bad channels Cin=%d Cout=%d", Cin, Cout);
@@ -1000,7 +1033,7 @@ BX_API int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const voi
                "bx_conv_layer_sd: activations, weights and bias must be 16-byte aligned");
     if (n == 0) return BX_OK;
     ConvSdParams p = {};
-    p.w = reinterpret_cast<const __half *>(w_sd); p.bias = bias; p.flag = d_flag; p.d_n = d_n;
+    p.w = reinterpret_cast<const __half *>(w_sd); p.bias = bias; p.flag = d_flag; p.d_n = d_n; p.tile_ctr = d_tile_ctr;
     p.in = in_presplit ? nullptr : reinterpret_cast<const float *>(in);
     p.in_sd = in_presplit ? reinterpret_cast<const __half *>(in) : nullptr;
     p.out = out_presplit ? nullptr : reinterpret_cast<float *>(out);

@@ -281,6 +281,16 @@ BX_API int bx_fps_set_sync_mode(int mode) {
 
 BX_API int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint, int32_t *idx, float *kpts,
                   void *stream) {
+    return bx_fps_ex(xyz, h_offsets, B, npoint, idx, kpts, 0, stream);
+}
+
+// max_cluster > 0: THROUGHPUT form -- at most that many CTAs per cloud (2 or 4), more points per thread.  An iteration is a
+// latency chain (reductions + cluster exchange, ~1.1 us) whatever the cluster size, so the default form spreads a cloud over
+// 8 SMs only to shorten the register scan; when several pairs are in flight the 16 SMs of a pair's two clouds are taken from
+// the other pairs' convolutions for 2.2 ms (measured: 7 % of the pipelined rate).  Two CTAs per cloud hold 10 points per
+// thread: 1.4x the latency on a quarter of the SMs.  Same indices in every form (the tie rank does not depend on the layout).
+BX_API int bx_fps_ex(const float *xyz, const int32_t *h_offsets, int B, int npoint, int32_t *idx, float *kpts, int max_cluster,
+                     void *stream) {
     BX_REQUIRE(xyz && h_offsets && idx, "bx_fps: null pointer");
     BX_REQUIRE(B >= 1 && B <= kMaxClouds, "bx_fps: B=%d out of range [1,%d]", B, kMaxClouds);
     BX_REQUIRE(npoint >= 0, "bx_fps: npoint < 0");
@@ -300,6 +310,17 @@ BX_API int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint,
     // larger clouds: 1024 threads per CTA and few points per thread -- the per-iteration register scan is a dependent
     // chain per thread, so its latency scales with the points per thread, while the reductions / cluster exchange
     // do not depend on the thread count
+    if (max_cluster > 0 && maxN <= 49152) {
+        const int cl = max_cluster >= 4 ? 4 : 2;
+        const int per_cta = (maxN + cl - 1) / cl;          // points per CTA of 1024 threads
+        if (per_cta <= 4096) return launch_fps<1024, 4>(xyz, d_off, B, cl, npoint, idx, kpts, st);
+        if (per_cta <= 6144) return launch_fps<1024, 6>(xyz, d_off, B, cl, npoint, idx, kpts, st);
+        if (per_cta <= 10240) return launch_fps<1024, 10>(xyz, d_off, B, cl, npoint, idx, kpts, st);
+        if (per_cta <= 12288) return launch_fps<1024, 12>(xyz, d_off, B, cl, npoint, idx, kpts, st);
+    }
+    { static int cl16 = -1; if (cl16 < 0) { const char *e = getenv("BX_FPS_CL16"); cl16 = e ? atoi(e) : 0; }     // experiment: 16-CTA clusters, fewer points per thread
+      if (cl16 && maxN <= 16384) return launch_fps<1024, 1>(xyz, d_off, B, 16, npoint, idx, kpts, st);
+      if (cl16 && maxN <= 32768) return launch_fps<1024, 2>(xyz, d_off, B, 16, npoint, idx, kpts, st); }
     if (maxN <= 16384) return launch_fps<1024, 2>(xyz, d_off, B, 8, npoint, idx, kpts, st);
     if (maxN <= 24576) return launch_fps<1024, 3>(xyz, d_off, B, 8, npoint, idx, kpts, st);
     if (maxN <= 32768) return launch_fps<1024, 4>(xyz, d_off, B, 8, npoint, idx, kpts, st);

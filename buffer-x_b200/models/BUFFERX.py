@@ -17,6 +17,8 @@ Throughput API on top of the reference surface (CUDA streams + graphs instead of
   * ``forward_async(data_source) -> handle`` / ``handle.result()``: several pairs in flight on separate
     streams (FPS is a latency-bound 16-SM kernel; a second pair's convolutions fill the other SMs).
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -189,6 +191,7 @@ class BufferX(nn.Module):
         self._use_graphs = False
         self._slots = {}
         self._slots_per_shape = 2
+        self._fps_cluster = 0        # > 0: throughput form of the FPS kernel (ops.fps max_cluster), chosen by enable_cuda_graphs
         self._rr = {}
 
     def get_parameter(self):
@@ -244,6 +247,12 @@ class BufferX(nn.Module):
         """Capture the per-pair enqueue once per (Ns, Nt, aligned) shape and replay it (no effect on results)."""
         self._use_graphs = bool(flag)
         self._slots_per_shape = int(slots_per_shape)
+        # three or more pairs in flight: the key-point sampling of a pair runs beside the other pairs' convolutions; bx_fps_ex offers
+        # a 2- / 4-CTA-per-cloud form (fewer SMs, longer)
+        # (measured on C2 with six pairs in flight: 2 CTAs per cloud 5.1 ms per FPS and 163 pairs/s, 8 CTAs 2.2 ms and 177 -- what the
+        # other streams lose is governed by how LONG the sampling holds its SMs, not by how many, so the default stays the
+        # latency form; BX_FPS_CLUSTER=2|4 selects the throughput form for experiments)
+        self._fps_cluster = int(os.environ.get("BX_FPS_CLUSTER", "0")) if (flag and self._slots_per_shape >= 3) else 0
         self._slots.clear()
         self._rr.clear()
         return self
@@ -310,7 +319,7 @@ class BufferX(nn.Module):
         # ---- key-points: one FPS per cloud, both clouds in one launch --------------------------------
         xyz = torch.cat([src, tgt], dim=0)
         nfps = max(Kr, K)
-        fidx, fk = ops.fps(xyz, [0, Ns, Ns + Nt], nfps)
+        fidx, fk = ops.fps(xyz, [0, Ns, Ns + Nt], nfps, max_cluster=self._fps_cluster)
         kpts1, kpts2 = fk[0, :Kr].contiguous(), fk[1, :Kr].contiguous()
         src_kpts, tgt_kpts = fk[0, :K].contiguous(), fk[1, :K].contiguous()
         # ---- density-aware radii of every scale from one histogram ------------------------------------

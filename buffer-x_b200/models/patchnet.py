@@ -19,6 +19,10 @@ USE_FFMA = os.environ.get("BX_CONV", "sd").lower() == "ffma"
 # BX_CONV=tc: the descriptor stack on the round-1 TF32 kernel (bx_conv_tc.cu) instead of the shifted-descriptor fp16-split
 # kernel (bx_conv_sd.cu, the default).  The TF32 kernel is also the automatic fall-back when an activation leaves fp16 range.
 USE_TF32_DESC = os.environ.get("BX_CONV", "sd").lower() == "tc"
+# BX_SD_DYNAMIC=1: the persistent conv kernels draw their tiles from a device-side counter (bx_conv_layer_sd d_tile_ctr) instead
+# of the static stride.  Measured with six pairs in flight: 170.1 vs 170.5 pairs/s -- no gain (a launch whose CTAs start late
+# still cannot finish before they have been scheduled), so the static stride stays the default; the path is kept and tested.
+DYNAMIC_TILES = os.environ.get("BX_SD_DYNAMIC", "0") == "1"
 # Debug switch only: BX_COSTVOL=direct runs the first CostNet layer as a convolution over the on-the-fly cost volume
 # (GEOM_COSTVOL) instead of its factorised form (bx_costvol_ab + GEOM_COSTAB).
 DIRECT_COSTVOL = os.environ.get("BX_COSTVOL", "factored").lower() == "direct"
@@ -126,11 +130,14 @@ class Cylindrical_Net(_ConvStack):
         use_sd = not USE_FFMA and not self.force_tf32
         assert use_sd or not presplit_in
         flag = self.overflow_flag(dev) if use_sd else None
+        # dynamic tile scheduling of the persistent conv kernels: one zeroed counter pair per layer (and per call = per stream)
+        ctrs = torch.zeros(2 * len(L), dtype=torch.int32, device=dev) if (use_sd and DYNAMIC_TILES) else None
         for i, l in enumerate(L):
             out = torch.empty((K, l["cout"], 140) if USE_FFMA else (K, l["cout"] // 4, 140, 4), dtype=torch.float32, device=dev)
             if use_sd:       # layer-to-layer activations in the presplit padded fp16 format; fp32 in at the first, fp32 out at the last layer
                 out = out if i == len(L) - 1 else ops.conv_sd_buffer(K, l["cout"], dev)
-                ops.conv_layer_sd(ops.GEOM_CYL3D if i == 0 else ops.GEOM_CYL2D, cur, l["w_sd"], l["b"], out, K, l["cin"], l["cout"], l["relu"], flag)
+                ops.conv_layer_sd(ops.GEOM_CYL3D if i == 0 else ops.GEOM_CYL2D, cur, l["w_sd"], l["b"], out, K, l["cin"], l["cout"], l["relu"], flag,
+                                  tile_ctr=None if ctrs is None else ctrs[2 * i:2 * i + 2])
                 cur = out
                 continue
             conv, w = (ops.conv_layer, l["w"]) if USE_FFMA else (ops.conv_layer_tc, l["w_tc"])
@@ -167,6 +174,7 @@ class CostNet(_ConvStack):
         factored = (not USE_FFMA) and not DIRECT_COSTVOL
         use_sd = not USE_FFMA and not self.force_tf32
         flag = self.flag_source(dev) if (use_sd and self.flag_source is not None) else None
+        ctrs = torch.zeros(2 * len(L), dtype=torch.int32, device=dev) if (use_sd and DYNAMIC_TILES) else None
         for i, l in enumerate(L):
             kd, kh, kw = l["k"]
             OD, OH, OW = D - kd + 1, H - kh + 1, W - kw + 1
@@ -175,7 +183,8 @@ class CostNet(_ConvStack):
                 nxt_sd = nxt is not None and nxt.get("w_sd") is not None
                 out = (ops.conv_sd_buffer(maxM, l["cout"], dev, OD * OW) if nxt_sd
                        else torch.empty((maxM, l["cout"] // 4, OD * OW, 4), dtype=torch.float32, device=dev))
-                ops.conv_layer_sd(ops.GEOM_VALID3D, cur, l["w_sd"], l["b"], out, maxM, l["cin"], l["cout"], l["relu"], flag, d_n=d_M, D=D, W=W)
+                ops.conv_layer_sd(ops.GEOM_VALID3D, cur, l["w_sd"], l["b"], out, maxM, l["cin"], l["cout"], l["relu"], flag, d_n=d_M, D=D, W=W,
+                                  tile_ctr=None if ctrs is None else ctrs[2 * i:2 * i + 2])
                 cur, D, H, W = out, OD, OH, OW
                 continue
             conv, w = (ops.conv_layer, l["w"]) if USE_FFMA else (ops.conv_layer_tc, l["w_tc"])

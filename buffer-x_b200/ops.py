@@ -23,7 +23,7 @@ SYMBOLS = [
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
     "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab", "bx_concat_matches",
-    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes", "bx_conv_layer_sd_costab", "bx_lrf_batched", "bx_select_patches_batched",
+    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes", "bx_conv_layer_sd_costab", "bx_lrf_batched", "bx_select_patches_batched", "bx_fps_ex",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
@@ -57,6 +57,7 @@ def load_library():
     lib.bx_ransac_workspace_bytes.argtypes = [c_int]
     P = c_void_p
     lib.bx_fps.argtypes = [P, P, c_int, c_int, P, P, P]
+    lib.bx_fps_ex.argtypes = [P, P, c_int, c_int, P, P, c_int, P]
     lib.bx_radius_estimate.argtypes = [P, c_int, P, c_int, c_int64, P, c_int, c_double, P, P, P, P, P]
     lib.bx_permute_cloud.argtypes = [P, P, c_int, P, P]
     lib.bx_select_patches.argtypes = [P, c_int, P, c_int, c_float, P, c_int, P, P, P]
@@ -71,7 +72,7 @@ def load_library():
     lib.bx_conv_layer.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_layer_tc.argtypes = [c_int, P, P, P, P, c_int, P] + [c_int] * 9 + [P, P, P, P, P]
     lib.bx_conv_tc_ntile.argtypes = [c_int]
-    lib.bx_conv_layer_sd.argtypes = [c_int, P, c_int, P, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P]
+    lib.bx_conv_layer_sd.argtypes = [c_int, P, c_int, P, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, P]
     lib.bx_conv_sd_rows.argtypes = [c_int, c_int]
     lib.bx_conv_layer_sd_costab.argtypes = [P, P, P, P, P, c_int, c_int, P, c_int, P, P]
     lib.bx_fps_set_sync_mode.argtypes = [c_int]
@@ -173,15 +174,16 @@ class _Span:
         return False
 
 
-def fps(xyz: torch.Tensor, offsets, npoint: int, want_kpts=True):
-    """xyz [sumN,3] f32 cuda; offsets: host sequence of B+1 ints.  Returns idx [B,npoint] i32, kpts [B,npoint,3]."""
+def fps(xyz: torch.Tensor, offsets, npoint: int, want_kpts=True, max_cluster=0):
+    """xyz [sumN,3] f32 cuda; offsets: host sequence of B+1 ints.  Returns idx [B,npoint] i32, kpts [B,npoint,3].
+    max_cluster 2 / 4: throughput form (fewer SMs per cloud, same indices)."""
     lib = load_library()
     off = np.ascontiguousarray(offsets, dtype=np.int32)
     B = len(off) - 1
     idx = torch.empty((B, npoint), dtype=I32, device=xyz.device)
     kp = torch.empty((B, npoint, 3), dtype=F32, device=xyz.device) if want_kpts else None
     with _Span("fps"):
-        _check(lib.bx_fps(_dp(xyz, F32, "xyz"), off.ctypes.data_as(c_void_p), B, npoint, _dp(idx), _dp(kp), _stream()), "bx_fps")
+        _check(lib.bx_fps_ex(_dp(xyz, F32, "xyz"), off.ctypes.data_as(c_void_p), B, npoint, _dp(idx), _dp(kp), int(max_cluster), _stream()), "bx_fps")
     return idx, kp
 
 
@@ -411,9 +413,10 @@ def conv_sd_buffer(n: int, C: int, device, rows_per_sample: int = 176):
     return torch.empty((C // 16, 4, conv_sd_rows(n, rows_per_sample), 8), dtype=torch.float16, device=device)
 
 
-def conv_layer_sd(geom, x, w_sd, bias, out, n, Cin, Cout, relu, flag=None, d_n=None, D=0, W=0):
+def conv_layer_sd(geom, x, w_sd, bias, out, n, Cin, Cout, relu, flag=None, d_n=None, D=0, W=0, tile_ctr=None):
     """x: fp32 channel-blocked [n, Cin/4, S_in, 4] or presplit fp16 [Cin/16, 4, rows, 8]; out likewise (dtype decides);
-    ``flag``: int32[1] fp16-range flag (sticky); ``d_n``: device-side sample count; D, W: input raster of GEOM_VALID3D."""
+    ``flag``: int32[1] fp16-range flag (sticky); ``d_n``: device-side sample count; D, W: input raster of GEOM_VALID3D;
+    ``tile_ctr``: int32[2] zeroed device counters -> dynamic tile scheduling (one pair per launch in flight)."""
     ev = None
     if profiler is not None:
         if geom == GEOM_VALID3D:
@@ -424,7 +427,7 @@ def conv_layer_sd(geom, x, w_sd, bias, out, n, Cin, Cout, relu, flag=None, d_n=N
     in_sd, out_sd = x.dtype == torch.float16, out.dtype == torch.float16
     _check(load_library().bx_conv_layer_sd(geom, _dp(x, None, "x"), int(in_sd), _dp(w_sd, torch.float16, "w_sd"), _dp(bias, F32, "bias"),
                                            _dp(out, None, "out"), int(out_sd), int(n), _dp(d_n, I32, "d_n"), Cin, Cout, int(D), int(W), int(bool(relu)),
-                                           _dp(flag, I32, "flag"), _stream()), "bx_conv_layer_sd")
+                                           _dp(flag, I32, "flag"), _dp(tile_ctr, I32, "tile_ctr"), _stream()), "bx_conv_layer_sd")
     if ev:
         ev[1].record()
     return out

@@ -50,6 +50,10 @@ unsigned long long bx_launch_count(void); /* kernels launched by this library si
  * idx: [B,npoint] int32 (index inside the cloud); kpts: [B,npoint,3] (may be NULL).
  * Limit: N <= 131072 per cloud. */
 int bx_fps(const float *xyz, const int32_t *h_offsets, int B, int npoint, int32_t *idx, float *kpts, void *stream);
+/* The same with at most max_cluster (2 or 4) CTAs per cloud: fewer SMs, ~1.4x the latency -- for callers that keep several
+ * pairs in flight (0 = bx_fps).  Identical indices. */
+int bx_fps_ex(const float *xyz, const int32_t *h_offsets, int B, int npoint, int32_t *idx, float *kpts, int max_cluster,
+              void *stream);
 /* Switch for the FPS cluster exchange: 0 = st.async + transaction-count mbarrier (production), 1 = cluster.sync() per iteration
  * (racecheck-clean reference form), 2 = remote stores + remote mbarrier arrive / acquire wait (round 1), -1 = BX_FPS_SYNC
  * environment variable.  Same results in every mode.  Returns the old value. */
@@ -155,9 +159,14 @@ int bx_conv_layer(int geom, const float *in, const float *w, const float *bias, 
  * n = sample capacity; *d_n (optional, device) = the number of samples actually present (match count).
  * w_sd: fp16 hi/lo weight image [chunk][tap][kcore][split][NT][8] (ops.conv_sd_weights; NT = bx_conv_tc_ntile(Cout));
  * bias fp32 [Cout].  An activation with |x| >= 65000 cannot be split into fp16 operands -> *d_flag |= 1 (d_flag may be
- * NULL) and the caller re-runs the stack with bx_conv_layer_tc. */
+ * NULL) and the caller re-runs the stack with bx_conv_layer_tc.
+ * d_tile_ctr (optional, device, int32[2], zero before its first use): dynamic tile scheduling for presplit-input layers --
+ * the persistent CTAs draw 128-row tiles from the counter instead of a fixed stride, so a launch that starts while other
+ * streams still hold some SMs is not held up by its late CTAs; the kernel rewinds the counter when it finishes.  One
+ * counter pair per launch in flight (the callers keep one per layer and stream). */
 int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const void *w_sd, const float *bias, void *out, int out_presplit,
-                     int n, const int32_t *d_n, int Cin, int Cout, int D, int W, int relu, int32_t *d_flag, void *stream);
+                     int n, const int32_t *d_n, int Cin, int Cout, int D, int W, int relu, int32_t *d_flag, int32_t *d_tile_ctr,
+                     void *stream);
 long long bx_conv_sd_rows(int n, int rows_per_sample);
 /* The second CostNet layer (32 -> 64, k = 3x3x3 over relu(A - B) regenerated from the factor maps of bx_costvol_ab) as a
  * 96 -> 64, k = (3,1,3) convolution over the 18 x 18 (n, l) raster on the same kernel.  fa [n,8,60,4], fb [n,8,54,4] fp32;

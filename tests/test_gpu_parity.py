@@ -73,6 +73,22 @@ def test_fps_mbarrier_exchange_equals_cluster_sync_exchange(dev, oracle, n, m):
     assert torch.equal(a, b) and torch.equal(a, c) and (a[0].cpu().numpy() == oracle.fps(xyz, m)).all()
 
 
+@pytest.mark.parametrize("n,m", [(20000, 700), (7000, 300), (40000, 200), (4097, 64)])
+@pytest.mark.parametrize("cl", [2, 4])
+def test_fps_throughput_form_same_indices(dev, oracle, n, m, cl):
+    """bx_fps_ex with 2 / 4 CTAs per cloud (the form BufferX uses with several pairs in flight): the indices of the default
+    8-CTA form and of the oracle, incl. exact ties (duplicated points)."""
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(n + cl)
+    xyz = rng.normal(size=(n, 3)).astype(np.float32)
+    xyz[n // 2:n // 2 + 50] = xyz[:50]                                   # exact duplicates: tie-breaking by rank
+    d = cu(np.concatenate([xyz, xyz[::-1]]), dev)                        # two clouds in one launch
+    a, ka = ops.fps(d, [0, n, 2 * n], m)
+    b, kb = ops.fps(d, [0, n, 2 * n], m, max_cluster=cl)
+    assert torch.equal(a, b) and torch.equal(ka, kb)
+    assert (b[0].cpu().numpy() == oracle.fps(xyz, m)).all()
+
+
 def test_fps_two_clouds_one_launch(dev, oracle):
     from bufferx_b200 import ops
     rng = np.random.default_rng(0)
@@ -725,6 +741,24 @@ def test_conv_layer_kernels(dev, geom, Cin, Cout, dims, k, n, impl):
     got = out.cpu().numpy().reshape(ref.shape)
     err = np.abs(got - ref.numpy()).max() / np.abs(ref.numpy()).max()
     assert err < 2e-5, f"{impl} {geom} Cin={Cin} Cout={Cout}: rel err {err}"     # fp32-grade (3xTF32 / FFMA) vs torch fp32
+
+
+def test_conv_sd_dynamic_tiles_same_bits(dev):
+    """bx_conv_layer_sd with a device-side tile counter (dynamic scheduling of the persistent CTAs) writes exactly what the
+    static stride writes, launch after launch (the kernel rewinds the counter itself), incl. a device-side sample count."""
+    from bufferx_b200 import ops
+    torch.manual_seed(5)
+    n, Cin, Cout = 700, 64, 64
+    x = ops.sd_pack(torch.relu(torch.randn(n, Cin, 7, 20, device=dev)))
+    Wt = torch.randn(9, Cin, Cout, device=dev) * 0.05
+    w, b = ops.conv_sd_weights(Wt), torch.randn(Cout, device=dev) * 0.1
+    ref = ops.conv_layer_sd(ops.GEOM_CYL2D, x, w, b, ops.conv_sd_buffer(n, Cout, dev).zero_(), n, Cin, Cout, True, None)
+    ctr = torch.zeros(2, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        out = ops.conv_layer_sd(ops.GEOM_CYL2D, x, w, b, ops.conv_sd_buffer(n, Cout, dev).zero_(), n, Cin, Cout, True, None, tile_ctr=ctr)
+        assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+        assert ctr.tolist() == [0, 0]
+
 
 
 @pytest.mark.parametrize("tap", list(range(9)))

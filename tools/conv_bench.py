@@ -26,6 +26,7 @@ if MODE == "sd":     # layer-to-layer activations in the presplit padded fp16 fo
 else:
     bufs = [torch.empty((K, l["cout"] // 4, 140, 4), device=dev) for l in L]
 times = [[] for _ in L]
+ctrs = torch.zeros(2 * len(L), dtype=torch.int32, device=dev)
 for r in range(reps + 2):
     flush.zero_()
     cur = x
@@ -33,7 +34,7 @@ for r in range(reps + 2):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         if MODE == "sd":
-            ops.conv_layer_sd(ops.GEOM_CYL3D if i == 0 else ops.GEOM_CYL2D, cur, l["w_sd"], l["b"], bufs[i], K, l["cin"], l["cout"], l["relu"], None)
+            ops.conv_layer_sd(ops.GEOM_CYL3D if i == 0 else ops.GEOM_CYL2D, cur, l["w_sd"], l["b"], bufs[i], K, l["cin"], l["cout"], l["relu"], None, tile_ctr=(ctrs[2 * i:2 * i + 2] if os.environ.get("BX_SD_DYNAMIC", "0") == "1" else None))
         elif i == 0:
             ops.conv_layer_tc(ops.GEOM_CYL3D, cur, l["w_tc"], l["b"], bufs[i], K, l["cin"], l["cout"], 3, 7, 20, 3, 3, 3, l["relu"])
         else:
