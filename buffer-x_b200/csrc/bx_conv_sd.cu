@@ -86,6 +86,8 @@ struct ConvSdParams {
     int nbs;                   // weight ring length in super-stages (<= SD_MAXNBS); resident: == nchunks * 3, every stage is loaded once
     int resident;              // the whole weight image stays in shared memory (fits for Cin * Cout <= 64 * 64): no re-streaming per tile
     int *tile_ctr;             // dynamic tile scheduling (presplit-input kernels): [0] next tile, [1] CTAs that have finished; NULL = static stride
+    int stage_sync;            // verification form (bx_conv_sd_set_stage_sync / BX_SD_STAGE_SYNC=1): staging hand-over through named barriers (bar.sync / bar.arrive)
+                               // instead of mbarriers -- the form compute-sanitizer's racecheck models; same results
     int wchunk;                // 1: a weight stage is a whole 16-channel chunk (nine taps, one copy / one barrier per chunk); 0: three taps
     int stagger;               // experiment (BX_SD_STAGGER=<cycles>): CTA b starts (b % 16) * stagger cycles late so the tile stores of the SMs do not coincide
 };
@@ -303,13 +305,15 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
         const int sw = warp - NE - 1, row = (sw & 3) * 32 + lane, sc0 = (sw >> 2) * SCW;
         uint32_t k = 0;
         for (int t = tile_of(0); t >= 0; t = tile_of(++k)) {
-            mbar_wait(bar_base + 8u * BAR_STAGED, k & 1u);
+            if (p.stage_sync) asm volatile("bar.sync 1, %0;" ::"r"((NE + NST) * 32) : "memory");       // epilogue warps arrive, storers wait
+            else mbar_wait(bar_base + 8u * BAR_STAGED, k & 1u);
             sd_store_rows<SCW, OUT_SD>(p, t, row, sc0, n_samples, [&](int c, float (&r)[8]) {
                 const float4 u0 = stage[((sc0 + c) >> 2) * SD_BM + row], u1 = stage[(((sc0 + c) >> 2) + 1) * SD_BM + row];
                 r[0] = u0.x; r[1] = u0.y; r[2] = u0.z; r[3] = u0.w; r[4] = u1.x; r[5] = u1.y; r[6] = u1.z; r[7] = u1.w;
             });
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_base + 8u * BAR_STFREE);
+            if (p.stage_sync) asm volatile("bar.arrive 2, %0;" ::"r"((NE + NST) * 32) : "memory");
+            else if (lane == 0) mbar_arrive(bar_base + 8u * BAR_STFREE);
         }
     } else if (warp < NE) {
         // =========================== epilogue: segment drains, bias, ReLU, stores ==========================
@@ -372,12 +376,16 @@ __global__ void __launch_bounds__((4 * ECS + SdRoles<NT, IN_SD, OUT_SD>::NLW + 2
             }
             SD_TR_T0();
             if constexpr (STAGED) {
-                if (k >= 1) mbar_wait(bar_base + 8u * BAR_STFREE, (uint32_t)((k - 1) & 1));      // the storers have read the previous tile
+                if (k >= 1) {                                                                      // the storers have read the previous tile
+                    if (p.stage_sync) asm volatile("bar.sync 2, %0;" ::"r"((NE + NST) * 32) : "memory");
+                    else mbar_wait(bar_base + 8u * BAR_STFREE, (uint32_t)((k - 1) & 1));
+                }
 #pragma unroll
                 for (int c = 0; c < CW; c += 4)
                     stage[((ecs * CW + c) >> 2) * SD_BM + quarter * 32 + lane] = make_float4(run[c], run[c + 1], run[c + 2], run[c + 3]);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_base + 8u * BAR_STAGED);
+                if (p.stage_sync) asm volatile("bar.arrive 1, %0;" ::"r"((NE + NST) * 32) : "memory");
+                else if (lane == 0) mbar_arrive(bar_base + 8u * BAR_STAGED);
             } else {
                 sd_store_tile<CW, OUT_SD>(p, t, quarter, ecs, lane, n_samples, run);
             }
@@ -967,8 +975,11 @@ int launch_sd2(ConvSdParams p, cudaStream_t st) {
     return BX_OK;
 }
 
+int g_sd_stage_sync = -1;      // -1: follow BX_SD_STAGE_SYNC
+
 template <int NT, int ECS, int IN_SD, int OUT_SD>
 int launch_sd(ConvSdParams p, cudaStream_t st) {
+    { static int env = -1; if (env < 0) { const char *e = getenv("BX_SD_STAGE_SYNC"); env = e ? atoi(e) : 0; } p.stage_sync = g_sd_stage_sync >= 0 ? g_sd_stage_sync : env; }
     // the whole weight image resident in shared memory when it leaves room for >= 6 A chunks (Cin * Cout <= 64 * 64: 144 KB),
     // else a ring of SdRing<NT>::NBS super-stages of three taps
     constexpr int B_SUPER = SdRing<NT>::SB * 64 * NT;
@@ -1013,6 +1024,15 @@ int dispatch_sd(const ConvSdParams &p, int in_sd, int out_sd, cudaStream_t st) {
 }
 
 }  // namespace
+
+// Staging hand-over between the epilogue and the storer warps of conv_sd_kernel: 0 = mbarriers (production), 1 = named barriers
+// (bar.arrive / bar.sync: the form compute-sanitizer racecheck models; bit-identical results), -1 = follow BX_SD_STAGE_SYNC.
+// Returns the previous value.
+BX_API int bx_conv_sd_set_stage_sync(int mode) {
+    const int old = g_sd_stage_sync;
+    g_sd_stage_sync = mode;
+    return old;
+}
 
 // rows of a presplit activation image: n samples of rows_per_sample raster rows (176 for the cylindrical layers: 8 x 22),
 // rounded to whole 128-row tiles, + the 48-row halo a tile's operand fetch reaches past its last row

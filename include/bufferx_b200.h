@@ -168,6 +168,10 @@ int bx_conv_layer_sd(int geom, const void *in, int in_presplit, const void *w_sd
                      int n, const int32_t *d_n, int Cin, int Cout, int D, int W, int relu, int32_t *d_flag, int32_t *d_tile_ctr,
                      void *stream);
 long long bx_conv_sd_rows(int n, int rows_per_sample);
+/* Verification switch: how the epilogue warps of the shifted-descriptor kernel hand a finished tile to its storer warps --
+ * 0 mbarriers (production), 1 named barriers (the form compute-sanitizer's racecheck models), -1 follow BX_SD_STAGE_SYNC.
+ * Identical results; returns the previous value. */
+int bx_conv_sd_set_stage_sync(int mode);
 /* The second CostNet layer (32 -> 64, k = 3x3x3 over relu(A - B) regenerated from the factor maps of bx_costvol_ab) as a
  * 96 -> 64, k = (3,1,3) convolution over the 18 x 18 (n, l) raster on the same kernel.  fa [n,8,60,4], fb [n,8,54,4] fp32;
  * w_sd: ops.conv_sd_weights_costab; out: fp32 [n,16,256,4] or presplit over the 16 x 16 raster (rows = bx_conv_sd_rows(n, 256)). */

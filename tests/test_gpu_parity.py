@@ -743,6 +743,26 @@ def test_conv_layer_kernels(dev, geom, Cin, Cout, dims, k, n, impl):
     assert err < 2e-5, f"{impl} {geom} Cin={Cin} Cout={Cout}: rel err {err}"     # fp32-grade (3xTF32 / FFMA) vs torch fp32
 
 
+def test_conv_sd_stage_handover_forms_same_bits(dev):
+    """The epilogue -> storer staging hand-over with mbarriers (production) and with named barriers (the form racecheck models,
+    profiles/r02_sanitizer_racecheck_*.txt) writes the same bits, for a narrow and a wide layer."""
+    from bufferx_b200 import ops
+    lib = ops.load_library()
+    torch.manual_seed(6)
+    for Cin, Cout, n in ((64, 64, 500), (64, 128, 300)):
+        x = ops.sd_pack(torch.relu(torch.randn(n, Cin, 7, 20, device=dev)))
+        w, b = ops.conv_sd_weights(torch.randn(9, Cin, Cout, device=dev) * 0.05), torch.randn(Cout, device=dev) * 0.1
+        outs = []
+        old = lib.bx_conv_sd_set_stage_sync(0)
+        try:
+            for mode in (0, 1):
+                lib.bx_conv_sd_set_stage_sync(mode)
+                outs.append(ops.conv_layer_sd(ops.GEOM_CYL2D, x, w, b, ops.conv_sd_buffer(n, Cout, dev).zero_(), n, Cin, Cout, True, None))
+        finally:
+            lib.bx_conv_sd_set_stage_sync(old)
+        assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+
+
 def test_conv_sd_dynamic_tiles_same_bits(dev):
     """bx_conv_layer_sd with a device-side tile counter (dynamic scheduling of the persistent CTAs) writes exactly what the
     static stride writes, launch after launch (the kernel rewinds the counter itself), incl. a device-side sample count."""
