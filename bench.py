@@ -3,8 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3|C4|C5|C1]
 
-A "step" is one pass of the hot path over one BATCH of synthetic pairs (``--pairs-per-step``, default 32 C2 pairs: a
-step is ~0.28 s of GPU work, the default 20 steps a 5-6 s timed region through 32 distinct pairs per rank).  Every pair
+A "step" is one pass of the hot path over one BATCH of synthetic pairs (``--pairs-per-step``, default 48 C2 pairs: a
+step is ~0.28 s of GPU work, the default 20 steps a 5-6 s timed region through 48 distinct pairs per rank).  Every pair
 goes through the whole path (FPS -> radius estimation -> 6x [patch gathering, LRF, SPT, conv stack, pooling] -> 3x
 [matching, cost volume, hypotheses] -> consensus -> RANSAC -> refinement); the one collective of the path, the
 all-gather of the 32-float result records, is INSIDE the timed region.
@@ -37,7 +37,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "registration pairs/sec (20k-pt clouds, 1500 kpts, 50k RANSAC)"
-DEFAULT_BATCH = {"C1": 32, "C2": 32, "C3": 8, "C5": 16, "C4": 512}
+DEFAULT_BATCH = {"C1": 128, "C2": 48, "C3": 16, "C5": 32, "C4": 512}     # sized for a timed region of >= 3-5 s at 20 steps
 
 
 def measured_peaks():
@@ -230,7 +230,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"],
                     help="BASELINE.json configs; C4 = 512 C2 pairs split round-robin over the ranks (strong scaling, one step = the whole job)")
-    ap.add_argument("--pairs-per-step", type=int, default=None, help="pairs per step and rank (default: C2 32, C3 8, C5 16; C4: 512 / world)")
+    ap.add_argument("--pairs-per-step", type=int, default=None, help="pairs per step and rank (default: C2 48, C3 16, C5 32, C1 128; C4: 512 / world)")
     ap.add_argument("--depth", type=int, default=6,
                     help="pairs in flight per GPU (CUDA-graph slots on separate streams).  Measured on 1xB200 (round 1): "
                          "2 -> 92.6, 3 -> 97.3, 4 -> 111.7, 6 -> 112.8, 8 -> 114.3 pairs/s")
