@@ -165,6 +165,135 @@ select_patches_batched_kernel(const SpJobs jobs, int P, float *__restrict__ patc
                         patches + (size_t)jobs.koff[j] * P * 3, (int)blockIdx.x - jobs.boff[j]);
 }
 
+// ---- hash-grid form of select_patches (large clouds: N >= ~50 k points) --------------------------------------------------
+// The streaming kernel reads the permuted cloud front to back until a key-point has its P hits: fine when a ball holds a
+// few per cent of the cloud (C2: 20 k points), wasteful for a LiDAR-sized cloud (C3: 120 k points, a ball holds < 2 %).
+// Here the cloud is binned into a spatial hash of cubic cells of edge >= radius (classic three-prime hash of the integer
+// cell coordinates, 2^17 buckets: no bounding box needed, aliases only add candidates), and a key-point looks at the 27
+// cells around it only.  The ORDER contract (first P hits in permuted-index order, patch_embedder.py:92-120) does not
+// need a sort: hits set bits in a per-key-point bitmap over the point indices (N / 8 bytes of shared memory), and the
+// bitmap is read back front to back -- counts per thread range, a block scan, then every thread emits the hits of its
+// range at their ordered slots.  Membership is the same exact test d2 < r*r as everywhere, so index rows and patches are
+// bit-identical to the streaming kernel (tests/test_gpu_parity.py::test_select_patches_grid_equals_scan).
+constexpr int HG_BITS = 17, HG_CELLS = 1 << HG_BITS;
+constexpr int HG_THREADS = 128;
+
+__device__ __forceinline__ int hg_coord(float v, float inv_cell) { return (int)floorf(v * inv_cell); }
+__device__ __forceinline__ unsigned hg_hash(int ix, int iy, int iz) {
+    return ((unsigned)ix * 73856093u ^ (unsigned)iy * 19349663u ^ (unsigned)iz * 83492791u) & (unsigned)(HG_CELLS - 1);
+}
+// cell edge = radius * (1 + 1e-3): two points closer than the radius then differ by less than one cell in exact arithmetic
+// with 1e-3 of slack for the fp32 rounding of v * inv_cell (|v| / cell < 2^13 cells keeps that error below 1e-3)
+__device__ __forceinline__ float hg_inv_cell(float r) { return 1.0f / (r * 1.001f); }
+
+__global__ void hg_count_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ d_radius, int *__restrict__ cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float ic = hg_inv_cell(*d_radius);
+    const float4 p = pts4[i];
+    atomicAdd(cnt + hg_hash(hg_coord(p.x, ic), hg_coord(p.y, ic), hg_coord(p.z, ic)), 1);
+}
+
+// exclusive scan of the HG_CELLS bucket counts (one CTA of 1024 threads, 128 consecutive buckets per thread, 16-byte accesses);
+// cursor = start
+__global__ void __launch_bounds__(1024) hg_scan_kernel(const int *__restrict__ cnt, int *__restrict__ start, int *__restrict__ cursor) {
+    __shared__ int sh[33];
+    constexpr int PER4 = HG_CELLS / 1024 / 4;
+    const int t = threadIdx.x;
+    const int4 *c4 = reinterpret_cast<const int4 *>(cnt) + (size_t)t * PER4;
+    int local = 0;
+#pragma unroll 8
+    for (int j = 0; j < PER4; ++j) { const int4 v = c4[j]; local += (v.x + v.y) + (v.z + v.w); }
+    int total;
+    int run = bx_block_exscan(local, sh, &total);
+    int4 *s4 = reinterpret_cast<int4 *>(start) + (size_t)t * PER4, *u4 = reinterpret_cast<int4 *>(cursor) + (size_t)t * PER4;
+#pragma unroll 8
+    for (int j = 0; j < PER4; ++j) {
+        const int4 v = c4[j];
+        int4 o;
+        o.x = run; o.y = o.x + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+        run = o.w + v.w;
+        s4[j] = o;
+        u4[j] = o;
+    }
+    if (t == 1023) start[HG_CELLS] = run;
+}
+
+__global__ void hg_scatter_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ d_radius, int *__restrict__ cursor,
+                                  float4 *__restrict__ sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float ic = hg_inv_cell(*d_radius);
+    const float4 p = pts4[i];
+    const int pos = atomicAdd(cursor + hg_hash(hg_coord(p.x, ic), hg_coord(p.y, ic), hg_coord(p.z, ic)), 1);
+    sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));        // the order inside a bucket does not matter (bitmap)
+}
+
+__global__ void __launch_bounds__(HG_THREADS)
+hg_query_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ kpts, int K, const float *__restrict__ d_radius, int P,
+                const int *__restrict__ start, const float4 *__restrict__ sorted, int *__restrict__ idx, float *__restrict__ patches) {
+    extern __shared__ unsigned hg_bits[];                 // (N + 31) / 32 words
+    __shared__ int sh[33];
+    __shared__ int s_first;
+    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = (N + 31) >> 5;
+    const float r = *d_radius, r2 = r * r, ic = hg_inv_cell(r);
+    const float qx = kpts[3 * (size_t)k], qy = kpts[3 * (size_t)k + 1], qz = kpts[3 * (size_t)k + 2];
+    for (int w = tid; w < W; w += HG_THREADS) hg_bits[w] = 0u;
+    if (tid == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    const int cx = hg_coord(qx, ic), cy = hg_coord(qy, ic), cz = hg_coord(qz, ic);
+    for (int c = warp; c < 27; c += HG_THREADS / 32) {
+        const unsigned h = hg_hash(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1);
+        const int s = start[h], e = start[h + 1];
+        for (int j = s + lane; j < e; j += 32) {
+            const float4 p = sorted[j];
+            if (bx_d2(qx - p.x, qy - p.y, qz - p.z) < r2) {
+                const int i = __float_as_int(p.w);
+                atomicOr(&hg_bits[i >> 5], 1u << (i & 31));
+            }
+        }
+    }
+    __syncthreads();
+    // ordered read-back: thread t owns the contiguous word range [w0, w1)
+    const int per = (W + HG_THREADS - 1) / HG_THREADS, w0 = min(tid * per, W), w1 = min(w0 + per, W);
+    int local = 0;
+    for (int w = w0; w < w1; ++w) local += __popc(hg_bits[w]);
+    int total;
+    int off = bx_block_exscan(local, sh, &total);
+    int *row = idx ? idx + (size_t)k * P : nullptr;
+    float *out = patches + (size_t)k * P * 3;
+    if (local > 0 && off == 0) {                          // the thread that holds the first hit
+        for (int w = w0; w < w1; ++w) if (hg_bits[w]) { s_first = (w << 5) + __ffs(hg_bits[w]) - 1; break; }
+    }
+    for (int w = w0; w < w1 && off < P; ++w) {
+        unsigned m = hg_bits[w];
+        while (m && off < P) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int i = (w << 5) + b;
+            if (row) row[off] = i;
+            const bool centre = (off == P - 1);            // slot P-1 always holds the key-point itself (patch_embedder.py:109)
+            const float4 p = pts4[i];
+            out[3 * off] = centre ? qx : p.x;
+            out[3 * off + 1] = centre ? qy : p.y;
+            out[3 * off + 2] = centre ? qz : p.z;
+            ++off;
+        }
+    }
+    __syncthreads();
+    // padding: ball_query repeats the first hit; the fix-up replaces those slots by the key-point.
+    // No hit at all: index row = 0, slot 0 = point 0 of the permuted cloud, every other slot = key-point.
+    const int cnt = min(total, P);
+    const int first = cnt > 0 ? s_first : 0;
+    for (int s = cnt + tid; s < P; s += HG_THREADS) {
+        if (row) row[s] = first;
+        float x = qx, y = qy, z = qz;
+        if (cnt == 0 && s == 0 && P > 1) { const float4 p0 = pts4[0]; x = p0.x; y = p0.y; z = p0.z; }
+        out[3 * s] = x; out[3 * s + 1] = y; out[3 * s + 2] = z;
+    }
+}
+
 // ---- segmented form of select_patches (alternative, BX_PATCHES=seg): the same ordered "first P hits", fully parallel ------
 // The streaming kernel above is one dependent scan per key-point (early exit included) with three block barriers per 2048
 // points.  Here the scan is cut into independent (key-point, 2048-point segment) tasks:
@@ -477,6 +606,40 @@ BX_API int bx_select_patches_batched(int njobs, const void *const *pts4, const i
     jobs.boff[njobs] = blocks;
     if (blocks == 0) return BX_OK;
     select_patches_batched_kernel<<<blocks, SP_WARPS * 32, 0, bx_stream(stream)>>>(jobs, P, patches);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
+BX_API long long bx_select_patches_grid_workspace_bytes(int N) {
+    return (long long)(3 * HG_CELLS + 8) * 4 + (long long)N * 16;
+}
+
+// Hash-grid form (see above): same contract as bx_select_patches with a device-side radius.  workspace:
+// bx_select_patches_grid_workspace_bytes(N) bytes, 16-byte aligned, contents undefined on entry.
+BX_API int bx_select_patches_grid(const float *pts4, int N, const float *kpts, int K, const float *d_radius, int P, int32_t *idx,
+                                  float *patches, void *workspace, void *stream) {
+    BX_REQUIRE(pts4 && kpts && patches && workspace && d_radius, "bx_select_patches_grid: null pointer");
+    BX_REQUIRE(N >= 1 && K >= 0 && P >= 1, "bx_select_patches_grid: bad sizes N=%d K=%d P=%d", N, K, P);
+    BX_REQUIRE(((reinterpret_cast<uintptr_t>(pts4) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0, "bx_select_patches_grid: pts4 / workspace must be 16-byte aligned");
+    const size_t bitmap = (size_t)((N + 31) / 32) * 4;
+    BX_REQUIRE(bitmap <= 200 * 1024, "bx_select_patches_grid: N=%d exceeds the shared-memory bitmap (1.6 M points)", N);
+    if (K == 0) return BX_OK;
+    cudaStream_t st = bx_stream(stream);
+    float4 *sorted = reinterpret_cast<float4 *>(workspace);
+    int *cnt = reinterpret_cast<int *>(sorted + N);
+    int *start = cnt + HG_CELLS, *cursor = start + HG_CELLS + 4;      // 16-byte aligned arrays (int4 accesses in the scan)
+    BX_CUDA(cudaMemsetAsync(cnt, 0, (size_t)HG_CELLS * 4, st));
+    const float4 *p4 = reinterpret_cast<const float4 *>(pts4);
+    hg_count_kernel<<<(N + 255) / 256, 256, 0, st>>>(p4, N, d_radius, cnt);
+    BX_LAUNCH_CHECK();
+    hg_scan_kernel<<<1, 1024, 0, st>>>(cnt, start, cursor);
+    BX_LAUNCH_CHECK();
+    hg_scatter_kernel<<<(N + 255) / 256, 256, 0, st>>>(p4, N, d_radius, cursor, sorted);
+    BX_LAUNCH_CHECK();
+    static BxPerDevice attr = {};
+    if (bx_needs_attr(attr, bitmap))
+        BX_CUDA(cudaFuncSetAttribute(hg_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    hg_query_kernel<<<K, HG_THREADS, bitmap, st>>>(p4, N, kpts, K, d_radius, P, start, sorted, idx, patches);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

@@ -139,12 +139,17 @@ class MiniSpinNet(nn.Module):
             Rs.append(R_all[o:o + K])
             axes.append(ra_all[o:o + K])
             o += K
-        if one_sel:
+        # small clouds: all jobs through the streaming scan in one launch; LiDAR-sized clouds: the hash-grid form, job by job
+        small = [j for j in range(len(sel)) if sel[j][0].shape[0] < ops.GRID_MIN_POINTS] if one_sel else []
+        if len(small) == len(sel):
             ops.select_patches_batched(sel, P, patches)
         o = 0
-        for (pts4, kpts, des_r), K in zip(sel, Ks):
-            if not one_sel:
-                ops.select_patches(pts4, kpts, des_r, P, patches=patches[o:o + K])
+        for j, ((pts4, kpts, des_r), K) in enumerate(zip(sel, Ks)):
+            if len(small) != len(sel):
+                if one_sel and j not in small:
+                    ops.select_patches_grid(pts4, kpts, des_r, P, patches=patches[o:o + K])
+                else:
+                    ops.select_patches(pts4, kpts, des_r, P, patches=patches[o:o + K])
             if not one_lrf:
                 ops.lrf(patches[o:o + K], des_r, bool(is_aligned_to_global_z), delta=delta[o:o + K], Rt=R_all[o:o + K], ra=ra_all[o:o + K])
             o += K

@@ -23,7 +23,7 @@ SYMBOLS = [
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
     "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab", "bx_concat_matches",
-    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes", "bx_conv_layer_sd_costab", "bx_lrf_batched", "bx_select_patches_batched", "bx_fps_ex", "bx_conv_sd_set_stage_sync",
+    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes", "bx_conv_layer_sd_costab", "bx_lrf_batched", "bx_select_patches_batched", "bx_fps_ex", "bx_conv_sd_set_stage_sync", "bx_select_patches_grid", "bx_select_patches_grid_workspace_bytes",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
@@ -65,6 +65,9 @@ def load_library():
     lib.bx_select_patches_workspace_bytes.argtypes = [c_int, c_int]
     lib.bx_select_patches_workspace_bytes.restype = c_int64
     lib.bx_select_patches_batched.argtypes = [c_int, P, P, P, P, P, c_int, P, P]
+    lib.bx_select_patches_grid.argtypes = [P, c_int, P, c_int, P, c_int, P, P, P, P]
+    lib.bx_select_patches_grid_workspace_bytes.argtypes = [c_int]
+    lib.bx_select_patches_grid_workspace_bytes.restype = c_int64
     lib.bx_ball_query.argtypes = [P, c_int, P, c_int, c_float, c_int, P, P]
     lib.bx_lrf.argtypes = [P, c_int, c_int, c_float, P, c_int, P, P, P, P]
     lib.bx_lrf_batched.argtypes = [P, c_int, c_int, c_float, P, c_int, c_int, P, P, P, P]
@@ -243,6 +246,25 @@ def select_patches(pts4: torch.Tensor, kpts: torch.Tensor, radius, P: int, want_
                                                     _stream()), "bx_select_patches_seg")
     if ev:
         ev[1].record()
+    return patches, idx
+
+
+# clouds of at least this many points gather their patches through the spatial hash grid (bx_select_patches_grid) instead of the
+# streaming scan: a ball then holds so small a part of the cloud that reading the cloud front to back costs more than binning it
+GRID_MIN_POINTS = int(os.environ.get("BX_PATCHES_GRID_MIN", "50000"))
+
+
+def select_patches_grid(pts4: torch.Tensor, kpts: torch.Tensor, radius: torch.Tensor, P: int, want_idx=False, patches=None):
+    """Hash-grid form of select_patches (device-side radius tensor); bit-identical output."""
+    K, N = kpts.shape[0], pts4.shape[0]
+    if patches is None:
+        patches = torch.empty((K, P, 3), dtype=F32, device=pts4.device)
+    idx = torch.empty((K, P), dtype=I32, device=pts4.device) if want_idx else None
+    lib = load_library()
+    ws = torch.empty((int(lib.bx_select_patches_grid_workspace_bytes(N)) + 15) // 16 * 4, dtype=I32, device=pts4.device)
+    with _Span("select_patches", 16.0 * N + 12.0 * K + K * P * (12.0 + (4.0 if want_idx else 0.0))):
+        _check(lib.bx_select_patches_grid(_dp(pts4, F32, "pts4"), N, _dp(kpts, F32, "kpts"), K, _dp(radius, F32, "radius"), P, _dp(idx), _dp(patches, F32, "patches"),
+                                          _dp(ws), _stream()), "bx_select_patches_grid")
     return patches, idx
 
 

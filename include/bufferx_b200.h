@@ -92,6 +92,13 @@ int bx_select_patches_batched(int njobs, const void *const *pts4, const int32_t 
 int bx_select_patches_seg(const float *pts4, int N, const float *kpts, int K, float radius, const float *d_radius, int P,
                           int32_t *idx, float *patches, void *workspace, void *stream);
 long long bx_select_patches_workspace_bytes(int N, int K);
+/* Hash-grid form for large clouds (N >= ~50 k points): the permuted cloud is binned into a spatial hash of cells of edge >=
+ * radius, a key-point tests the 27 cells around it only, hits set bits in a per-key-point bitmap over the point indices that
+ * is read back in index order -- same contract and bit-identical output as bx_select_patches (device-side radius required).
+ * workspace: bx_select_patches_grid_workspace_bytes(N) bytes, 16-byte aligned. */
+int bx_select_patches_grid(const float *pts4, int N, const float *kpts, int K, const float *d_radius, int P, int32_t *idx,
+                           float *patches, void *workspace, void *stream);
+long long bx_select_patches_grid_workspace_bytes(int N);
 
 /* Plain ordered ball query (pointnet2_ops.ball_query; utils/common.py:442): xyz [n,3] packed. */
 int bx_ball_query(const float *xyz, int n, const float *qry, int m, float radius, int nsample, int32_t *idx,

@@ -138,6 +138,27 @@ def test_select_patches_bit_exact(dev, oracle, radius, P):
     assert (pat2.cpu().numpy() == epat).all()
 
 
+@pytest.mark.parametrize("n,K,radius,P", [(60000, 300, 0.35, 512), (60000, 64, 0.02, 64), (131073, 100, 0.6, 512), (9000, 50, 5.0, 128)])
+def test_select_patches_grid_equals_scan(dev, oracle, n, K, radius, P):
+    """bx_select_patches_grid (spatial hash + per-key-point index bitmap) against the streaming scan and, at the small size,
+    the oracle: identical index rows and patches -- dense balls (more than P hits), empty balls, a radius larger than the cloud
+    (every bucket aliased), N not a multiple of 32, negative coordinates."""
+    from bufferx_b200 import ops
+    rng = np.random.default_rng(n + K)
+    pts = (rng.uniform(-3, 3, size=(n, 3)) * [1, 1, 0.3]).astype(np.float32)
+    perm = rng.permutation(n).astype(np.int32)
+    kp = pts[rng.choice(n, K, replace=False)]
+    kp[0] = [40.0, 40.0, 40.0]                                           # a key-point far outside the cloud: no hit at all
+    pts4 = ops.permute_cloud(cu(pts, dev), cu(perm, dev))
+    rad = torch.tensor([radius], dtype=torch.float32, device=dev)
+    pa, ia = ops.select_patches(pts4, cu(kp, dev), rad, P, want_idx=True)
+    pb, ib = ops.select_patches_grid(pts4, cu(kp, dev), rad, P, want_idx=True)
+    assert torch.equal(ia, ib) and torch.equal(pa, pb)
+    if n <= 10000:
+        eidx, epat = oracle.select_patches(pts, perm, kp, radius, P)
+        assert (ib.cpu().numpy() == eidx).all() and (pb.cpu().numpy() == epat).all()
+
+
 def test_select_patches_batched_equals_per_job(dev, oracle):
     """bx_select_patches_batched (all (cloud, scale) jobs of a pair in one launch) against the oracle job by job: different
     clouds, key-point counts (one not a multiple of the 4 key-points of a CTA) and radii, incl. an empty-ball radius."""
