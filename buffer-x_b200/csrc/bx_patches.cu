@@ -186,17 +186,19 @@ __device__ __forceinline__ unsigned hg_hash(int ix, int iy, int iz) {
 // with 1e-3 of slack for the fp32 rounding of v * inv_cell (|v| / cell < 2^13 cells keeps that error below 1e-3)
 __device__ __forceinline__ float hg_inv_cell(float r) { return 1.0f / (r * 1.001f); }
 
-__global__ void hg_count_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ d_radius, int *__restrict__ cnt) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void hg_count_body(const float4 *__restrict__ pts4, int N, const float *__restrict__ d_radius, int *__restrict__ cnt, int i) {
     if (i >= N) return;
     const float ic = hg_inv_cell(*d_radius);
     const float4 p = pts4[i];
     atomicAdd(cnt + hg_hash(hg_coord(p.x, ic), hg_coord(p.y, ic), hg_coord(p.z, ic)), 1);
 }
+__global__ void hg_count_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ d_radius, int *__restrict__ cnt) {
+    hg_count_body(pts4, N, d_radius, cnt, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
 // exclusive scan of the HG_CELLS bucket counts (one CTA of 1024 threads, 128 consecutive buckets per thread, 16-byte accesses);
 // cursor = start
-__global__ void __launch_bounds__(1024) hg_scan_kernel(const int *__restrict__ cnt, int *__restrict__ start, int *__restrict__ cursor) {
+__device__ __forceinline__ void hg_scan_body(const int *__restrict__ cnt, int *__restrict__ start, int *__restrict__ cursor) {
     __shared__ int sh[33];
     constexpr int PER4 = HG_CELLS / 1024 / 4;
     const int t = threadIdx.x;
@@ -218,24 +220,28 @@ __global__ void __launch_bounds__(1024) hg_scan_kernel(const int *__restrict__ c
     }
     if (t == 1023) start[HG_CELLS] = run;
 }
+__global__ void __launch_bounds__(1024) hg_scan_kernel(const int *__restrict__ cnt, int *__restrict__ start, int *__restrict__ cursor) { hg_scan_body(cnt, start, cursor); }
 
-__global__ void hg_scatter_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ d_radius, int *__restrict__ cursor,
-                                  float4 *__restrict__ sorted) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void hg_scatter_body(const float4 *__restrict__ pts4, int N, const float *__restrict__ d_radius, int *__restrict__ cursor,
+                                                float4 *__restrict__ sorted, int i) {
     if (i >= N) return;
     const float ic = hg_inv_cell(*d_radius);
     const float4 p = pts4[i];
     const int pos = atomicAdd(cursor + hg_hash(hg_coord(p.x, ic), hg_coord(p.y, ic), hg_coord(p.z, ic)), 1);
     sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));        // the order inside a bucket does not matter (bitmap)
 }
+__global__ void hg_scatter_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ d_radius, int *__restrict__ cursor,
+                                  float4 *__restrict__ sorted) {
+    hg_scatter_body(pts4, N, d_radius, cursor, sorted, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
-__global__ void __launch_bounds__(HG_THREADS)
-hg_query_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ kpts, int K, const float *__restrict__ d_radius, int P,
-                const int *__restrict__ start, const float4 *__restrict__ sorted, int *__restrict__ idx, float *__restrict__ patches) {
+__device__ __forceinline__ void hg_query_body(const float4 *__restrict__ pts4, int N, const float *__restrict__ kpts, const float *__restrict__ d_radius, int P,
+                                              const int *__restrict__ start, const float4 *__restrict__ sorted, int *__restrict__ idx,
+                                              float *__restrict__ patches, int k) {
     extern __shared__ unsigned hg_bits[];                 // (N + 31) / 32 words
     __shared__ int sh[33];
     __shared__ int s_first;
-    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (N + 31) >> 5;
     const float r = *d_radius, r2 = r * r, ic = hg_inv_cell(r);
     const float qx = kpts[3 * (size_t)k], qy = kpts[3 * (size_t)k + 1], qz = kpts[3 * (size_t)k + 2];
@@ -292,6 +298,41 @@ hg_query_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict_
         if (cnt == 0 && s == 0 && P > 1) { const float4 p0 = pts4[0]; x = p0.x; y = p0.y; z = p0.z; }
         out[3 * s] = x; out[3 * s + 1] = y; out[3 * s + 2] = z;
     }
+}
+
+__global__ void __launch_bounds__(HG_THREADS)
+hg_query_kernel(const float4 *__restrict__ pts4, int N, const float *__restrict__ kpts, int K, const float *__restrict__ d_radius, int P,
+                const int *__restrict__ start, const float4 *__restrict__ sorted, int *__restrict__ idx, float *__restrict__ patches) {
+    hg_query_body(pts4, N, kpts, d_radius, P, start, sorted, idx, patches, blockIdx.x);
+}
+
+// all (cloud, scale) jobs of a pair: one launch per phase (blockIdx.y = job for the point-parallel phases)
+struct HgJobs {
+    const float4 *pts4[SP_MAXJOBS];
+    const float *kpts[SP_MAXJOBS];
+    const float *d_radius[SP_MAXJOBS];
+    float4 *sorted[SP_MAXJOBS];
+    int *cnt[SP_MAXJOBS];                 // cnt, start = cnt + HG_CELLS, cursor = start + HG_CELLS + 4
+    int N[SP_MAXJOBS], koff[SP_MAXJOBS + 1];
+    int njobs;
+};
+__global__ void hg_count_batched_kernel(const HgJobs J) {
+    const int j = blockIdx.y;
+    hg_count_body(J.pts4[j], J.N[j], J.d_radius[j], J.cnt[j], blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(1024) hg_scan_batched_kernel(const HgJobs J) {
+    int *cnt = J.cnt[blockIdx.x];
+    hg_scan_body(cnt, cnt + HG_CELLS, cnt + 2 * HG_CELLS + 4);
+}
+__global__ void hg_scatter_batched_kernel(const HgJobs J) {
+    const int j = blockIdx.y;
+    hg_scatter_body(J.pts4[j], J.N[j], J.d_radius[j], J.cnt[j] + 2 * HG_CELLS + 4, J.sorted[j], blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(HG_THREADS) hg_query_batched_kernel(const HgJobs J, int P, float *__restrict__ patches) {
+    int j = 0;
+    while (j + 1 < J.njobs && (int)blockIdx.x >= J.koff[j + 1]) ++j;
+    hg_query_body(J.pts4[j], J.N[j], J.kpts[j], J.d_radius[j], P, J.cnt[j] + HG_CELLS, J.sorted[j], nullptr,
+                  patches + (size_t)J.koff[j] * P * 3, (int)blockIdx.x - J.koff[j]);
 }
 
 // ---- segmented form of select_patches (alternative, BX_PATCHES=seg): the same ordered "first P hits", fully parallel ------
@@ -611,7 +652,7 @@ BX_API int bx_select_patches_batched(int njobs, const void *const *pts4, const i
 }
 
 BX_API long long bx_select_patches_grid_workspace_bytes(int N) {
-    return (long long)(3 * HG_CELLS + 8) * 4 + (long long)N * 16;
+    return (long long)(3 * HG_CELLS + 8) * 4 + (long long)N * 16;      // a multiple of 16
 }
 
 // Hash-grid form (see above): same contract as bx_select_patches with a device-side radius.  workspace:
@@ -640,6 +681,52 @@ BX_API int bx_select_patches_grid(const float *pts4, int N, const float *kpts, i
     if (bx_needs_attr(attr, bitmap))
         BX_CUDA(cudaFuncSetAttribute(hg_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     hg_query_kernel<<<K, HG_THREADS, bitmap, st>>>(p4, N, kpts, K, d_radius, P, start, sorted, idx, patches);
+    BX_LAUNCH_CHECK();
+    return BX_OK;
+}
+
+// All (cloud, scale) jobs of a pair through the hash grid: one launch per phase.  workspace: the sum over the jobs of
+// bx_select_patches_grid_workspace_bytes(N[j]) bytes (16-byte aligned); patches: job after job like bx_select_patches_batched.
+BX_API int bx_select_patches_grid_batched(int njobs, const void *const *pts4, const int32_t *N, const void *const *kpts, const int32_t *K,
+                                          const void *const *d_radius, int P, float *patches, void *workspace, void *stream) {
+    BX_REQUIRE(pts4 && N && kpts && K && d_radius && patches && workspace, "bx_select_patches_grid_batched: null pointer");
+    BX_REQUIRE(njobs >= 1 && njobs <= SP_MAXJOBS && P >= 1, "bx_select_patches_grid_batched: njobs=%d out of range [1,%d]", njobs, SP_MAXJOBS);
+    BX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "bx_select_patches_grid_batched: workspace must be 16-byte aligned");
+    HgJobs J = {};
+    J.njobs = njobs;
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    int koff = 0, maxN = 0;
+    for (int j = 0; j < njobs; ++j) {
+        BX_REQUIRE(pts4[j] && kpts[j] && d_radius[j] && N[j] >= 1 && K[j] >= 0, "bx_select_patches_grid_batched: bad job %d", j);
+        BX_REQUIRE((reinterpret_cast<uintptr_t>(pts4[j]) & 15) == 0, "bx_select_patches_grid_batched: pts4 must be 16-byte aligned");
+        J.pts4[j] = reinterpret_cast<const float4 *>(pts4[j]);
+        J.kpts[j] = reinterpret_cast<const float *>(kpts[j]);
+        J.d_radius[j] = reinterpret_cast<const float *>(d_radius[j]);
+        J.N[j] = N[j];
+        J.sorted[j] = reinterpret_cast<float4 *>(ws);
+        J.cnt[j] = reinterpret_cast<int *>(J.sorted[j] + N[j]);
+        ws += bx_select_patches_grid_workspace_bytes(N[j]);
+        J.koff[j] = koff;
+        koff += K[j];
+        if (N[j] > maxN) maxN = N[j];
+    }
+    J.koff[njobs] = koff;
+    const size_t bitmap = (size_t)((maxN + 31) / 32) * 4;
+    BX_REQUIRE(bitmap <= 200 * 1024, "bx_select_patches_grid_batched: N=%d exceeds the shared-memory bitmap (1.6 M points)", maxN);
+    if (koff == 0) return BX_OK;
+    cudaStream_t st = bx_stream(stream);
+    for (int j = 0; j < njobs; ++j) BX_CUDA(cudaMemsetAsync(J.cnt[j], 0, (size_t)HG_CELLS * 4, st));
+    const dim3 pg((unsigned)((maxN + 255) / 256), (unsigned)njobs);
+    hg_count_batched_kernel<<<pg, 256, 0, st>>>(J);
+    BX_LAUNCH_CHECK();
+    hg_scan_batched_kernel<<<njobs, 1024, 0, st>>>(J);
+    BX_LAUNCH_CHECK();
+    hg_scatter_batched_kernel<<<pg, 256, 0, st>>>(J);
+    BX_LAUNCH_CHECK();
+    static BxPerDevice attr = {};
+    if (bx_needs_attr(attr, bitmap))
+        BX_CUDA(cudaFuncSetAttribute(hg_query_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    hg_query_batched_kernel<<<koff, HG_THREADS, bitmap, st>>>(J, P, patches);
     BX_LAUNCH_CHECK();
     return BX_OK;
 }

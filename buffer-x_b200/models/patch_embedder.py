@@ -139,14 +139,15 @@ class MiniSpinNet(nn.Module):
             Rs.append(R_all[o:o + K])
             axes.append(ra_all[o:o + K])
             o += K
-        # small clouds: all jobs through the streaming scan in one launch; LiDAR-sized clouds: the hash-grid form, job by job
-        small = [j for j in range(len(sel)) if sel[j][0].shape[0] < ops.GRID_MIN_POINTS] if one_sel else []
-        if len(small) == len(sel):
-            ops.select_patches_batched(sel, P, patches)
+        # small clouds: all jobs through the streaming scan in one launch; larger ones: all jobs through the hash grid, one launch
+        # per phase; a mix of both (C5: 60 k vs 30 k points is above the threshold on both sides; 5 k vs 20 k would not be): job by job
+        big = [pts4.shape[0] >= ops.GRID_MIN_POINTS for (pts4, _, _) in sel]
+        if one_sel and (all(big) or not any(big)):
+            ops.select_patches_batched(sel, P, patches, grid=all(big))
         o = 0
         for j, ((pts4, kpts, des_r), K) in enumerate(zip(sel, Ks)):
-            if len(small) != len(sel):
-                if one_sel and j not in small:
+            if not (one_sel and (all(big) or not any(big))):
+                if big[j] and isinstance(des_r, torch.Tensor):
                     ops.select_patches_grid(pts4, kpts, des_r, P, patches=patches[o:o + K])
                 else:
                     ops.select_patches(pts4, kpts, des_r, P, patches=patches[o:o + K])

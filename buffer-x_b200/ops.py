@@ -23,7 +23,7 @@ SYMBOLS = [
     "bx_pool_desc", "bx_mutual_nn",
     "bx_hypotheses", "bx_consensus", "bx_ransac_workspace_bytes", "bx_ransac", "bx_refine", "bx_conv_tc_set_segment_stages",
     "bx_radius_neighbors", "bx_grid_subsample", "bx_costvol_ab", "bx_concat_matches",
-    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes", "bx_conv_layer_sd_costab", "bx_lrf_batched", "bx_select_patches_batched", "bx_fps_ex", "bx_conv_sd_set_stage_sync", "bx_select_patches_grid", "bx_select_patches_grid_workspace_bytes",
+    "bx_pca_analysis", "bx_project_range", "bx_voxel_down_sample", "bx_conv_layer_sd", "bx_conv_sd_rows", "bx_spt_pnt_sd", "bx_fps_set_sync_mode", "bx_select_patches_seg", "bx_select_patches_workspace_bytes", "bx_conv_layer_sd_costab", "bx_lrf_batched", "bx_select_patches_batched", "bx_fps_ex", "bx_conv_sd_set_stage_sync", "bx_select_patches_grid", "bx_select_patches_grid_workspace_bytes", "bx_select_patches_grid_batched",
 ]
 
 GEOM_CYL3D, GEOM_CYL2D, GEOM_VALID3D, GEOM_COSTVOL, GEOM_COSTAB = 0, 1, 2, 3, 4
@@ -67,6 +67,7 @@ def load_library():
     lib.bx_select_patches_batched.argtypes = [c_int, P, P, P, P, P, c_int, P, P]
     lib.bx_select_patches_grid.argtypes = [P, c_int, P, c_int, P, c_int, P, P, P, P]
     lib.bx_select_patches_grid_workspace_bytes.argtypes = [c_int]
+    lib.bx_select_patches_grid_batched.argtypes = [c_int, P, P, P, P, P, c_int, P, P, P]
     lib.bx_select_patches_grid_workspace_bytes.restype = c_int64
     lib.bx_ball_query.argtypes = [P, c_int, P, c_int, c_float, c_int, P, P]
     lib.bx_lrf.argtypes = [P, c_int, c_int, c_float, P, c_int, P, P, P, P]
@@ -251,7 +252,8 @@ def select_patches(pts4: torch.Tensor, kpts: torch.Tensor, radius, P: int, want_
 
 # clouds of at least this many points gather their patches through the spatial hash grid (bx_select_patches_grid) instead of the
 # streaming scan: a ball then holds so small a part of the cloud that reading the cloud front to back costs more than binning it
-GRID_MIN_POINTS = int(os.environ.get("BX_PATCHES_GRID_MIN", "50000"))
+# (measured: C3 2 x 120 k points 102 -> 120 pairs/s; C2 2 x 20 k points 171.8 -> 176.5 pairs/s with six pairs in flight)
+GRID_MIN_POINTS = int(os.environ.get("BX_PATCHES_GRID_MIN", "12000"))
 
 
 def select_patches_grid(pts4: torch.Tensor, kpts: torch.Tensor, radius: torch.Tensor, P: int, want_idx=False, patches=None):
@@ -268,8 +270,9 @@ def select_patches_grid(pts4: torch.Tensor, kpts: torch.Tensor, radius: torch.Te
     return patches, idx
 
 
-def select_patches_batched(jobs, P: int, patches: torch.Tensor):
-    """jobs: [(pts4 [N,4], kpts [K,3], radius 1-element CUDA tensor)]; patches [sum K, P, 3] is filled job after job by ONE launch."""
+def select_patches_batched(jobs, P: int, patches: torch.Tensor, grid=False):
+    """jobs: [(pts4 [N,4], kpts [K,3], radius 1-element CUDA tensor)]; patches [sum K, P, 3] is filled job after job by ONE launch
+    (grid=True: the hash-grid form, one launch per phase)."""
     import ctypes
     n = len(jobs)
     VP, I = ctypes.c_void_p * n, ctypes.c_int32 * n
@@ -278,8 +281,15 @@ def select_patches_batched(jobs, P: int, patches: torch.Tensor):
     rad = VP(*[_dp(j[2], F32, "radius") for j in jobs])
     Ns, Ks = I(*[int(j[0].shape[0]) for j in jobs]), I(*[int(j[1].shape[0]) for j in jobs])
     assert patches.shape[0] == sum(Ks) and patches.is_contiguous()
+    lib = load_library()
+    ws = None
+    if grid:
+        ws = torch.empty(sum(int(lib.bx_select_patches_grid_workspace_bytes(int(a))) for a in Ns) // 4, dtype=I32, device=patches.device)
     with _Span("select_patches", sum(16.0 * a + 12.0 * b + b * P * 12.0 for a, b in zip(Ns, Ks))):
-        _check(load_library().bx_select_patches_batched(n, pts, Ns, kps, Ks, rad, P, _dp(patches, F32, "patches"), _stream()), "bx_select_patches_batched")
+        if grid:
+            _check(lib.bx_select_patches_grid_batched(n, pts, Ns, kps, Ks, rad, P, _dp(patches, F32, "patches"), _dp(ws), _stream()), "bx_select_patches_grid_batched")
+        else:
+            _check(lib.bx_select_patches_batched(n, pts, Ns, kps, Ks, rad, P, _dp(patches, F32, "patches"), _stream()), "bx_select_patches_batched")
     return patches
 
 

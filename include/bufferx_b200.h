@@ -99,6 +99,10 @@ long long bx_select_patches_workspace_bytes(int N, int K);
 int bx_select_patches_grid(const float *pts4, int N, const float *kpts, int K, const float *d_radius, int P, int32_t *idx,
                            float *patches, void *workspace, void *stream);
 long long bx_select_patches_grid_workspace_bytes(int N);
+/* All (cloud, scale) jobs of a pair through the hash grid, one launch per phase (arguments like bx_select_patches_batched;
+ * workspace = the sum of bx_select_patches_grid_workspace_bytes(N[j]) bytes). */
+int bx_select_patches_grid_batched(int njobs, const void *const *pts4, const int32_t *N, const void *const *kpts, const int32_t *K,
+                                   const void *const *d_radius, int P, float *patches, void *workspace, void *stream);
 
 /* Plain ordered ball query (pointnet2_ops.ball_query; utils/common.py:442): xyz [n,3] packed. */
 int bx_ball_query(const float *xyz, int n, const float *qry, int m, float radius, int nsample, int32_t *idx,

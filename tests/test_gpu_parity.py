@@ -171,9 +171,10 @@ def test_select_patches_batched_equals_per_job(dev, oracle):
         kp = pts[oracle.fps(pts, K)]
         jobs.append((ops.permute_cloud(cu(pts, dev), cu(perm, dev)), cu(kp, dev), torch.tensor([radius], dtype=torch.float32, device=dev)))
         expect.append(oracle.select_patches(pts, perm, kp, radius, P)[1])
-    out = torch.full((sum(j[1].shape[0] for j in jobs), P, 3), float("nan"), dtype=torch.float32, device=dev)
-    ops.select_patches_batched(jobs, P, out)
-    assert (out.cpu().numpy() == np.concatenate(expect)).all()
+    for grid in (False, True):          # streaming scan / hash grid, all jobs in one launch (per phase)
+        out = torch.full((sum(j[1].shape[0] for j in jobs), P, 3), float("nan"), dtype=torch.float32, device=dev)
+        ops.select_patches_batched(jobs, P, out, grid=grid)
+        assert (out.cpu().numpy() == np.concatenate(expect)).all(), f"grid={grid}"
 
 
 def test_ball_query_bit_exact(dev, oracle):
