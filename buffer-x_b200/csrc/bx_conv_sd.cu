@@ -26,15 +26,21 @@
 //               the kernel is bound by the tensor core's shared-memory operand reads), then al * bh into the cross columns.
 //               |x| >= 65504 cannot be represented: the loader raises *flag and the host re-runs the layer on the TF32 kernel.
 //
-// Persistent warp-specialised CTA, one per SM:
-//   4 loader warps    fill the A ring (NA chunk slots): fp32 channel-blocked activations [n][C/4][pos][4] -> fp16 hi/lo,
-//                     padding rows / wrap columns materialised by index arithmetic; fence.proxy.async + mbarrier.
-//   1 weight warp     streams the host-arranged weight image [chunk][tap][kcore][split][n][8 x fp16] through the B ring with
-//                     cp.async.bulk + mbarrier transaction counts (SB stages per copy).
-//   1 MMA warp        per (chunk, tap): 2 x tcgen05.mma.kind::f16 (SS form, M = 128, N = 2*NT and NT, K = 16); tcgen05.commit to the
-//                     slot / segment / tile barriers.  No thread ever touches an activation between shared memory and the MMA.
-//   4*ECS epilogue warps   drain finished segments (tcgen05.ld) into running sums, then bias (+ReLU) and 16-byte
-//                     channel-blocked stores of the valid rows -- while the tensor core already works on the next tile.
+// Persistent warp-specialised CTA, one per SM (presplit in and out -- the layer-to-layer case -- 15 warps):
+//   8 epilogue warps  drain finished segments (tcgen05.ld) into fp32 running sums that start from the bias; a finished tile is
+//                     parked as fp32 in a shared-memory staging buffer and the warps go back to draining.
+//   1 A producer      one thread: a chunk = four 2816-byte bulk copies of the previous layer's presplit image (ring of NA chunks).
+//                     (fp32-input variant: 4 loader warps convert channel-blocked activations to fp16 hi/lo instead.)
+//   4 storer warps    staged tile -> ReLU, fp16 hi/lo split, global stores of values, wrap-column copies and zero rows (the
+//                     next layer's operand image) -- off the epilogue warps' critical path.
+//   1 MMA warp        per (chunk, tap): 2 (3 for Cout 128) x tcgen05.mma.kind::f16 (SS form, M = 128, K = 16); probes the barrier the
+//                     next step needs (mbarrier.test_wait) before issuing the current step's MMAs; tcgen05.commit to the slot /
+//                     segment / tile barriers.  No thread ever touches an activation between shared memory and the MMA.
+//   1 weight thread   the host-arranged weight image [chunk][tap][kcore][split][n][8 x fp16]: loaded ONCE and kept resident when
+//                     it fits (Cin * Cout <= 64 * 64), else streamed with cp.async.bulk + mbarrier transaction counts (whole-chunk
+//                     stages for Cout <= 64, three-tap stages for Cout 128).
+// What paces the kernel was measured, not assumed: tools/umma_probe.cu (instruction rates of the SS / TS / pair forms, drain and
+// copy rates) and the -DBX_TC_TRACE build of this file (cycle split of the MMA warp and an epilogue warp); DESIGN.md section 5.1.
 #include <cuda_fp16.h>
 
 #include "bx_common.cuh"
