@@ -324,6 +324,50 @@ __global__ void __launch_bounds__(1024) hg_scan_batched_kernel(const HgJobs J) {
     int *cnt = J.cnt[blockIdx.x];
     hg_scan_body(cnt, cnt + HG_CELLS, cnt + 2 * HG_CELLS + 4);
 }
+// The same scan spread over HG_CHUNKS CTAs per job (one CTA per job scanning 131072 buckets is a 80 us latency chain on six
+// SMs -- as long as the query itself): chunk totals first, then every chunk scans its 4096 buckets from the sum of the
+// totals before it.  Totals live behind the cursor array (workspace ints [3 * HG_CELLS + 8, + HG_CHUNKS)).
+constexpr int HG_CHUNK = 4096, HG_CHUNKS = HG_CELLS / HG_CHUNK, HG_SCAN_THREADS = 256;
+__global__ void __launch_bounds__(HG_SCAN_THREADS) hg_chunksum_batched_kernel(const HgJobs J) {
+    __shared__ int sh[33];
+    const int *cnt = J.cnt[blockIdx.y] + (size_t)blockIdx.x * HG_CHUNK;
+    const int4 *c4 = reinterpret_cast<const int4 *>(cnt) + threadIdx.x * (HG_CHUNK / HG_SCAN_THREADS / 4);
+    int local = 0;
+#pragma unroll
+    for (int j = 0; j < HG_CHUNK / HG_SCAN_THREADS / 4; ++j) { const int4 v = c4[j]; local += (v.x + v.y) + (v.z + v.w); }
+    int total;
+    bx_block_exscan(local, sh, &total);
+    if (threadIdx.x == 0) J.cnt[blockIdx.y][3 * HG_CELLS + 8 + blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(HG_SCAN_THREADS) hg_chunkscan_batched_kernel(const HgJobs J) {
+    __shared__ int sh[33];
+    int *base = J.cnt[blockIdx.y];
+    const int chunk = blockIdx.x;
+    // sum of the totals of the chunks before this one (HG_CHUNKS = 32: one warp-wide sum, computed by every warp)
+    const int lane = threadIdx.x & 31;
+    int before = (lane < chunk) ? base[3 * HG_CELLS + 8 + lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(BX_FULL, before, o);
+    constexpr int PER4 = HG_CHUNK / HG_SCAN_THREADS / 4;
+    const size_t off4 = ((size_t)chunk * HG_CHUNK) / 4 + (size_t)threadIdx.x * PER4;
+    const int4 *c4 = reinterpret_cast<const int4 *>(base) + off4;
+    int4 v[PER4];
+    int local = 0;
+#pragma unroll
+    for (int j = 0; j < PER4; ++j) { v[j] = c4[j]; local += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
+    int total;
+    int run = before + bx_block_exscan(local, sh, &total);
+    int4 *s4 = reinterpret_cast<int4 *>(base + HG_CELLS) + off4, *u4 = reinterpret_cast<int4 *>(base + 2 * HG_CELLS + 4) + off4;
+#pragma unroll
+    for (int j = 0; j < PER4; ++j) {
+        int4 o;
+        o.x = run; o.y = o.x + v[j].x; o.z = o.y + v[j].y; o.w = o.z + v[j].z;
+        run = o.w + v[j].w;
+        s4[j] = o;
+        u4[j] = o;
+    }
+    if (chunk == HG_CHUNKS - 1 && threadIdx.x == HG_SCAN_THREADS - 1) base[HG_CELLS + HG_CELLS] = run;      // start[HG_CELLS] = N
+}
 __global__ void hg_scatter_batched_kernel(const HgJobs J) {
     const int j = blockIdx.y;
     hg_scatter_body(J.pts4[j], J.N[j], J.d_radius[j], J.cnt[j] + 2 * HG_CELLS + 4, J.sorted[j], blockIdx.x * blockDim.x + threadIdx.x);
@@ -652,7 +696,7 @@ BX_API int bx_select_patches_batched(int njobs, const void *const *pts4, const i
 }
 
 BX_API long long bx_select_patches_grid_workspace_bytes(int N) {
-    return (long long)(3 * HG_CELLS + 8) * 4 + (long long)N * 16;      // a multiple of 16
+    return (long long)(3 * HG_CELLS + 8 + 32) * 4 + (long long)N * 16;      // sorted points, counts, starts, cursors, chunk totals; a multiple of 16
 }
 
 // Hash-grid form (see above): same contract as bx_select_patches with a device-side radius.  workspace:
@@ -719,7 +763,10 @@ BX_API int bx_select_patches_grid_batched(int njobs, const void *const *pts4, co
     const dim3 pg((unsigned)((maxN + 255) / 256), (unsigned)njobs);
     hg_count_batched_kernel<<<pg, 256, 0, st>>>(J);
     BX_LAUNCH_CHECK();
-    hg_scan_batched_kernel<<<njobs, 1024, 0, st>>>(J);
+    static_assert(HG_CHUNKS == 32, "the chunk scan sums the earlier chunk totals with one warp");
+    hg_chunksum_batched_kernel<<<dim3(HG_CHUNKS, (unsigned)njobs), HG_SCAN_THREADS, 0, st>>>(J);
+    BX_LAUNCH_CHECK();
+    hg_chunkscan_batched_kernel<<<dim3(HG_CHUNKS, (unsigned)njobs), HG_SCAN_THREADS, 0, st>>>(J);
     BX_LAUNCH_CHECK();
     hg_scatter_batched_kernel<<<pg, 256, 0, st>>>(J);
     BX_LAUNCH_CHECK();
