@@ -47,6 +47,10 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
+    # objects are only reusable for the flag set they were compiled with (a trace build must not leak into a normal one)
+    stamp, flags = os.path.join(OBJ, "flags.txt"), " ".join(ARCH + COMMON)
+    if not os.path.exists(stamp) or open(stamp).read() != flags:
+        force = True
     headers = [os.path.join(HERE, "bx_common.cuh"), os.path.join(PKG, "..", "include", "bufferx_b200.h"),
                os.path.abspath(__file__)]
     headers += [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
@@ -65,6 +69,8 @@ def build(force=False, verbose=False):
         for log in ex.map(run, jobs):
             if verbose and log:
                 print(log)
+    with open(stamp, "w") as f:
+        f.write(flags)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in EXACT + FAST]
     if force or jobs or _stale(OUT, objs):
         run([_nvcc()] + ARCH + ["-shared", "-o", OUT] + objs)
